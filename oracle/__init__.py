@@ -1,0 +1,163 @@
+"""CPU oracle for the pytorchltr loss / metric hot path -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of ``oracle/ltr_oracle.c`` (a plain-C restatement of the
+reference's algorithm, each function citing the reference file:line it follows).
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this module; nothing under
+``pytorchltr_b200/`` does, and the product path never falls back to it.
+
+Parity status: pinned against the reference's known-answer tests and against
+fixtures generated from the unmodified reference (``tests/golden``), except
+``listnet`` which has no reference counterpart ("parity unpinned").
+
+All entry points take numpy arrays (``scores`` float32 ``(B, L)``, ``relevance``
+int64 ``(B, L)``, ``n`` int64 ``(B,)``) and return float64 numpy arrays.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libltr_oracle.so")
+
+ADDITIVE_MODES = {"hinge": 0, "dcg_hinge": 1, "logistic": 2}
+LAMBDA_MODES = {"arp1": 0, "arp2": 1, "ndcg1": 2, "ndcg2": 3}
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compiles ``ltr_oracle.c`` with gcc (``make -C oracle``)."""
+    src = os.path.join(_HERE, "ltr_oracle.c")
+    if (force or not os.path.exists(_SO)
+            or os.path.getmtime(_SO) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libltr_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _f32(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+
+
+def _i64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int64))
+
+
+def _prep(scores, relevance, n):
+    s = _f32(scores)
+    y = _i64(relevance)
+    if s.ndim == 3:
+        s = s.reshape(s.shape[0], s.shape[1])
+    if y.ndim == 3:
+        y = y.reshape(y.shape[0], y.shape[1])
+    nn = _i64(n)
+    assert s.ndim == 2 and s.shape == y.shape and nn.shape == (s.shape[0],)
+    return s, y, nn
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def set_threads(t: int):
+    lib().ltr_oracle_set_threads(ctypes.c_int(int(t)))
+
+
+def max_threads() -> int:
+    return int(lib().ltr_oracle_max_threads())
+
+
+def pairwise_additive(mode, scores, relevance, n, sigma=1.0, f32=False, want_grad=True):
+    """-> (loss (B,), grad (B, L) | None); reference: loss/pairwise_additive.py:51-163."""
+    s, y, nn = _prep(scores, relevance, n)
+    B, L = s.shape
+    loss = np.zeros(B, dtype=np.float64)
+    grad = np.zeros((B, L), dtype=np.float64) if want_grad else None
+    rc = lib().ltr_oracle_pairwise_additive(
+        ctypes.c_int(ADDITIVE_MODES[mode]), ctypes.c_int(int(f32)), _p(s), _p(y), _p(nn),
+        ctypes.c_int(B), ctypes.c_int(L), ctypes.c_double(sigma), _p(loss), _p(grad))
+    assert rc == 0
+    return loss, grad
+
+
+def lambda_loss(mode, scores, relevance, n, sigma=1.0, want_grad=True, want_ranking=False):
+    """-> (loss, grad | None[, ranking]); reference: loss/pairwise_lambda.py:50-241."""
+    s, y, nn = _prep(scores, relevance, n)
+    B, L = s.shape
+    loss = np.zeros(B, dtype=np.float64)
+    grad = np.zeros((B, L), dtype=np.float64) if want_grad else None
+    ranking = np.zeros((B, L), dtype=np.int64) if want_ranking else None
+    rc = lib().ltr_oracle_lambda(
+        ctypes.c_int(LAMBDA_MODES[mode]), ctypes.c_int(0), _p(s), _p(y), _p(nn),
+        ctypes.c_int(B), ctypes.c_int(L), ctypes.c_double(sigma), _p(loss), _p(grad),
+        _p(ranking))
+    assert rc == 0
+    if want_ranking:
+        return loss, grad, ranking
+    return loss, grad
+
+
+def listnet(scores, relevance, n, want_grad=True):
+    """-> (loss, grad | None).  No reference counterpart: parity unpinned."""
+    s, y, nn = _prep(scores, relevance, n)
+    B, L = s.shape
+    loss = np.zeros(B, dtype=np.float64)
+    grad = np.zeros((B, L), dtype=np.float64) if want_grad else None
+    rc = lib().ltr_oracle_listnet(_p(s), _p(y), _p(nn), ctypes.c_int(B), ctypes.c_int(L),
+                                  _p(loss), _p(grad))
+    assert rc == 0
+    return loss, grad
+
+
+def rank_by_score(scores, n):
+    """-> ranking (B, L) int64; reference: utils/tensor_operations.py:48-64."""
+    s = _f32(scores)
+    if s.ndim == 3:
+        s = s.reshape(s.shape[0], s.shape[1])
+    nn = _i64(n)
+    B, L = s.shape
+    ranking = np.zeros((B, L), dtype=np.int64)
+    rc = lib().ltr_oracle_rank_by_score(_p(s), _p(nn), ctypes.c_int(B), ctypes.c_int(L),
+                                        _p(ranking))
+    assert rc == 0
+    return ranking
+
+
+def dcg(scores, relevance, n, k=None, exp=True, normalized=False):
+    """-> (B,) if k else (B, L); reference: evaluation/dcg.py:41-99 (ndcg: :8-38)."""
+    s, y, nn = _prep(scores, relevance, n)
+    B, L = s.shape
+    if k is not None and k <= 0:
+        raise IndexError("k must be positive")
+    out = np.zeros(B if k is not None else (B, L), dtype=np.float64)
+    rc = lib().ltr_oracle_dcg(_p(s), _p(y), _p(nn), ctypes.c_int(B), ctypes.c_int(L),
+                              ctypes.c_int(0 if k is None else int(k)), ctypes.c_int(int(exp)),
+                              ctypes.c_int(int(normalized)), _p(out))
+    assert rc == 0
+    return out
+
+
+def ndcg(scores, relevance, n, k=None, exp=True):
+    return dcg(scores, relevance, n, k=k, exp=exp, normalized=True)
+
+
+def arp(scores, relevance, n):
+    """-> (B,); reference: evaluation/arp.py:7-42."""
+    s, y, nn = _prep(scores, relevance, n)
+    B, L = s.shape
+    out = np.zeros(B, dtype=np.float64)
+    rc = lib().ltr_oracle_arp(_p(s), _p(y), _p(nn), ctypes.c_int(B), ctypes.c_int(L), _p(out))
+    assert rc == 0
+    return out
