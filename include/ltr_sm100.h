@@ -1,0 +1,145 @@
+/*
+ * ltr_sm100.h -- C ABI of libltr_sm100.so: the pytorchltr loss / metric hot path
+ * `(scores, relevance, n) -> per-query loss | metric` as hand-written CUDA for
+ * NVIDIA B200 (sm_100a).
+ *
+ * The reference (rjagerman/pytorchltr) is pure Python on this path; it has no FFI.
+ * Each entry point below therefore replaces one Python-level interface of the
+ * reference (cited file:line, relative to the reference root) and is what a ctypes
+ * binding inside those modules would call -- see INTEGRATION.md for the stubs.
+ *
+ * Common contract
+ *   - Padded batches, row-major and contiguous: scores float32 [B*L] (ld = L),
+ *     relevance int64 or int32 [B*L] (`rel_bytes` = 8 or 4), n int64 or int32 [B]
+ *     (`n_bytes` = 8 or 4).  Documents j >= n[b] are padding.  n is clamped to [0, L].
+ *   - Device entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t,
+ *     NULL = legacy default stream), never synchronise, never allocate and keep no
+ *     pointer after returning: they are CUDA-graph capturable and re-entrant.
+ *   - `*_host` entry points take HOST pointers (pinned memory makes the copies
+ *     asynchronous) plus a caller-owned device workspace; they enqueue
+ *     H2D copies -> kernel -> D2H copies on `stream` and return without synchronising.
+ *   - The caller owns every buffer.  Inputs are read-only.
+ *   - Return value: 0 on success, a negative LTR_E* code otherwise; nothing is thrown
+ *     and the process is never terminated.  ltr_strerror() names the code,
+ *     ltr_last_cuda_error() returns the cudaError_t behind the last LTR_ECUDA of the
+ *     calling thread.
+ *   - 1 <= L <= LTR_MAX_LIST_SIZE; B >= 0 (B == 0 is a no-op).
+ *   - Rankings break score ties lowest-index-first and place padded documents last in
+ *     index order.  (The reference breaks ties with a random permutation drawn from the
+ *     global torch RNG, utils/tensor_operations.py:43-45; any tie order is a valid
+ *     reference output.  This library consumes no RNG state.)
+ */
+#ifndef LTR_SM100_H_
+#define LTR_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTR_VERSION 100            /* major*100 + minor */
+#define LTR_MAX_LIST_SIZE 4096
+
+/* error codes */
+#define LTR_OK 0
+#define LTR_EINVAL (-1)            /* bad argument (NULL pointer, bad mode, bad dtype width, k < 1) */
+#define LTR_EUNSUPPORTED (-2)      /* L > LTR_MAX_LIST_SIZE or not an sm_100 device */
+#define LTR_ECUDA (-3)             /* a CUDA runtime call failed: see ltr_last_cuda_error() */
+
+/* `mode` of ltr_pairwise_additive: loss/pairwise_additive.py */
+#define LTR_ADD_HINGE 0            /* PairwiseHingeLoss      :93-113  */
+#define LTR_ADD_DCG_HINGE 1        /* PairwiseDCGHingeLoss   :116-133 */
+#define LTR_ADD_LOGISTIC 2         /* PairwiseLogisticLoss   :136-163 */
+
+/* `mode` of ltr_lambda: loss/pairwise_lambda.py */
+#define LTR_LAM_ARP1 0             /* LambdaARPLoss1   :95-117  */
+#define LTR_LAM_ARP2 1             /* LambdaARPLoss2   :120-140 */
+#define LTR_LAM_NDCG1 2            /* LambdaNDCGLoss1  :143-173 */
+#define LTR_LAM_NDCG2 3            /* LambdaNDCGLoss2  :176-218 */
+
+/* `metric` of ltr_rank_metrics */
+#define LTR_METRIC_DCG 0           /* evaluation/dcg.py:41-99 */
+#define LTR_METRIC_NDCG 1          /* evaluation/dcg.py:8-38  */
+#define LTR_METRIC_ARP 2           /* evaluation/arp.py:7-42  */
+
+/* loss family selector of the host-buffer entry point */
+#define LTR_FAMILY_ADDITIVE 0
+#define LTR_FAMILY_LAMBDA 1
+#define LTR_FAMILY_LISTNET 2
+
+int ltr_version(void);
+const char *ltr_strerror(int rc);
+int ltr_last_cuda_error(void);
+
+/*
+ * Replaces _PairwiseAdditiveLoss.forward (loss/pairwise_additive.py:51-90) with the
+ * per-pair bodies :107-113 / :158-163 and the DCG modifier :132-133, plus the
+ * backward pass autograd derives from them.
+ *   loss_out    [B]   per-query loss.
+ *   dscores_out [B*L] d loss_b / d scores[b, :] (0 on padding), NULL to skip.
+ *   loss_sum    [1]   NULL, or a device scalar to which sum_b loss_b is added
+ *                     atomically (caller zeroes it; feeds the scalar all-reduce).
+ * sigma is only used by LTR_ADD_LOGISTIC.
+ */
+int ltr_pairwise_additive(int mode, const float *scores, const void *rel, int rel_bytes,
+                          const void *n, int n_bytes, int B, int L, float sigma,
+                          float *loss_out, float *dscores_out, float *loss_sum, void *stream);
+
+/*
+ * Replaces LambdaLoss.forward (loss/pairwise_lambda.py:50-92) incl. rank_by_score
+ * (utils/tensor_operations.py:48-64), the gathers, the per-pair bodies (:114-117,
+ * :135-140, :165-173, :198-218), _ndcg_gains (:221-228), _max_dcg (:231-241), and
+ * the backward pass (scatter through the gather).
+ *   ranking_out [B*L] int64, NULL to skip: the ranking used (== ltr_rank_by_score).
+ */
+int ltr_lambda(int mode, const float *scores, const void *rel, int rel_bytes, const void *n,
+               int n_bytes, int B, int L, float sigma, float *loss_out, float *dscores_out,
+               int64_t *ranking_out, float *loss_sum, void *stream);
+
+/*
+ * ListNet (top-1 softmax cross entropy).  Named by the task, absent from the reference
+ * snapshot: softmax(relevance) vs log_softmax(scores) over the valid documents, masking
+ * idiom of utils/tensor_operations.py:81-87.  Parity unpinned.
+ */
+int ltr_listnet(const float *scores, const void *rel, int rel_bytes, const void *n, int n_bytes,
+                int B, int L, float *loss_out, float *dscores_out, float *loss_sum, void *stream);
+
+/*
+ * Replaces dcg / ndcg (evaluation/dcg.py:41-99, :8-38) and arp (evaluation/arp.py:7-42).
+ *   k > 0 : out[b * out_ld] = metric@min(k, L)   (the reference's dcg[:, :k][:, -1])
+ *   k == 0: (dcg / ndcg only) all cut-offs, out[b * out_ld + r] for r < L  (k=None)
+ *   exp_gain: 1 -> gain 2^rel - 1, 0 -> gain rel.  Ignored by LTR_METRIC_ARP (k too).
+ * As in the reference, dcg does not mask the relevance of padded documents (:85).
+ */
+int ltr_rank_metrics(int metric, const float *scores, const void *rel, int rel_bytes,
+                     const void *n, int n_bytes, int B, int L, int k, int exp_gain, float *out,
+                     int out_ld, void *stream);
+
+/* Replaces rank_by_score (utils/tensor_operations.py:48-64): ranking_out [B*L] int64. */
+int ltr_rank_by_score(const float *scores, const void *n, int n_bytes, int B, int L,
+                      int64_t *ranking_out, void *stream);
+
+/*
+ * Backward of every loss above: out[b, j] = g[b] * dscores[b, j]  (the chain rule
+ * autograd applies to the saved per-query gradient).  `out` may alias `dscores`.
+ */
+int ltr_scale_rows(const float *g, const float *dscores, float *out, int B, int L, void *stream);
+
+/*
+ * Host-buffer form of the three loss families (the call the reference's CPU path is
+ * compared with end to end): copies scores / relevance (int64) / n (int64) from host
+ * memory into `workspace`, runs the fused loss + gradient kernel and copies loss_out
+ * [B] and dscores_out [B*L] (if not NULL) back to host memory, all on `stream`.
+ * `workspace` is a device buffer of at least ltr_host_workspace_bytes(B, L) bytes.
+ */
+size_t ltr_host_workspace_bytes(int B, int L);
+int ltr_loss_host(int family, int mode, const float *h_scores, const int64_t *h_rel,
+                  const int64_t *h_n, int B, int L, float sigma, float *h_loss_out,
+                  float *h_dscores_out, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTR_SM100_H_ */

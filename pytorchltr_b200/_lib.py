@@ -1,0 +1,88 @@
+"""ctypes binding of ``libltr_sm100.so`` (C ABI: ``include/ltr_sm100.h``).
+
+There is no CPU fallback: if the shared library is missing, or a call fails, the
+error is raised to the caller.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libltr_sm100.so")
+
+# every symbol include/ltr_sm100.h declares
+SYMBOLS = (
+    "ltr_version", "ltr_strerror", "ltr_last_cuda_error", "ltr_pairwise_additive", "ltr_lambda",
+    "ltr_listnet", "ltr_rank_metrics", "ltr_rank_by_score", "ltr_scale_rows",
+    "ltr_host_workspace_bytes", "ltr_loss_host",
+)
+
+ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
+LAM_ARP1, LAM_ARP2, LAM_NDCG1, LAM_NDCG2 = 0, 1, 2, 3
+METRIC_DCG, METRIC_NDCG, METRIC_ARP = 0, 1, 2
+FAMILY_ADDITIVE, FAMILY_LAMBDA, FAMILY_LISTNET = 0, 1, 2
+MAX_LIST_SIZE = 4096
+
+_lock = threading.Lock()
+_lib = None
+
+
+class LtrError(RuntimeError):
+    """A libltr_sm100 call returned a negative LTR_E* code."""
+
+
+def _declare(lib):
+    c_int, c_void_p, c_float, c_size_t = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_size_t
+    lib.ltr_version.restype = c_int
+    lib.ltr_version.argtypes = []
+    lib.ltr_strerror.restype = ctypes.c_char_p
+    lib.ltr_strerror.argtypes = [c_int]
+    lib.ltr_last_cuda_error.restype = c_int
+    lib.ltr_last_cuda_error.argtypes = []
+    lib.ltr_pairwise_additive.restype = c_int
+    lib.ltr_pairwise_additive.argtypes = [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                          c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ltr_lambda.restype = c_int
+    lib.ltr_lambda.argtypes = [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                               c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ltr_listnet.restype = c_int
+    lib.ltr_listnet.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p]
+    lib.ltr_rank_metrics.restype = c_int
+    lib.ltr_rank_metrics.argtypes = [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.ltr_rank_by_score.restype = c_int
+    lib.ltr_rank_by_score.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.ltr_scale_rows.restype = c_int
+    lib.ltr_scale_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.ltr_host_workspace_bytes.restype = c_size_t
+    lib.ltr_host_workspace_bytes.argtypes = [c_int, c_int]
+    lib.ltr_loss_host.restype = c_int
+    lib.ltr_loss_host.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+                        "`python -m pytorchltr_b200.build` (needs nvcc); pytorchltr_b200 has no "
+                        "CPU fallback.")
+                handle = ctypes.CDLL(LIB_PATH)
+                missing = [s for s in SYMBOLS if not hasattr(handle, s)]
+                if missing:
+                    raise ImportError(f"{LIB_PATH} does not export {missing}")
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().ltr_strerror(rc).decode()
+        raise LtrError(f"libltr_sm100: {msg} (code {rc})")

@@ -1,0 +1,202 @@
+"""Torch <-> C-ABI glue: input normalisation, launches on the current stream, autograd.
+
+PyTorch is plumbing here (device memory, streams, the autograd graph); every number
+is produced by ``libltr_sm100.so``.  CPU tensors are accepted the way the reference
+accepts them, but are staged through the GPU (H2D copy, kernel, D2H copy): there is
+no CPU arithmetic path, and without a CUDA device the call raises.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from pytorchltr_b200 import _lib
+
+
+def _device_for(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "pytorchltr_b200 computes on CUDA only (sm_100a kernels, no CPU fallback) and "
+            "no CUDA device is available")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def normalise(scores: torch.Tensor, relevance: Optional[torch.Tensor], n: torch.Tensor,
+              device: torch.device):
+    """Returns contiguous device tensors ``scores (B, L) f32``, ``relevance (B, L) i64|i32``
+    and ``n (B,) i64|i32``.  Accepts ``(B, L)`` or ``(B, L, 1)`` like the reference
+    (loss/pairwise_additive.py:60-65)."""
+    if scores.dim() == 3:
+        scores = scores.reshape(scores.shape[0], scores.shape[1])
+    if scores.dim() != 2:
+        raise ValueError(f"scores must be (B, L) or (B, L, 1), got {tuple(scores.shape)}")
+    B, L = scores.shape
+    if L < 1:
+        raise ValueError("list size must be at least 1")
+    if L > _lib.MAX_LIST_SIZE:
+        raise ValueError(f"list size {L} exceeds LTR_MAX_LIST_SIZE={_lib.MAX_LIST_SIZE}")
+    s = scores.detach()
+    if s.dtype != torch.float32:
+        s = s.to(torch.float32)
+    s = s.to(device, non_blocking=True).contiguous()
+    y = None
+    if relevance is not None:
+        if relevance.dim() == 3:
+            relevance = relevance.reshape(relevance.shape[0], relevance.shape[1])
+        if tuple(relevance.shape) != (B, L):
+            raise ValueError(
+                f"relevance {tuple(relevance.shape)} does not match scores {(B, L)}")
+        y = relevance.detach()
+        if y.dtype not in (torch.int64, torch.int32):
+            y = y.to(torch.int64)
+        y = y.to(device, non_blocking=True).contiguous()
+    if n.dim() != 1 or n.shape[0] != B:
+        raise ValueError(f"n must have shape ({B},), got {tuple(n.shape)}")
+    nn = n.detach()
+    if nn.dtype not in (torch.int64, torch.int32):
+        nn = nn.to(torch.int64)
+    nn = nn.to(device, non_blocking=True).contiguous()
+    return s, y, nn, B, L
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def launch_loss(family: int, mode: int, s: torch.Tensor, y: torch.Tensor, nn: torch.Tensor,
+                sigma: float, want_grad: bool, want_ranking: bool = False,
+                loss_sum: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """One fused launch: per-query loss (B,), d loss / d scores (B, L), ranking (B, L)."""
+    B, L = s.shape
+    dev = s.device
+    loss = torch.empty(B, dtype=torch.float32, device=dev)
+    grad = torch.empty((B, L), dtype=torch.float32, device=dev) if want_grad else None
+    ranking = torch.empty((B, L), dtype=torch.int64, device=dev) if want_ranking else None
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        if family == _lib.FAMILY_ADDITIVE:
+            rc = lib.ltr_pairwise_additive(mode, s.data_ptr(), y.data_ptr(), y.element_size(),
+                                           nn.data_ptr(), nn.element_size(), B, L, float(sigma),
+                                           loss.data_ptr(), _ptr(grad), _ptr(loss_sum), st)
+        elif family == _lib.FAMILY_LAMBDA:
+            rc = lib.ltr_lambda(mode, s.data_ptr(), y.data_ptr(), y.element_size(),
+                                nn.data_ptr(), nn.element_size(), B, L, float(sigma),
+                                loss.data_ptr(), _ptr(grad), _ptr(ranking), _ptr(loss_sum), st)
+        elif family == _lib.FAMILY_LISTNET:
+            rc = lib.ltr_listnet(s.data_ptr(), y.data_ptr(), y.element_size(), nn.data_ptr(),
+                                 nn.element_size(), B, L, loss.data_ptr(), _ptr(grad),
+                                 _ptr(loss_sum), st)
+        else:
+            raise ValueError(f"unknown loss family {family}")
+    _lib.check(rc)
+    return loss, grad, ranking
+
+
+def scale_rows(g: torch.Tensor, dscores: torch.Tensor) -> torch.Tensor:
+    """``g[:, None] * dscores`` on the device (ltr_scale_rows)."""
+    B, L = dscores.shape
+    g = g.detach().to(device=dscores.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(dscores)
+    if B == 0:
+        return out
+    with torch.cuda.device(dscores.device):
+        rc = _lib.lib().ltr_scale_rows(g.data_ptr(), dscores.data_ptr(), out.data_ptr(), B, L,
+                                       _stream(dscores.device))
+    _lib.check(rc)
+    return out
+
+
+class _FusedLoss(torch.autograd.Function):
+    """``forward`` computes the per-query loss and the unscaled d loss_b / d scores in ONE
+    kernel and saves the latter; ``backward`` is the row scale ``g[b] * saved[b, :]``.
+
+    Nothing flows to relevance / n; the ranking, gains and discounts are constants of the
+    backward pass, exactly as in the reference (the gather indices carry no gradient).
+    Double backward is not supported (``once_differentiable``); the reference supports it
+    only implicitly through composite autograd.
+    """
+
+    @staticmethod
+    def forward(ctx, scores, relevance, n, family, mode, sigma):
+        dev = _device_for(scores)
+        s, y, nn, B, L = normalise(scores, relevance, n, dev)
+        want_grad = bool(ctx.needs_input_grad[0])
+        if B == 0:
+            loss = torch.empty(0, dtype=torch.float32, device=dev)
+            grad = torch.empty((0, L), dtype=torch.float32, device=dev) if want_grad else None
+        else:
+            loss, grad, _ = launch_loss(family, mode, s, y, nn, sigma, want_grad)
+        ctx.scores_shape = scores.shape
+        ctx.scores_dtype = scores.dtype
+        ctx.scores_device = scores.device
+        if want_grad:
+            ctx.save_for_backward(grad)
+        out = loss
+        if out.dtype != scores.dtype and scores.dtype.is_floating_point:
+            out = out.to(scores.dtype)
+        if out.device != scores.device:
+            out = out.to(scores.device)   # synchronising D2H copy: CPU callers get CPU results
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (saved,) = ctx.saved_tensors
+        out = scale_rows(g, saved)
+        if out.dtype != ctx.scores_dtype:
+            out = out.to(ctx.scores_dtype)
+        if out.device != ctx.scores_device:
+            out = out.to(ctx.scores_device)
+        return out.reshape(ctx.scores_shape), None, None, None, None, None
+
+
+def fused_loss(scores, relevance, n, family: int, mode: int, sigma: float = 1.0):
+    return _FusedLoss.apply(scores, relevance, n, family, mode, float(sigma))
+
+
+def rank_metric(metric: int, scores, relevance, n, k: Optional[int], exp: bool):
+    dev = _device_for(scores)
+    s, y, nn, B, L = normalise(scores, relevance, n, dev)
+    if k is not None:
+        # dcg[:, :k][:, -1] (evaluation/dcg.py:97-98) with Python slice semantics
+        kk = k if k >= 0 else L + k
+        kk = min(kk, L)
+        if kk <= 0:
+            raise IndexError("index -1 is out of bounds for dimension 1 with size 0")
+    else:
+        kk = 0
+    all_k = metric != _lib.METRIC_ARP and k is None
+    out = torch.empty((B, L) if all_k else (B,), dtype=torch.float32, device=dev)
+    if B > 0:
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ltr_rank_metrics(metric, s.data_ptr(), y.data_ptr(), y.element_size(),
+                                             nn.data_ptr(), nn.element_size(), B, L,
+                                             1 if metric == _lib.METRIC_ARP else kk,
+                                             1 if exp else 0, out.data_ptr(), L if all_k else 1,
+                                             _stream(dev))
+        _lib.check(rc)
+    if out.device != scores.device:
+        out = out.to(scores.device)
+    return out
+
+
+def rank_by_score(scores, n):
+    dev = _device_for(scores)
+    s, _, nn, B, L = normalise(scores, None, n, dev)
+    out = torch.empty((B, L), dtype=torch.int64, device=dev)
+    if B > 0:
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ltr_rank_by_score(s.data_ptr(), nn.data_ptr(), nn.element_size(), B, L,
+                                              out.data_ptr(), _stream(dev))
+        _lib.check(rc)
+    if out.device != scores.device:
+        out = out.to(scores.device)
+    return out

@@ -1,0 +1,739 @@
+// ltr_kernels.cu -- sm_100a kernels + C ABI of libltr_sm100.so (see include/ltr_sm100.h).
+//
+// One fused launch per loss call: each CTA stages a query's padded row into shared
+// memory, ranks it (bitonic argsort), builds the O(L) weight tables the loss needs
+// (gains, discounts, delta) and then generates the O(L^2) document pairs on the fly
+// from shared memory, producing the per-query loss AND d loss / d scores in the same
+// pass.  Nothing of size L^2 ever exists in memory (the reference materialises
+// ~78 L^2 bytes per query, utils/tensor_operations.py:94-119).
+//
+// Reference citations are relative to the reference root (pytorchltr/...).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ltr_common.cuh"
+#include "ltr_sm100.h"
+
+namespace ltr {
+
+enum PairMode : int {
+  PM_HINGE = 0,
+  PM_DCG_HINGE = 1,
+  PM_LOGISTIC = 2,
+  PM_ARP1 = 3,
+  PM_ARP2 = 4,
+  PM_NDCG1 = 5,
+  PM_NDCG2 = 6,
+};
+
+__host__ __device__ constexpr bool mode_needs_rank(int m) { return m == PM_NDCG1 || m == PM_NDCG2; }
+__host__ __device__ constexpr bool mode_is_lambda(int m) { return m >= PM_ARP1; }
+
+// Shared-memory carve-up of the generic pair kernel (and the metric kernels).
+struct RowSmem {
+  uint64_t* keys;  // [P]   sort keys
+  float* raw_s;    // [L]   scores, document order
+  int* raw_y;      // [L]   relevance, document order
+  float* s;        // [L]   scores, rank order
+  int* y;          // [L]   relevance, rank order
+  float* w;        // [L]   per-item weight (gain G, or G/D, or float(rel)), rank order
+  int* doc;        // [L]   rank -> document index
+  float* delta;    // [L]   |1/D(k) - 1/D(k+1)|, pairwise_lambda.py:206-211
+  float* disc;     // [L]   D(r) = log2(2 + r),    pairwise_lambda.py:168-170 / dcg.py:93
+  float* gout;     // [L]   gradient, document order
+  float* red;      // [40]  reduction scratch
+};
+
+__host__ __device__ inline size_t row_smem_bytes(int L, int P) {
+  return sizeof(uint64_t) * static_cast<size_t>(P) + static_cast<size_t>(L) * 4u * 9u + 40u * 4u;
+}
+
+__device__ __forceinline__ RowSmem carve(unsigned char* base, int L, int P) {
+  RowSmem m;
+  m.keys = reinterpret_cast<uint64_t*>(base);
+  float* f = reinterpret_cast<float*>(base + sizeof(uint64_t) * static_cast<size_t>(P));
+  m.raw_s = f;
+  m.raw_y = reinterpret_cast<int*>(f + L);
+  m.s = f + 2 * L;
+  m.y = reinterpret_cast<int*>(f + 3 * L);
+  m.w = f + 4 * L;
+  m.doc = reinterpret_cast<int*>(f + 5 * L);
+  m.delta = f + 6 * L;
+  m.disc = f + 7 * L;
+  m.gout = f + 8 * L;
+  m.red = f + 9 * L;
+  return m;
+}
+
+// Stage one padded row into shared memory (coalesced).
+__device__ __forceinline__ void stage_row(const RowSmem& m, const float* __restrict__ scores,
+                                          const void* __restrict__ rel, int rel_bytes, int b, int L) {
+  const size_t base = static_cast<size_t>(b) * L;
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    m.raw_s[j] = scores[base + j];
+    m.raw_y[j] = load_int_clamped(rel, rel_bytes, base + j);
+  }
+}
+
+// rank_by_score (utils/tensor_operations.py:48-64): valid documents by descending score,
+// padded documents last.  Leaves the sorted (key, doc) pairs in m.keys.
+__device__ __forceinline__ void rank_row_by_score(const RowSmem& m, int nb, int L, int P) {
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    uint32_t key = kPadKey;
+    if (j < nb) key = desc_key_f32(m.raw_s[j]);
+    m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
+  }
+  cta_bitonic_sort(m.keys, P);
+}
+
+// Ideal ranking: relevance descending, padding last (_max_dcg, pairwise_lambda.py:233;
+// ndcg's dcg(relevance.float(), ...), dcg.py:36).
+__device__ __forceinline__ void rank_row_by_relevance(const RowSmem& m, int nb, int L, int P) {
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    uint32_t key = kPadKey;
+    if (j < nb) key = desc_key_i32(m.raw_y[j]);
+    m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
+  }
+  cta_bitonic_sort(m.keys, P);
+}
+
+// ---------------------------------------------------------------------------------------
+// Row pass of the generic pair kernel: thread owns item `a` (rank order) and visits every
+// b in [0, nb).  Each ordered pair is seen from both endpoints, so a thread only ever
+// accumulates its own gradient: no synchronisation, at the price of evaluating the
+// sigmoid of every unordered pair twice (the tiled kernels in ltr_pair_tiles.cuh
+// evaluate it once).
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void row_pass(const RowSmem& m, int a, int nb, float sigma,
+                                         float& lacc, float& gacc) {
+  const float sa = m.s[a];
+  const int ya = m.y[a];
+  const float wa = m.w[a];
+  for (int b = 0; b < nb; ++b) {
+    const float sb = m.s[b];
+    const int yb = m.y[b];
+    if constexpr (MODE == PM_HINGE || MODE == PM_DCG_HINGE) {
+      // pairwise_additive.py:108-112: loss = 1.0 - (s_i - s_j) (two float32 roundings);
+      // 0 where rel_i - rel_j <= 0; 0 where loss < 0 (the kink loss == 0 keeps grad -1/+1).
+      const float d = sa - sb;
+      if (ya > yb) {
+        const float l = 1.0f - d;
+        if (!(l < 0.0f)) { lacc += l; gacc -= 1.0f; }
+      } else if (yb > ya) {
+        const float l = 1.0f + d;  // == 1.0f - (s_b - s_a) bit for bit
+        if (!(l < 0.0f)) gacc += 1.0f;
+      }
+    } else if constexpr (MODE == PM_LOGISTIC || MODE == PM_ARP2 || MODE == PM_NDCG2) {
+      // loss_ij = w_ij * log2(1 + exp(-sigma (s_i - s_j))) for rel_i > rel_j with
+      //   w = 1                         pairwise_additive.py:161-162
+      //   w = rel_i - rel_j             pairwise_lambda.py:137-140
+      //   w = delta_|i-j| |G_i - G_j|   pairwise_lambda.py:201-218
+      const int yd = ya - yb;
+      if (yd != 0) {
+        float w;
+        if constexpr (MODE == PM_LOGISTIC) w = 1.0f;
+        else if constexpr (MODE == PM_ARP2) w = fabsf(static_cast<float>(yd));
+        else w = m.delta[a > b ? a - b : b - a] * fabsf(wa - m.w[b]);
+        float x = sigma * (sa - sb);
+        if (yd < 0) x = -x;                    // sigma * (s_winner - s_loser)
+        const float u = -fabsf(x) * kLog2e;
+        const float t = ex2_approx(u);         // exp(-|x|) in (0, 1]: never overflows
+        const float p = 1.0f + t;
+        const float r = rcp_approx(p);
+        const float sg = x >= 0.0f ? t * r : r;  // sigmoid(-x)
+        const float lam = w * sg;
+        if (yd > 0) {
+          gacc -= lam;
+          float l = lg2_approx(p);             // log2(1 + e^-x) = max(-x, 0) log2 e + log2(1 + e^-|x|)
+          if (x < 0.0f) l -= u;
+          lacc = fmaf(w, l, lacc);
+        } else {
+          gacc += lam;
+        }
+      }
+    } else {
+      // ARP1 / NDCG1: every ordered pair incl. the diagonal, weight of the FIRST index:
+      //   w_i = rel_i        pairwise_lambda.py:114-117
+      //   w_i = G_i / D_i    pairwise_lambda.py:165-173
+      const float wb = m.w[b];
+      const float x = sigma * (sa - sb);
+      const float u = -fabsf(x) * kLog2e;
+      const float t = ex2_approx(u);
+      const float p = 1.0f + t;
+      const float r = rcp_approx(p);
+      const float tr = t * r;
+      const float s_neg = x >= 0.0f ? tr : r;  // sigmoid(-x): pair (a, b)
+      const float s_pos = x >= 0.0f ? r : tr;  // sigmoid(+x): pair (b, a)
+      float l = lg2_approx(p);
+      if (x < 0.0f) l -= u;
+      lacc = fmaf(wa, l, lacc);
+      gacc += wb * s_pos - wa * s_neg;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+pair_loss_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
+                 const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma,
+                 float* __restrict__ loss_out, float* __restrict__ grad_out,
+                 int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const RowSmem m = carve(smem_raw, L, P);
+  const bool want_rank = mode_needs_rank(MODE) || ranking_out != nullptr;
+
+  // Score-independent tables, once per (persistent) CTA.
+  if constexpr (MODE == PM_NDCG1 || MODE == PM_NDCG2) {
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+      const float d0 = log2f(2.0f + static_cast<float>(k));
+      const float d1 = log2f(3.0f + static_cast<float>(k));
+      m.disc[k] = d0;
+      m.delta[k] = fabsf(1.0f / d0 - 1.0f / d1);
+    }
+  }
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();  // previous query fully consumed
+    const int nb = load_n(n, n_bytes, b, L);
+    stage_row(m, scores, rel, rel_bytes, b, L);
+    __syncthreads();
+
+    if (want_rank) {
+      rank_row_by_score(m, nb, L, P);
+      for (int r = threadIdx.x; r < L; r += blockDim.x) {
+        const int d = static_cast<int>(m.keys[r] & 0xffffffffu);
+        m.doc[r] = d;
+        m.s[r] = m.raw_s[d];
+        m.y[r] = m.raw_y[d];
+        if (ranking_out) ranking_out[static_cast<size_t>(b) * L + r] = d;
+      }
+    } else {
+      for (int r = threadIdx.x; r < L; r += blockDim.x) {
+        m.doc[r] = r;
+        m.s[r] = m.raw_s[r];
+        m.y[r] = m.raw_y[r];
+      }
+    }
+
+    if constexpr (MODE == PM_NDCG1 || MODE == PM_NDCG2) {
+      // _max_dcg (pairwise_lambda.py:231-241) then _ndcg_gains (:221-228)
+      __syncthreads();  // everyone is done reading the score ranking out of m.keys
+      rank_row_by_relevance(m, nb, L, P);
+      float part = 0.0f;
+      for (int r = threadIdx.x; r < nb; r += blockDim.x) {
+        const int d = static_cast<int>(m.keys[r] & 0xffffffffu);
+        part += exp_gain_f32(m.raw_y[d]) / m.disc[r];
+      }
+      float max_dcg = cta_sum(part, m.red);
+      if (max_dcg == 0.0f) max_dcg = 1.0f;
+      for (int r = threadIdx.x; r < L; r += blockDim.x) {
+        const float g = exp_gain_f32(m.y[r]) / max_dcg;
+        m.w[r] = MODE == PM_NDCG1 ? g / m.disc[r] : g;
+      }
+    } else {
+      for (int r = threadIdx.x; r < L; r += blockDim.x) m.w[r] = static_cast<float>(m.y[r]);
+    }
+    for (int j = threadIdx.x; j < L; j += blockDim.x) m.gout[j] = 0.0f;
+    __syncthreads();
+
+    float lacc = 0.0f;
+    for (int a = threadIdx.x; a < nb; a += blockDim.x) {
+      float gacc = 0.0f;
+      row_pass<MODE>(m, a, nb, sigma, lacc, gacc);
+      m.gout[m.doc[a]] = gacc;   // backward of the gather (pairwise_lambda.py:69)
+    }
+    float loss = cta_sum(lacc, m.red);   // barriers inside also publish gout
+
+    float gscale = 1.0f;
+    if constexpr (MODE == PM_DCG_HINGE) {
+      // pairwise_additive.py:132-133: -1 / ln(2 + h); d/dh = 1 / ((2 + h) ln^2(2 + h))
+      const float lg = logf(2.0f + loss);
+      gscale = 1.0f / ((2.0f + loss) * lg * lg);
+      loss = -1.0f / lg;
+    } else if constexpr (MODE != PM_HINGE) {
+      gscale = sigma * kLog2e;           // lambda = -sigma w sigmoid(-x) / ln 2
+    }
+    if (threadIdx.x == 0) {
+      loss_out[b] = loss;
+      if (loss_sum) atomicAdd(loss_sum, loss);
+    }
+    if (grad_out) {
+      float* __restrict__ go = grad_out + static_cast<size_t>(b) * L;
+      for (int j = threadIdx.x; j < L; j += blockDim.x) go[j] = m.gout[j] * gscale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ListNet: one warp per query, three passes over the (L1-resident) row.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+listnet_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
+               const void* __restrict__ n, int n_bytes, int B, int L,
+               float* __restrict__ loss_out, float* __restrict__ grad_out,
+               float* __restrict__ loss_sum) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  for (int b = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_cta) {
+    const int nb = load_n(n, n_bytes, b, L);
+    const size_t base = static_cast<size_t>(b) * L;
+    float ms = -INFINITY, my = -INFINITY;
+    for (int j = lane; j < nb; j += 32) {
+      ms = fmaxf(ms, scores[base + j]);
+      my = fmaxf(my, static_cast<float>(load_int_clamped(rel, rel_bytes, base + j)));
+    }
+    ms = warp_max(ms);
+    my = warp_max(my);
+    float zs = 0.0f, zy = 0.0f, a = 0.0f;
+    for (int j = lane; j < nb; j += 32) {
+      const float ds = scores[base + j] - ms;
+      const float ey = expf(static_cast<float>(load_int_clamped(rel, rel_bytes, base + j)) - my);
+      zs += expf(ds);
+      zy += ey;
+      a = fmaf(ey, ds, a);
+    }
+    zs = warp_sum(zs);
+    zy = warp_sum(zy);
+    a = warp_sum(a);
+    // loss = -sum_j P_j (s_j - ms - ln zs) = ln zs - (sum_j e^{y_j - my} (s_j - ms)) / zy
+    const float loss = nb > 0 ? logf(zs) - a / zy : 0.0f;
+    if (lane == 0) {
+      loss_out[b] = loss;
+      if (loss_sum) atomicAdd(loss_sum, loss);
+    }
+    if (grad_out) {
+      const float izs = nb > 0 ? 1.0f / zs : 0.0f, izy = nb > 0 ? 1.0f / zy : 0.0f;
+      for (int j = lane; j < L; j += 32) {
+        float g = 0.0f;
+        if (j < nb) {
+          const float ey = expf(static_cast<float>(load_int_clamped(rel, rel_bytes, base + j)) - my);
+          g = expf(scores[base + j] - ms) * izs - ey * izy;
+        }
+        grad_out[base + j] = g;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Ranking metrics: dcg / ndcg (evaluation/dcg.py) and arp (evaluation/arp.py).
+// ---------------------------------------------------------------------------------------
+
+// Inclusive scan of v[0..L) in shared memory (Hillis-Steele, ping-pong between v and tmp).
+// Returns the buffer holding the result.
+__device__ __forceinline__ float* cta_inclusive_scan(float* v, float* tmp, int L) {
+  float* src = v;
+  float* dst = tmp;
+  __syncthreads();
+  for (int off = 1; off < L; off <<= 1) {
+    for (int j = threadIdx.x; j < L; j += blockDim.x)
+      dst[j] = j >= off ? src[j] + src[j - off] : src[j];
+    __syncthreads();
+    float* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+// per-rank dcg terms of the ranking held in m.keys -> out[r] (dcg.py:85-93).  The relevance
+// of padded documents is NOT masked, exactly as in the reference.
+__device__ __forceinline__ void dcg_terms(const RowSmem& m, float* out, int L, int exp_gain) {
+  for (int r = threadIdx.x; r < L; r += blockDim.x) {
+    const int d = static_cast<int>(m.keys[r] & 0xffffffffu);
+    float g = static_cast<float>(m.raw_y[d]);
+    if (exp_gain) g = exp2f(g) - 1.0f;
+    out[r] = g / log2f(static_cast<float>(r) + 2.0f);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+rank_metrics_kernel(int metric, const float* __restrict__ scores, const void* __restrict__ rel,
+                    int rel_bytes, const void* __restrict__ n, int n_bytes, int B, int L, int P,
+                    int k, int exp_gain, float* __restrict__ out, int out_ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const RowSmem m = carve(smem_raw, L, P);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const int nb = load_n(n, n_bytes, b, L);
+    stage_row(m, scores, rel, rel_bytes, b, L);
+    __syncthreads();
+    rank_row_by_score(m, nb, L, P);
+
+    if (metric == LTR_METRIC_ARP) {
+      // arp.py:32-42: sum_r (r + 1) rel_sort[r] / sum_r rel_sort[r] over valid ranks
+      float srp = 0.0f, nrp = 0.0f;
+      for (int r = threadIdx.x; r < nb; r += blockDim.x) {
+        const float y = static_cast<float>(m.raw_y[static_cast<int>(m.keys[r] & 0xffffffffu)]);
+        srp = fmaf(static_cast<float>(r + 1), y, srp);
+        nrp += y;
+      }
+      srp = cta_sum(srp, m.red);
+      nrp = cta_sum(nrp, m.red);
+      if (nrp == 0.0f) nrp = 1.0f;
+      if (threadIdx.x == 0) out[static_cast<size_t>(b) * out_ld] = srp / nrp;
+      continue;
+    }
+
+    const int kk = k > 0 ? (k < L ? k : L) : 0;
+    dcg_terms(m, m.s, L, exp_gain);
+    if (kk > 0) {
+      // dcg[:, :k][:, -1]: only the first kk ranks contribute
+      float part = 0.0f;
+      for (int r = threadIdx.x; r < kk; r += blockDim.x) part += m.s[r];
+      __syncthreads();
+      float v = cta_sum(part, m.red);
+      if (metric == LTR_METRIC_NDCG) {
+        rank_row_by_relevance(m, nb, L, P);
+        dcg_terms(m, m.w, L, exp_gain);
+        float ip = 0.0f;
+        __syncthreads();
+        for (int r = threadIdx.x; r < kk; r += blockDim.x) ip += m.w[r];
+        float iv = cta_sum(ip, m.red);
+        if (iv == 0.0f) iv = 1.0f;       // dcg.py:37
+        v = v / iv;
+      }
+      if (threadIdx.x == 0) out[static_cast<size_t>(b) * out_ld] = v;
+    } else {
+      float* cum = cta_inclusive_scan(m.s, m.gout, L);   // dcg.py:94 cumsum
+      float* icum = nullptr;
+      if (metric == LTR_METRIC_NDCG) {
+        rank_row_by_relevance(m, nb, L, P);
+        dcg_terms(m, m.w, L, exp_gain);
+        icum = cta_inclusive_scan(m.w, m.delta, L);
+      }
+      float* __restrict__ o = out + static_cast<size_t>(b) * out_ld;
+      for (int r = threadIdx.x; r < L; r += blockDim.x) {
+        float v = cum[r];
+        if (icum) { float iv = icum[r]; if (iv == 0.0f) iv = 1.0f; v = v / iv; }
+        o[r] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+rank_by_score_kernel(const float* __restrict__ scores, const void* __restrict__ n, int n_bytes,
+                     int B, int L, int P, int64_t* __restrict__ ranking_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const RowSmem m = carve(smem_raw, L, P);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const int nb = load_n(n, n_bytes, b, L);
+    const size_t base = static_cast<size_t>(b) * L;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) m.raw_s[j] = scores[base + j];
+    __syncthreads();
+    rank_row_by_score(m, nb, L, P);
+    for (int r = threadIdx.x; r < L; r += blockDim.x)
+      ranking_out[base + r] = static_cast<int64_t>(m.keys[r] & 0xffffffffu);
+  }
+}
+
+// out[b, j] = g[b] * d[b, j]: the backward of every loss (HBM-bound streaming pass).
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const float* __restrict__ g, const float* __restrict__ d, float* __restrict__ out,
+                  int B, int L) {
+  const size_t total = static_cast<size_t>(B) * L;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if ((L & 3) == 0) {
+    const size_t total4 = total >> 2;
+    const int L4 = L >> 2;
+    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
+    float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4; i += stride) {
+      const float gb = g[i / L4];
+      float4 v = d4[i];
+      v.x *= gb; v.y *= gb; v.z *= gb; v.w *= gb;
+      o4[i] = v;
+    }
+  } else {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += stride)
+      out[i] = g[i / L] * d[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host side of the C ABI
+// ---------------------------------------------------------------------------------------
+thread_local int tls_cuda_error = 0;
+
+inline int cuda_fail(cudaError_t e) {
+  tls_cuda_error = static_cast<int>(e);
+  return LTR_ECUDA;
+}
+#define LTR_CUDA(call)                                 \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) return cuda_fail(e__);     \
+  } while (0)
+
+struct DeviceInfo { int sms; int major; bool ok; };
+inline int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  int dev = 0;
+  LTR_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return LTR_EUNSUPPORTED;
+  if (!cache[dev].ok) {
+    int sms = 0, major = 0;
+    LTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LTR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    cache[dev].sms = sms;
+    cache[dev].major = major;
+    cache[dev].ok = true;
+  }
+  *out = cache[dev];
+  return out->major == 10 ? LTR_OK : LTR_EUNSUPPORTED;
+}
+
+inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+inline int check_common(const void* scores, const void* n, int n_bytes, int B, int L) {
+  if (B < 0 || L < 1) return LTR_EINVAL;
+  if (L > LTR_MAX_LIST_SIZE) return LTR_EUNSUPPORTED;
+  if (B > 0 && (!scores || !n)) return LTR_EINVAL;
+  if (n_bytes != 4 && n_bytes != 8) return LTR_EINVAL;
+  return LTR_OK;
+}
+
+inline int cta_threads_for(int L) {
+  int t = (L + 31) / 32 * 32;
+  if (t < 64) t = 64;
+  if (t > 1024) t = 1024;
+  return t;
+}
+
+// Persistent grid: as many CTAs as fit on the device at once, never more than queries.
+template <typename K>
+inline int persistent_grid(K kernel, int threads, size_t smem, int B, const DeviceInfo& di, int* grid) {
+  if (smem > 48 * 1024)
+    LTR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) return LTR_EUNSUPPORTED;
+  long long g = static_cast<long long>(per_sm) * di.sms;
+  *grid = static_cast<int>(g < B ? g : B);
+  return LTR_OK;
+}
+
+template <int MODE>
+int launch_pair(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                int B, int L, float sigma, float* loss_out, float* grad_out, int64_t* ranking_out,
+                float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+  const int P = next_pow2(L);
+  const int threads = cta_threads_for(L);
+  const size_t smem = row_smem_bytes(L, P);
+  int grid = 0;
+  int rc = persistent_grid(pair_loss_kernel<MODE>, threads, smem, B, di, &grid);
+  if (rc != LTR_OK) return rc;
+  pair_loss_kernel<MODE><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma,
+                                                      loss_out, grad_out, ranking_out, loss_sum);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,
+                  int n_bytes, int B, int L, float sigma, float* loss_out, float* grad_out,
+                  int64_t* ranking_out, float* loss_sum, void* stream) {
+  int rc = check_common(scores, n, n_bytes, B, L);
+  if (rc != LTR_OK) return rc;
+  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!rel || !loss_out) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LTR_CASE(M)                                                                               \
+  case M:                                                                                         \
+    return launch_pair<M>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,    \
+                          ranking_out, loss_sum, st, di)
+  switch (pm) {
+    LTR_CASE(PM_HINGE);
+    LTR_CASE(PM_DCG_HINGE);
+    LTR_CASE(PM_LOGISTIC);
+    LTR_CASE(PM_ARP1);
+    LTR_CASE(PM_ARP2);
+    LTR_CASE(PM_NDCG1);
+    LTR_CASE(PM_NDCG2);
+    default:
+      return LTR_EINVAL;
+  }
+#undef LTR_CASE
+}
+
+}  // namespace ltr
+
+using namespace ltr;
+
+extern "C" {
+
+int ltr_version(void) { return LTR_VERSION; }
+
+const char* ltr_strerror(int rc) {
+  switch (rc) {
+    case LTR_OK: return "success";
+    case LTR_EINVAL: return "invalid argument";
+    case LTR_EUNSUPPORTED: return "unsupported list size or device (needs sm_100, L <= LTR_MAX_LIST_SIZE)";
+    case LTR_ECUDA: return cudaGetErrorString(static_cast<cudaError_t>(tls_cuda_error));
+    default: return "unknown error";
+  }
+}
+
+int ltr_last_cuda_error(void) { return tls_cuda_error; }
+
+int ltr_pairwise_additive(int mode, const float* scores, const void* rel, int rel_bytes,
+                          const void* n, int n_bytes, int B, int L, float sigma, float* loss_out,
+                          float* dscores_out, float* loss_sum, void* stream) {
+  if (mode < LTR_ADD_HINGE || mode > LTR_ADD_LOGISTIC) return LTR_EINVAL;
+  return dispatch_pair(PM_HINGE + mode, scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out,
+                       dscores_out, nullptr, loss_sum, stream);
+}
+
+int ltr_lambda(int mode, const float* scores, const void* rel, int rel_bytes, const void* n,
+               int n_bytes, int B, int L, float sigma, float* loss_out, float* dscores_out,
+               int64_t* ranking_out, float* loss_sum, void* stream) {
+  if (mode < LTR_LAM_ARP1 || mode > LTR_LAM_NDCG2) return LTR_EINVAL;
+  return dispatch_pair(PM_ARP1 + mode, scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out,
+                       dscores_out, ranking_out, loss_sum, stream);
+}
+
+int ltr_listnet(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                int B, int L, float* loss_out, float* dscores_out, float* loss_sum, void* stream) {
+  int rc = check_common(scores, n, n_bytes, B, L);
+  if (rc != LTR_OK) return rc;
+  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!rel || !loss_out) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const int threads = 256, wpc = threads / 32;
+  long long want = (static_cast<long long>(B) + wpc - 1) / wpc;
+  long long cap = static_cast<long long>(di.sms) * 8;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  listnet_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, rel, rel_bytes, n, n_bytes, B, L, loss_out, dscores_out, loss_sum);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_bytes,
+                     const void* n, int n_bytes, int B, int L, int k, int exp_gain, float* out,
+                     int out_ld, void* stream) {
+  if (metric < LTR_METRIC_DCG || metric > LTR_METRIC_ARP) return LTR_EINVAL;
+  int rc = check_common(scores, n, n_bytes, B, L);
+  if (rc != LTR_OK) return rc;
+  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (k < 0) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!rel || !out) return LTR_EINVAL;
+  const bool all_k = metric != LTR_METRIC_ARP && k == 0;
+  if (out_ld < (all_k ? L : 1)) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const int P = next_pow2(L);
+  const int threads = cta_threads_for(L);
+  const size_t smem = row_smem_bytes(L, P);
+  int grid = 0;
+  rc = persistent_grid(rank_metrics_kernel, threads, smem, B, di, &grid);
+  if (rc != LTR_OK) return rc;
+  rank_metrics_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      metric, scores, rel, rel_bytes, n, n_bytes, B, L, P, k, exp_gain, out, out_ld);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_rank_by_score(const float* scores, const void* n, int n_bytes, int B, int L,
+                      int64_t* ranking_out, void* stream) {
+  int rc = check_common(scores, n, n_bytes, B, L);
+  if (rc != LTR_OK) return rc;
+  if (B == 0) return LTR_OK;
+  if (!ranking_out) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const int P = next_pow2(L);
+  const int threads = cta_threads_for(L);
+  const size_t smem = row_smem_bytes(L, P);
+  int grid = 0;
+  rc = persistent_grid(rank_by_score_kernel, threads, smem, B, di, &grid);
+  if (rc != LTR_OK) return rc;
+  rank_by_score_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      scores, n, n_bytes, B, L, P, ranking_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_scale_rows(const float* g, const float* dscores, float* out, int B, int L, void* stream) {
+  if (B < 0 || L < 1) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!g || !dscores || !out) return LTR_EINVAL;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const size_t total = static_cast<size_t>(B) * L;
+  const size_t work = (L & 3) == 0 ? total / 4 : total;
+  long long want = static_cast<long long>((work + 255) / 256);
+  long long cap = static_cast<long long>(di.sms) * 8;
+  const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+  scale_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, dscores, out, B, L);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t ltr_host_workspace_bytes(int B, int L) {
+  if (B < 0 || L < 1) return 0;
+  const size_t bl = static_cast<size_t>(B) * L;
+  // scores f32 | relevance i64 | n i64 | loss f32 | dscores f32
+  return align256(bl * 4) + align256(bl * 8) + align256(static_cast<size_t>(B) * 8) +
+         align256(static_cast<size_t>(B) * 4) + align256(bl * 4);
+}
+
+int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_rel,
+                  const int64_t* h_n, int B, int L, float sigma, float* h_loss_out,
+                  float* h_dscores_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || L < 1) return LTR_EINVAL;
+  if (L > LTR_MAX_LIST_SIZE) return LTR_EUNSUPPORTED;
+  if (B == 0) return LTR_OK;
+  if (!h_scores || !h_rel || !h_n || !h_loss_out || !workspace) return LTR_EINVAL;
+  if (workspace_bytes < ltr_host_workspace_bytes(B, L)) return LTR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bl = static_cast<size_t>(B) * L;
+  unsigned char* p = static_cast<unsigned char*>(workspace);
+  float* d_scores = reinterpret_cast<float*>(p);            p += align256(bl * 4);
+  int64_t* d_rel = reinterpret_cast<int64_t*>(p);           p += align256(bl * 8);
+  int64_t* d_n = reinterpret_cast<int64_t*>(p);             p += align256(static_cast<size_t>(B) * 8);
+  float* d_loss = reinterpret_cast<float*>(p);              p += align256(static_cast<size_t>(B) * 4);
+  float* d_grad = reinterpret_cast<float*>(p);
+  LTR_CUDA(cudaMemcpyAsync(d_scores, h_scores, bl * 4, cudaMemcpyHostToDevice, st));
+  LTR_CUDA(cudaMemcpyAsync(d_rel, h_rel, bl * 8, cudaMemcpyHostToDevice, st));
+  LTR_CUDA(cudaMemcpyAsync(d_n, h_n, static_cast<size_t>(B) * 8, cudaMemcpyHostToDevice, st));
+  float* gptr = h_dscores_out ? d_grad : nullptr;
+  int rc;
+  switch (family) {
+    case LTR_FAMILY_ADDITIVE:
+      rc = ltr_pairwise_additive(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, stream);
+      break;
+    case LTR_FAMILY_LAMBDA:
+      rc = ltr_lambda(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, nullptr, stream);
+      break;
+    case LTR_FAMILY_LISTNET:
+      rc = ltr_listnet(d_scores, d_rel, 8, d_n, 8, B, L, d_loss, gptr, nullptr, stream);
+      break;
+    default:
+      rc = LTR_EINVAL;
+  }
+  if (rc != LTR_OK) return rc;
+  LTR_CUDA(cudaMemcpyAsync(h_loss_out, d_loss, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
+  if (h_dscores_out)
+    LTR_CUDA(cudaMemcpyAsync(h_dscores_out, d_grad, bl * 4, cudaMemcpyDeviceToHost, st));
+  return LTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+"""Tensor helpers with the names and signatures of ``pytorchltr.utils.tensor_operations``.
+
+``rank_by_score`` runs on the sm_100a per-query argsort kernel.  The other helpers
+are shape plumbing that the fused kernels made unnecessary on the hot path (no pair
+tensor is ever materialised there); they are kept as thin torch expressions so code
+written against the reference keeps working.
+"""
+from typing import Optional
+
+import torch as _torch
+
+from pytorchltr_b200 import _ops
+
+
+def mask_padded_values(xs: _torch.FloatTensor, n: _torch.LongTensor,
+                       mask_value: float = -float('inf'),
+                       mutate: bool = False):
+    """Sets ``xs[b, j]`` to ``mask_value`` for ``j >= n[b]`` (reference :6-26).
+
+    Args:
+        xs: ``(B, L)`` values.
+        n: ``(B,)`` list sizes.
+        mask_value: value written over the padding (default ``-inf``).
+        mutate: write into ``xs`` instead of a copy.
+    """
+    out = xs if mutate else xs.clone()
+    positions = _torch.arange(out.shape[1], device=out.device)
+    padded = positions.unsqueeze(0) >= n.to(out.device).reshape(-1, 1)
+    out[padded] = mask_value
+    return out
+
+
+def tiebreak_argsort(x: _torch.FloatTensor, descending: bool = True,
+                     generator: Optional[_torch.Generator] = None) -> _torch.LongTensor:
+    """Per-row argsort with ties broken by a random column permutation (reference :29-45)."""
+    kwargs = {} if generator is None else {"generator": generator}
+    perm = _torch.randperm(x.shape[1], device=x.device, **kwargs)
+    order = _torch.argsort(x.index_select(1, perm), dim=1, descending=descending)
+    return perm[order]
+
+
+def rank_by_score(scores: _torch.FloatTensor, n: _torch.LongTensor,
+                  generator: Optional[_torch.Generator] = None) -> _torch.LongTensor:
+    """Ranks documents by descending score with padded documents last (reference :48-64).
+
+    Runs ``ltr_rank_by_score``.  Ties are broken lowest-index-first and padded documents
+    keep index order; ``generator`` is accepted for signature compatibility and ignored
+    (the reference draws a random tie-breaking permutation from it).
+    """
+    del generator
+    return _ops.rank_by_score(scores, n)
+
+
+def batch_pairs(x: _torch.Tensor) -> _torch.Tensor:
+    """``p[b, i, j, 0] = x[b, i]``, ``p[b, i, j, 1] = x[b, j]`` (reference :94-119).
+
+    Provided for API compatibility only: the losses never build this ``(B, L, L, 2)``
+    tensor, they generate pairs on chip.
+    """
+    if x.dim() == 3:
+        x = x.reshape(x.shape[0], x.shape[1])
+    L = x.shape[1]
+    first = x.unsqueeze(2).expand(-1, L, L)
+    second = x.unsqueeze(1).expand(-1, L, L)
+    return _torch.stack((first, second), dim=3)
