@@ -1,0 +1,524 @@
+#!/usr/bin/env python
+"""Benchmark of the loss hot path: `loss = fn(scores, relevance, n); loss.sum().backward()`.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one forward+backward pass of the hot path over one padded batch of synthetic
+queries (BASELINE.json metric "loss fwd+bwd queries/sec at (B, L)").  The default workload
+is BASELINE.json configs[1]: LambdaNDCGLoss2, B=4096 queries x L=128 documents per GPU, fp32,
+n ~ U[L/2, L], 5 relevance grades.  Successive steps use different batches of a resident
+pool that is larger than the 126 MB L2, so no step finds its inputs in cache.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (the fused loss+gradient kernel) vs the measured HBM peak
+  issue_roofline  the same kernel vs the FP32-issue / MUFU pair-rate ceiling, which is the
+                binding limit of every O(L^2) loss
+  cpu_baseline  the CPU oracle (a C port of the reference algorithm; the reference itself is
+                Python and cannot travel to the GPU box) on this host's cores, bounded sample
+  e2e           same metric through the public API with pinned HOST tensors: H2D of the inputs
+                and D2H of loss + gradient inside the timed region
+  clocks        SM clock / throttle reasons sampled during the timed region
+`--impl reference` times the CPU oracle port with all host threads on the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 * 1024 * 1024
+
+# name -> (loss, B per GPU, L, relevance distribution)
+CONFIGS = {
+    "c2": dict(loss="LambdaNDCGLoss2", B=4096, L=128, workload="LambdaNDCGLoss2 synthetic (B=4096, L=128) fp32"),
+    "c3": dict(loss="PairwiseDCGHingeLoss", B=1024, L=1024,
+               workload="PairwiseDCGHingeLoss synthetic (B=1024, L=1024) fp32"),
+    "c4": dict(loss="ListNetLoss", B=8192, L=200, skew=True,
+               workload="ListNet synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
+    "c5": dict(loss="LambdaNDCGLoss2", B=65536, L=512, strong=True,
+               workload="LambdaNDCGLoss2 synthetic (B=65536, L=512) query-sharded"),
+    "ns": dict(loss="LambdaNDCGLoss2", B=4096, L=1024,
+               workload="LambdaNDCGLoss2 synthetic (B=4096, L=1024) fp32 (north-star point)"),
+}
+ORACLE_MODE = {"LambdaNDCGLoss2": ("lambda", "ndcg2"), "LambdaNDCGLoss1": ("lambda", "ndcg1"),
+               "LambdaARPLoss1": ("lambda", "arp1"), "LambdaARPLoss2": ("lambda", "arp2"),
+               "PairwiseHingeLoss": ("additive", "hinge"), "PairwiseDCGHingeLoss": ("additive", "dcg_hinge"),
+               "PairwiseLogisticLoss": ("additive", "logistic"), "ListNetLoss": ("listnet", None)}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graphs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_batch_numpy(seed, B, L, skew=False):
+    """Synthetic padded batch: scores randn, n ~ U[L/2, L], relevance uniform
+    over 5 grades (or MSLR-like skew), padded relevance zeroed, padded scores left random."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    scores = rng.standard_normal((B, L), dtype=np.float32)
+    n = rng.integers(L // 2, L + 1, size=B, dtype=np.int64)
+    if skew:
+        rel = rng.choice(5, size=(B, L), p=[.52, .32, .13, .02, .01]).astype(np.int64)
+    else:
+        rel = rng.integers(0, 5, size=(B, L), dtype=np.int64)
+    rel[np.arange(L)[None, :] >= n[:, None]] = 0
+    return scores, rel, n
+
+
+def valid_pairs(n):
+    import numpy as np
+    n = np.asarray(n, dtype=np.float64)
+    return float((n * (n - 1) / 2).sum())
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, cfg, rank, world):
+    """CPU oracle port of the reference algorithm, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    family, mode = ORACLE_MODE[cfg["loss"]]
+    L = cfg["L"]
+    # bounded sample: a slice of the workload's batch sized for ~1 s per step
+    probe_B = 64
+    s, y, n = make_batch_numpy(1234, probe_B, L, cfg.get("skew", False))
+
+    def step(s, y, n):
+        if family == "lambda":
+            return oracle.lambda_loss(mode, s, y, n)
+        if family == "additive":
+            return oracle.pairwise_additive(mode, s, y, n)
+        return oracle.listnet(s, y, n)
+
+    step(s, y, n)
+    t0 = time.perf_counter()
+    step(s, y, n)
+    per_q = (time.perf_counter() - t0) / probe_B
+    sample_B = int(max(threads * 8, min(cfg["B"], 1.0 / max(per_q, 1e-9))))
+    s, y, n = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
+    for _ in range(min(args.warmup, 3)):
+        step(s, y, n)
+    steps = max(1, min(args.steps, 30))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(s, y, n)
+    dt = time.perf_counter() - t0
+    qps = sample_B * steps / dt
+    sample = (f"{sample_B} of the {cfg['B']} queries of one batch per step, {steps} steps; "
+              f"oracle/ltr_oracle.c (C port of the reference algorithm, OpenMP over queries)")
+    line = {
+        "impl": "reference", "metric": "loss fwd+bwd queries/sec", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "loss": cfg["loss"], "B_per_step": sample_B, "L": L},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every ~20 ms (NVML)."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, torch_device_index):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.nv = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append(mhz)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+
+    def summary(self, window):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "window": "unavailable: " + getattr(self, "err", "no samples")}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "window": window}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, cfg, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pytorchltr_b200.loss as ltr_loss
+    from pytorchltr_b200 import _lib, _ops
+    from pytorchltr_b200.distributed import global_sum_count, shard_bounds
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = cfg["L"]
+    if cfg.get("strong"):
+        lo, hi = shard_bounds(cfg["B"], rank, world)
+        B = hi - lo
+        scaling = "strong"
+    else:
+        B = cfg["B"]
+        scaling = "weak"
+    loss_fn = getattr(ltr_loss, cfg["loss"])()
+    family, mode = ORACLE_MODE[cfg["loss"]]
+
+    # ---- resident pool of distinct batches, larger than L2 ---------------------------------
+    in_bytes = B * L * 12 + B * 8
+    pool_n = max(4, -(-2 * L2_BYTES // in_bytes))
+    pool_n = min(pool_n, 64)
+    pool, pairs_per_batch = [], []
+    for i in range(pool_n):
+        s, y, n = make_batch_numpy(1234 + 1000 * rank + i, B, L, cfg.get("skew", False))
+        pairs_per_batch.append(valid_pairs(n))
+        pool.append((torch.from_numpy(s).to(dev).requires_grad_(True), torch.from_numpy(y).to(dev),
+                     torch.from_numpy(n).to(dev)))
+    pool_bytes = pool_n * in_bytes
+    torch.cuda.synchronize()
+
+    red = torch.zeros(2, device=dev)
+
+    def step(i):
+        s, y, n = pool[i % pool_n]
+        s.grad = None
+        out = loss_fn(s, y, n)
+        if world > 1:
+            # the path's only exchange: [sum loss, #queries] across the query shards
+            red.copy_(global_sum_count(out))
+        out.sum().backward()
+        return out
+
+    # ---- CUDA graphs: one per pool entry (launch-bound otherwise: ~25 us of GPU work/step) ---
+    graphs = None
+    launch = "eager"
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    step(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graphs = []
+            for i in range(pool_n):
+                g = torch.cuda.CUDAGraph()
+                pool[i][0].grad = None
+                with torch.cuda.graph(g):
+                    step(i)
+                graphs.append(g)
+            launch = "cuda_graph"
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); falling back to eager\n")
+            graphs = None
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % pool_n].replay()
+        else:
+            step(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        run_step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        run_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clock_window = "timed region"
+    if len(sampler.samples) < 5:
+        # the timed region was shorter than a few NVML periods: keep the same load running
+        t_end = time.perf_counter() + 0.5
+        i = 0
+        while time.perf_counter() < t_end:
+            run_step(i)
+            i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        clock_window = "timed region + 0.5 s of the same load"
+    sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_queries = B * world if not cfg.get("strong") else cfg["B"]
+    value = total_queries * args.steps / (ms * 1e-3)
+
+    # parity spot check of the timed path (not timed): last batch vs the oracle on a sample
+    parity = None
+    if rank == 0:
+        import oracle
+        s, y, n = pool[0]
+        idx = np.arange(0, B, max(1, B // 16))
+        run_step(0)
+        torch.cuda.synchronize()
+        sn, yn, nn = s.detach().cpu().numpy()[idx], y.cpu().numpy()[idx], n.cpu().numpy()[idx]
+        if family == "lambda":
+            rl, rg = oracle.lambda_loss(mode, sn, yn, nn)
+        elif family == "additive":
+            rl, rg = oracle.pairwise_additive(mode, sn, yn, nn)
+        else:
+            rl, rg = oracle.listnet(sn, yn, nn)
+        got = s.grad.detach().cpu().double().numpy()[idx]
+        gerr = float((np.abs(got - rg) / (np.abs(rg).max(axis=1, keepdims=True) + 1e-30)).max())
+        parity = {"max_grad_err_rel_to_rowmax": gerr, "queries_checked": int(len(idx)), "ok": gerr <= 1e-5}
+
+    # ---- dominant kernel alone: the fused loss + gradient kernel -----------------------------
+    lib_family = {"lambda": _lib.FAMILY_LAMBDA, "additive": _lib.FAMILY_ADDITIVE,
+                  "listnet": _lib.FAMILY_LISTNET}[family]
+    lib_mode = {"ndcg2": _lib.LAM_NDCG2, "ndcg1": _lib.LAM_NDCG1, "arp1": _lib.LAM_ARP1,
+                "arp2": _lib.LAM_ARP2, "hinge": _lib.ADD_HINGE, "dcg_hinge": _lib.ADD_DCG_HINGE,
+                "logistic": _lib.ADD_LOGISTIC, None: 0}[mode]
+    lib = _lib.lib()
+    loss_buf = torch.empty(B, device=dev)
+    grad_buf = torch.empty(B, L, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def kernel_only(i):
+        s, y, n = pool[i % pool_n]
+        if lib_family == _lib.FAMILY_LAMBDA:
+            rc = lib.ltr_lambda(lib_mode, s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L, 1.0,
+                                loss_buf.data_ptr(), grad_buf.data_ptr(), None, None, st)
+        elif lib_family == _lib.FAMILY_ADDITIVE:
+            rc = lib.ltr_pairwise_additive(lib_mode, s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L,
+                                           1.0, loss_buf.data_ptr(), grad_buf.data_ptr(), None, st)
+        else:
+            rc = lib.ltr_listnet(s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L,
+                                 loss_buf.data_ptr(), grad_buf.data_ptr(), None, st)
+        _lib.check(rc)
+
+    for i in range(8):
+        kernel_only(i)
+    torch.cuda.synchronize()
+    reps = max(1, min(20, 2000 // pool_n))
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for r in range(reps):
+        for i in range(pool_n):
+            kernel_only(i)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / (reps * pool_n)
+    alg_bytes = B * (16 * L + 16)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.config, {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "fused loss+gradient kernel (ltr_lambda / ltr_pairwise_additive / ltr_listnet)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src}
+    issue = None
+    if family != "listnet":
+        mean_pairs = sum(pairs_per_batch) / len(pairs_per_batch)
+        sm_hz = (sampler.max_mhz or 1965) * 1e6
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        # 3 MUFU (ex2, rcp, lg2) per unordered pair at 16 MUFU lanes / clk / SM (hinge: FP32 issue,
+        # ~6 lane-ops per pair at 128 lanes / clk / SM)
+        per_pair_clk = (6.0 / 128.0) if "Hinge" in cfg["loss"] else (3.0 / 16.0)
+        peak_pairs = sms * sm_hz / per_pair_clk
+        ach_pairs = mean_pairs / (kernel_ms * 1e-3)
+        issue = {"bound": "mufu" if "Hinge" not in cfg["loss"] else "fp32_issue",
+                 "achieved": ach_pairs, "peak": peak_pairs, "unit": "unordered pairs/s",
+                 "frac": ach_pairs / peak_pairs, "pairs_per_launch": mean_pairs,
+                 "note": "binding roofline of the O(L^2) losses (SURVEY.md F4); peak derived from "
+                         "SM count x max SM clock x pipe width"}
+
+    # ---- e2e: public API, pinned host tensors in, host loss + gradient out -------------------
+    e2e = None
+    if not args.no_e2e:
+        host_n = 4
+        host_pool = []
+        for i in range(host_n):
+            s, y, n = make_batch_numpy(99 + 1000 * rank + i, B, L, cfg.get("skew", False))
+            host_pool.append((torch.from_numpy(s).pin_memory().requires_grad_(True),
+                              torch.from_numpy(y).pin_memory(), torch.from_numpy(n).pin_memory()))
+
+        def e2e_step(i):
+            s, y, n = host_pool[i % host_n]
+            s.grad = None
+            out = loss_fn(s, y, n)          # H2D scores/relevance/n, kernel, D2H loss
+            out.sum().backward()            # H2D g, scale kernel, D2H gradient
+            return out
+
+        e_steps = max(5, min(args.steps, 100))
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": total_queries * e_steps / dt, "unit": "queries/s",
+               "h2d_bytes_per_step": B * L * 12 + B * 8 + B * 4, "d2h_bytes_per_step": B * 4 + B * L * 4,
+               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "path": "loss_fn(pinned CPU tensors).sum().backward(): results returned as CPU tensors"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        threads = oracle.max_threads()
+        s, y, n = make_batch_numpy(1234, min(B, 64), L, cfg.get("skew", False))
+
+        def ostep(s, y, n):
+            if family == "lambda":
+                oracle.lambda_loss(mode, s, y, n)
+            elif family == "additive":
+                oracle.pairwise_additive(mode, s, y, n)
+            else:
+                oracle.listnet(s, y, n)
+
+        ostep(s, y, n)
+        t0 = time.perf_counter()
+        ostep(s, y, n)
+        per_q = (time.perf_counter() - t0) / len(n)
+        sample_B = int(max(threads * 8, min(4 * B, 5.0 / max(per_q, 1e-9))))
+        s, y, n = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
+        t0 = time.perf_counter()
+        ostep(s, y, n)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sample_B / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                        "sample": f"{sample_B} queries of the same synthetic workload in one call "
+                                  f"({dt:.1f} s wall), oracle/ltr_oracle.c with OpenMP over queries"}
+
+    if rank == 0:
+        launches_per_step = 2  # fused loss+gradient kernel, backward row-scale kernel
+        line = {
+            "metric": "loss fwd+bwd queries/sec", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"], "loss": cfg["loss"], "B_per_gpu": B, "L": L,
+                       "global_batch": total_queries, "parallelism": f"query-sharded dp{world}",
+                       "launch": launch,
+                       "l2_policy": f"inputs larger than L2: {pool_n} distinct resident batches "
+                                    f"({pool_bytes / 2**20:.0f} MiB) visited round-robin",
+                       "n_distribution": "n ~ U[L/2, L]", "sigma": 1.0},
+            "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "clocks": sampler.summary(clock_window),
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_note": "per step: 1 fused loss+gradient kernel + 1 row-scale kernel of "
+                                 "libltr_sm100.so (plus torch's sum / ones_like fill)",
+            "parity_spot_check": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+    if world != args.gpus and rank == 0:
+        sys.stderr.write(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun "
+                         f"for N > 1; running {world} rank(s)\n")
+    run_ours(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+"""Query-sharded data parallelism for the loss / metric path.
+
+Every query (row ``b`` of the padded batch) is independent -- the reference reduces within
+a row only (loss/pairwise_additive.py:45, loss/pairwise_lambda.py:48) -- so a batch is split
+into contiguous blocks of queries, one per rank, with NO data-path collective: each rank
+runs the fused kernel on its own shard and the gradient w.r.t. its scores stays local.
+The only exchange is the 2-element ``[sum, count]`` all-reduce behind a global mean
+(NCCL over NVLink / NVSwitch for CUDA tensors, gloo for the CPU tests).
+
+The reference has no distributed code at all; this module is new surface.
+"""
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_queries: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous ``[lo, hi)`` block of queries owned by ``rank``; blocks differ by at most
+    one query and cover ``range(num_queries)`` exactly."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank {rank} / world size {world_size}")
+    base, extra = divmod(num_queries, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(scores: torch.Tensor, relevance: torch.Tensor, n: torch.Tensor,
+                rank: Optional[int] = None, world_size: Optional[int] = None):
+    """This rank's block of queries of a replicated ``(scores, relevance, n)`` batch."""
+    if rank is None:
+        rank = dist.get_rank()
+    if world_size is None:
+        world_size = dist.get_world_size()
+    lo, hi = shard_bounds(scores.shape[0], rank, world_size)
+    return scores[lo:hi], relevance[lo:hi], n[lo:hi]
+
+
+def _world(group) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def global_sum_count(per_query: torch.Tensor, group=None) -> torch.Tensor:
+    """All-reduced ``[sum over all queries of all ranks, number of queries]`` (float64 on
+    CPU / float32 on CUDA); one 2-element collective."""
+    dtype = torch.float32 if per_query.is_cuda else torch.float64
+    # built from device-side fills only (no host->device copy): CUDA-graph capturable
+    buf = torch.empty(2, dtype=dtype, device=per_query.device)
+    buf[0] = per_query.detach().sum().to(dtype)
+    buf[1] = float(per_query.numel())
+    if _world(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+def global_mean(per_query: torch.Tensor, group=None) -> torch.Tensor:
+    """Mean of a per-query quantity (a loss or a metric) over the queries of ALL ranks."""
+    buf = global_sum_count(per_query, group)
+    return (buf[0] / buf[1].clamp(min=1.0)).to(per_query.dtype)
+
+
+def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.Tensor,
+                      n: torch.Tensor, group=None) -> torch.Tensor:
+    """Global mean loss over the query shards of all ranks.
+
+    ``loss_fn(scores, relevance, n)`` runs on the local shard only.  The returned scalar
+    equals the mean over every query of every rank; its backward gives each rank
+    ``d mean / d scores_local = grad_local / B_global`` (other ranks' terms do not depend
+    on the local scores), so no gradient collective is needed for the scores.
+    """
+    per_query = loss_fn(scores, relevance, n)
+    local_sum = per_query.sum()
+    buf = global_sum_count(per_query, group)
+    count = buf[1].clamp(min=1.0).to(local_sum.dtype)
+    others = (buf[0].to(local_sum.dtype) - local_sum.detach())
+    return (local_sum + others) / count
