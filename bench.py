@@ -341,7 +341,8 @@ def run_ours(args, cfg, rank, local_rank, world):
         if family == "lambda":
             rl, rg = oracle.lambda_loss(mode, sn, yn, nn)
         elif family == "additive":
-            rl, rg = oracle.pairwise_additive(mode, sn, yn, nn)
+            # hinge: float32 restatement (pairs on the kink flip between f32 and f64 rounding)
+            rl, rg = oracle.pairwise_additive(mode, sn, yn, nn, f32="hinge" in mode)
         else:
             rl, rg = oracle.listnet(sn, yn, nn)
         got = s.grad.detach().cpu().double().numpy()[idx]

@@ -42,7 +42,10 @@ def _loss_module(mode, sigma=1.0):
 
 def _oracle_loss(mode, s, y, n, sigma=1.0, f32=False):
     if mode in ADDITIVE:
-        return oracle.pairwise_additive(mode, s, y, n, sigma=sigma, f32=f32)
+        # hinge family: compare with the float32 restatement -- a pair sitting on the kink
+        # (1 - (s_i - s_j) == 0 after float32 rounding) is active in float32 and may not be in
+        # float64, which changes an integer gradient count by one
+        return oracle.pairwise_additive(mode, s, y, n, sigma=sigma, f32=f32 or "hinge" in mode)
     if mode == "listnet":
         return oracle.listnet(s, y, n)
     return oracle.lambda_loss(mode, s, y, n, sigma=sigma)
