@@ -11,7 +11,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "ltr_common.cuh"
+#include "ltr_pair_warp.cuh"
 #include "ltr_sm100.h"
 
 namespace ltr {
@@ -534,6 +538,32 @@ int launch_pair(const float* scores, const void* rel, int rel_bytes, const void*
   return LTR_OK;
 }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// LTR_KERNEL=generic forces the generic one-CTA-per-query kernel (debugging / A-B timing).
+inline bool force_generic() {
+  const char* v = getenv("LTR_KERNEL");
+  return v && strcmp(v, "generic") == 0;
+}
+
+template <int TW>
+int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                     int B, int L, float sigma, float* loss_out, float* grad_out, int64_t* ranking_out,
+                     float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+  const int threads = kWarpsPerCta * 32;
+  int per_sm = 0;
+  LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_warp_kernel<TW>, threads, 0));
+  if (per_sm < 1) return LTR_EUNSUPPORTED;
+  const long long want = (static_cast<long long>(B) + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long cap = static_cast<long long>(per_sm) * di.sms;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  const int vec_ok = (L % 4 == 0) && aligned16(scores) && aligned16(rel) && (!grad_out || aligned16(grad_out));
+  pair_warp_kernel<TW><<<grid, threads, 0, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, vec_ok,
+                                                 loss_out, grad_out, ranking_out, loss_sum);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,
                   int n_bytes, int B, int L, float sigma, float* loss_out, float* grad_out,
                   int64_t* ranking_out, float* loss_sum, void* stream) {
@@ -546,6 +576,18 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (L <= kWarpL && !force_generic()) {
+    // sigmoid-weighted pair losses on short lists: one warp per query, every pair once
+    if (pm == PM_LOGISTIC)
+      return launch_pair_warp<TW_UNIT>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
+                                       ranking_out, loss_sum, st, di);
+    if (pm == PM_ARP2)
+      return launch_pair_warp<TW_DIFF>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
+                                       ranking_out, loss_sum, st, di);
+    if (pm == PM_NDCG2)
+      return launch_pair_warp<TW_DELTA>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
+                                        ranking_out, loss_sum, st, di);
+  }
 #define LTR_CASE(M)                                                                               \
   case M:                                                                                         \
     return launch_pair<M>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,    \

@@ -1,0 +1,189 @@
+// ltr_pair_tiles.cuh -- register-tiled O(L^2) pair evaluation, every unordered pair ONCE.
+//
+// Used by the sigmoid-weighted losses whose pair weight is symmetric and whose winner is
+// decided by relevance (PairwiseLogisticLoss, LambdaARPLoss2, LambdaNDCGLoss2):
+//
+//     loss_b  = sum_{rel_i > rel_j} w_ij * log2(1 + exp(-sigma (s_i - s_j)))
+//     lambda  = sigma / ln2 * w_ij * sigmoid(-sigma (s_winner - s_loser))
+//     grad[winner] -= lambda,  grad[loser] += lambda
+//
+// Layout.  The query's documents sit in RANK order (descending score).  They are cut into C
+// chunks of R consecutive ranks; lane l owns chunk l as ROWS (in registers).  In step m every
+// lane pairs its rows with the COLUMNS of chunk (l + m) mod C, read from shared memory, so the
+// C lanes cover every unordered chunk pair exactly once in floor(C/2) steps (plus the
+// within-chunk triangle).  Row gradients accumulate in registers; column gradients of a step
+// are added to a warp-private shared array with one vector read-modify-write (every lane
+// touches a different chunk, so there are no conflicts and no atomics).
+//
+// Pair math (2 MUFU + ~14 FP32 ops per pair).  exp(-sigma (s_i - s_j)) is FACTORED as
+// a_i * b_j with a_i = exp(-sigma (s_i - mid)), b_j = exp(+sigma (s_j - mid)) computed once per
+// document (double-precision exponent, so the product is good to a few float32 ulps); the pair
+// then needs only rcp and lg2 on the MUFU pipe.  With q = a_i b_j and p = 1 + q:
+//     i wins (G_i > G_j):  sigmoid(-x) = q / p,  log2(1 + e^-x) = lg2(p)
+//     j wins (G_i < G_j):  sigmoid(-x) = 1 / p,  log2(1 + e^-x) = lg2(p) + (e_i - e_j)
+// (e = sigma (s - mid) log2 e, so e_i - e_j = -lg2 q).  The factored form needs
+// sigma * (max - min) * log2 e <= kFactoredRange so that q stays finite; queries outside that
+// range take the stable form exp(-|x|) (3 MUFU) instead.
+//
+// Padding costs nothing per pair: a padded document is given b = 0 and G = 0 as a column and
+// a = 0, G = +BIG as a row, which sends every pair that involves it down the "i wins" branch
+// with q = 0, i.e. an exact zero contribution to loss and gradients.  (Stable form: padding is
+// a document of gain 0 scored -1e30, whose pairs evaluate to exp(-1e30) = 0 exactly.)
+//
+// delta_|i-j| (LambdaNDCGLoss2, pairwise_lambda.py:206-211) only depends on the rank distance:
+// a step with chunk distance d needs the 2R-1 values delta[|R d + e|], e in (-R, R), which are
+// fetched as two 128-bit loads from a per-R window table built once per CTA.
+#pragma once
+
+#include "ltr_common.cuh"
+
+namespace ltr {
+
+constexpr float kFactoredRange = 64.0f;    // max |sigma| * (max - min) * log2(e) for q = a_i * b_j
+constexpr float kBigGain = 1.0e30f;
+
+// What a column (and, before it is pulled into registers, a row) looks like in shared memory.
+struct __align__(16) PairItem {
+  float a;   // exp(-sigma (s - mid))   [stable form: sigma * s]
+  float b;   // exp(+sigma (s - mid))   [stable form: unused]
+  float e;   // sigma (s - mid) log2 e  [stable form: unused]
+  float g;   // weight basis: normalised gain G (NDCG2) or float(rel) (ARP2, logistic)
+};
+
+enum : int { TW_UNIT = 0, TW_DIFF = 1, TW_DELTA = 2 };   // w = 1 | |g_i - g_j| | delta |g_i - g_j|
+
+// One pair.  racc/cacc receive +lambda' for the column and -lambda' for the row, where
+// lambda' > 0 when the row wins; the caller scales by sigma / ln 2 at the end.
+template <int TW, bool FACTORED>
+__device__ __forceinline__ void pair_once(float ra, float re, float rg, const PairItem& c, float dw,
+                                          float& lacc, float& racc, float& cacc) {
+  const float gd = rg - c.g;
+  float ws;   // signed weight, > 0 when the row (i) wins
+  if constexpr (TW == TW_DELTA) ws = dw * gd;
+  else if constexpr (TW == TW_DIFF) ws = gd;
+  else ws = fminf(fmaxf(gd, -1.0f), 1.0f);   // integer grades: sign(gd)
+  float sg, lp;
+  if constexpr (FACTORED) {
+    const float q = ra * c.b;
+    const float p = q + 1.0f;
+    const float r = rcp_approx(p);
+    const float lg = lg2_approx(p);
+    const float qr = q * r;
+    const bool iwins = gd > 0.0f;
+    sg = iwins ? qr : r;
+    const float t1 = (c.e - re) - lg;        // -(lg2(p) + (e_i - e_j))
+    lp = iwins ? lg : t1;                    // ws * lp == |ws| * log2(1 + e^-x)
+  } else {
+    // stable form: ra = sigma * s_i, c.a = sigma * s_j
+    const float d = ra - c.a;                // x if the row wins, -x otherwise
+    const float u = -fabsf(d) * kLog2e;
+    const float t = ex2_approx(u);
+    const float p = 1.0f + t;
+    const float r = rcp_approx(p);
+    const float lg = lg2_approx(p);
+    const bool iwins = gd > 0.0f;
+    const bool xneg = iwins ? d < 0.0f : d > 0.0f;   // x = sigma (s_winner - s_loser) < 0
+    sg = xneg ? r : t * r;
+    const float l = xneg ? lg - u : lg;
+    lp = iwins ? l : -l;
+  }
+  lacc = fmaf(ws, lp, lacc);
+  const float lam = ws * sg;
+  racc -= lam;
+  cacc += lam;
+}
+
+// Window tables: for R rows per chunk and chunk distance d in (-kMaxChunks, kMaxChunks), entry
+// (d + kMaxChunks) holds delta[|R d + e|] at slot e + R - 1 (8 floats, the last ones unused).
+constexpr int kMaxChunks = 32;
+__host__ __device__ constexpr int window_table_floats() { return (2 * kMaxChunks + 1) * 8; }
+
+// All-pairs pass over one "ring" of C <= 32 chunks of R ranks held by one warp (C*R >= n).
+//   items : rank-ordered PairItems of this query in shared memory, padded to C*R entries
+//   gcol  : warp-private column-gradient accumulators [C*R], zero on entry
+//   wtab  : window table for this R (TW_DELTA only)
+// Returns per-lane partial loss; racc[r] holds -sum lambda' of the lane's rows.
+template <int TW, bool FACTORED, int R>
+__device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, float* __restrict__ gcol,
+                                           const float* __restrict__ wtab, int C, int n, int lane,
+                                           float (&racc)[R]) {
+  const bool active = lane < C;
+  const int me = active ? lane : 0;
+  float ra[R], re[R], rg[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const PairItem it = items[me * R + r];
+    const bool valid = active && (me * R + r < n);
+    if constexpr (FACTORED) {
+      ra[r] = valid ? it.a : 0.0f;
+      rg[r] = valid ? it.g : kBigGain;
+    } else {
+      ra[r] = it.a;                          // stable form: padding is already (-1e30, gain 0)
+      rg[r] = it.g;
+    }
+    re[r] = it.e;
+    racc[r] = 0.0f;
+  }
+  float lacc = 0.0f;
+
+  // within-chunk triangle (rank distance c - r > 0)
+  {
+    float dwin[8];
+    if constexpr (TW == TW_DELTA) {
+      const float4* w4 = reinterpret_cast<const float4*>(wtab + kMaxChunks * 8);
+      const float4 w0 = w4[0], w1 = w4[1];
+      dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
+      dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = r + 1; c < R; ++c) {
+        const PairItem col = items[me * R + c];
+        float dw = 1.0f;
+        if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
+        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], col, dw, lacc, racc[r], racc[c]);
+      }
+    }
+  }
+
+  const int steps = C >> 1;
+  for (int m = 1; m <= steps; ++m) {
+    int pc = me + m;
+    if (pc >= C) pc -= C;
+    const bool commit = active && !((2 * m == C) && lane >= m);   // even ring: last step is shared
+    float dwin[8];
+    if constexpr (TW == TW_DELTA) {
+      const float4* w4 = reinterpret_cast<const float4*>(wtab + (pc - me + kMaxChunks) * 8);
+      const float4 w0 = w4[0], w1 = w4[1];
+      dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
+      dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
+    }
+    PairItem col[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) col[c] = items[pc * R + c];
+    float tl = 0.0f, tr[R], tc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { tr[r] = 0.0f; tc[r] = 0.0f; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        float dw = 1.0f;
+        if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
+        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], col[c], dw, tl, tr[r], tc[c]);
+      }
+    }
+    if (commit) {
+      lacc += tl;
+#pragma unroll
+      for (int r = 0; r < R; ++r) racc[r] += tr[r];
+#pragma unroll
+      for (int c = 0; c < R; ++c) gcol[pc * R + c] += tc[c];
+    }
+    __syncwarp();
+  }
+  return active ? lacc : 0.0f;
+}
+
+}  // namespace ltr
