@@ -14,6 +14,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "ltr_common.cuh"
 #include "ltr_pair_warp.cuh"
 #include "ltr_sm100.h"
@@ -546,6 +548,47 @@ inline bool force_generic() {
   return v && strcmp(v, "generic") == 0;
 }
 
+// Work queues of the warp-per-query kernel: {next query, warps done} pairs in device memory.
+// A launch takes the next slot round-robin; the kernel leaves its slot zeroed when its last
+// warp retires, so a slot is clean again long before the rotation comes back to it.
+constexpr int kQueueSlots = 1024;
+__device__ unsigned int g_work_queues[2 * kQueueSlots];
+
+inline int next_queue(unsigned int** out) {
+  static std::atomic<unsigned int> counter{0};
+  unsigned int* base = nullptr;
+  LTR_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_work_queues));
+  *out = base + 2 * (counter.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
+  return LTR_OK;
+}
+
+// Score-independent tables (delta windows, discounts, ideal-DCG prefix sums): filled on first
+// use per device by a kernel on the caller's stream.  If that first use is being captured into
+// a CUDA graph the fill becomes a node of that graph and is repeated by the next eager call
+// (it is idempotent), so the tables are always written before any kernel that reads them runs.
+__device__ PairTables g_pair_tables;
+
+inline int pair_tables(cudaStream_t st, const PairTables** out) {
+  static std::atomic<bool> ready[64];
+  int dev = 0;
+  LTR_CUDA(cudaGetDevice(&dev));
+  PairTables* t = nullptr;
+  LTR_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&t), g_pair_tables));
+  if (dev < 0 || dev >= 64 || !ready[dev].load(std::memory_order_acquire)) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    LTR_CUDA(cudaStreamIsCapturing(st, &cap));
+    init_pair_tables_kernel<<<1, 1024, 0, st>>>(t);
+    LTR_CUDA(cudaGetLastError());
+    if (cap == cudaStreamCaptureStatusNone && dev >= 0 && dev < 64) {
+      // later launches may be on other streams: make the fill visible to all of them
+      LTR_CUDA(cudaStreamSynchronize(st));
+      ready[dev].store(true, std::memory_order_release);
+    }
+  }
+  *out = t;
+  return LTR_OK;
+}
+
 template <int TW>
 int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
                      int B, int L, float sigma, float* loss_out, float* grad_out, int64_t* ranking_out,
@@ -558,8 +601,14 @@ int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const 
   const long long cap = static_cast<long long>(per_sm) * di.sms;
   const int grid = static_cast<int>(want < cap ? want : cap);
   const int vec_ok = (L % 4 == 0) && aligned16(scores) && aligned16(rel) && (!grad_out || aligned16(grad_out));
+  unsigned int* queue = nullptr;
+  int rc = next_queue(&queue);
+  if (rc != LTR_OK) return rc;
+  const PairTables* tabs = nullptr;
+  rc = pair_tables(st, &tabs);
+  if (rc != LTR_OK) return rc;
   pair_warp_kernel<TW><<<grid, threads, 0, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, vec_ok,
-                                                 loss_out, grad_out, ranking_out, loss_sum);
+                                                 loss_out, grad_out, ranking_out, loss_sum, queue, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }

@@ -32,7 +32,8 @@
 //
 // delta_|i-j| (LambdaNDCGLoss2, pairwise_lambda.py:206-211) only depends on the rank distance:
 // a step with chunk distance d needs the 2R-1 values delta[|R d + e|], e in (-R, R), which are
-// fetched as two 128-bit loads from a per-R window table built once per CTA.
+// fetched as two 128-bit read-only loads from a per-R window table (PairTables, built once per
+// device and L1-resident afterwards).
 #pragma once
 
 #include "ltr_common.cuh"
@@ -100,7 +101,7 @@ __host__ __device__ constexpr int window_table_floats() { return (2 * kMaxChunks
 
 // All-pairs pass over one "ring" of C <= 32 chunks of R ranks held by one warp (C*R >= n).
 //   items : rank-ordered PairItems of this query in shared memory, padded to C*R entries
-//   gcol  : warp-private column-gradient accumulators [C*R], zero on entry
+//   gcol  : warp-private column-gradient accumulators, chunk c at gcol[4c .. 4c+R), zero on entry
 //   wtab  : window table for this R (TW_DELTA only)
 // Returns per-lane partial loss; racc[r] holds -sum lambda' of the lane's rows.
 template <int TW, bool FACTORED, int R>
@@ -131,7 +132,7 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
     float dwin[8];
     if constexpr (TW == TW_DELTA) {
       const float4* w4 = reinterpret_cast<const float4*>(wtab + kMaxChunks * 8);
-      const float4 w0 = w4[0], w1 = w4[1];
+      const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
       dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
       dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
     }
@@ -148,14 +149,16 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
   }
 
   const int steps = C >> 1;
+  // even ring: the last step pairs chunk l with l + C/2 from both ends; only the lower half commits
+  const bool dup_last = ((C & 1) == 0) && lane >= steps;
+  int pc = me;
   for (int m = 1; m <= steps; ++m) {
-    int pc = me + m;
-    if (pc >= C) pc -= C;
-    const bool commit = active && !((2 * m == C) && lane >= m);   // even ring: last step is shared
+    pc = pc + 1 == C ? 0 : pc + 1;
+    const bool commit = active && !(dup_last && m == steps);
     float dwin[8];
     if constexpr (TW == TW_DELTA) {
-      const float4* w4 = reinterpret_cast<const float4*>(wtab + (pc - me + kMaxChunks) * 8);
-      const float4 w0 = w4[0], w1 = w4[1];
+      const float4* w4 = reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2;
+      const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
       dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
       dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
     }
@@ -178,8 +181,21 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
       lacc += tl;
 #pragma unroll
       for (int r = 0; r < R; ++r) racc[r] += tr[r];
+      // column gradients: chunk pc owns gcol[4 pc .. 4 pc + 3] (one vector read-modify-write)
+      if constexpr (R == 4) {
+        float4* g4 = reinterpret_cast<float4*>(gcol) + pc;
+        float4 g = *g4;
+        g.x += tc[0]; g.y += tc[1]; g.z += tc[2]; g.w += tc[3];
+        *g4 = g;
+      } else if constexpr (R == 2) {
+        float2* g2 = reinterpret_cast<float2*>(gcol + pc * 4);
+        float2 g = *g2;
+        g.x += tc[0]; g.y += tc[1];
+        *g2 = g;
+      } else {
 #pragma unroll
-      for (int c = 0; c < R; ++c) gcol[pc * R + c] += tc[c];
+        for (int c = 0; c < R; ++c) gcol[pc * 4 + c] += tc[c];
+      }
     }
     __syncwarp();
   }

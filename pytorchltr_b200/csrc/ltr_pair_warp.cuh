@@ -1,60 +1,34 @@
 // ltr_pair_warp.cuh -- one WARP per query for list sizes up to 128 (the headline (4096, 128)
 // workload): no CTA barrier in the steady state, everything of a query lives in the warp's
-// registers plus 3.5 KB of shared memory.
+// registers plus ~4 KB of shared memory.
 //
-// Per query: 128-bit loads of the padded row -> in-register bitonic argsort of (score, index)
-// keys (rank_by_score, utils/tensor_operations.py:48-64) -> optional second sort of the
-// relevance grades for the ideal DCG (_max_dcg, pairwise_lambda.py:231-241) -> per-document
-// factors into shared memory in rank order -> ring_pass (ltr_pair_tiles.cuh) -> gradient
-// scattered back to document order (backward of the gather, pairwise_lambda.py:69) and stored
-// with 128-bit writes.
+// Per query: 128-bit loads of the padded row -> in-register bitonic argsort
+// (rank_by_score, utils/tensor_operations.py:48-64) -> ideal DCG from a grade histogram
+// (_max_dcg, pairwise_lambda.py:231-241) -> per-document factors into shared memory in rank
+// order -> ring_pass (ltr_pair_tiles.cuh) -> gradient scattered back to document order
+// (backward of the gather, pairwise_lambda.py:69) and stored with 128-bit writes.
+//
+// Queries are handed out dynamically (one atomic per query on a self-resetting device
+// counter): list sizes vary by 2x, pair counts by 4x, so a static split leaves most of the SMs
+// idle in the tail.
 #pragma once
 
 #include "ltr_pair_tiles.cuh"
+#include "ltr_sm100.h"
 
 namespace ltr {
 
 constexpr int kWarpL = 128;          // max list size of the warp-per-query kernel
 constexpr int kWarpE = 4;            // elements per lane in the sort (32 * 4 = 128)
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 
-// ---- warp-wide bitonic sort of 32*E 64-bit keys, element index = lane * E + r, ascending ----
+// direction predicates of the bitonic network for element index lane * E + r
 template <int E>
-__device__ __forceinline__ void warp_bitonic_sort64(uint64_t (&k)[E], int lane) {
-#pragma unroll
-  for (int size = 2; size <= 32 * E; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride < E) {
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const int q = r ^ stride;
-          if (q > r) {
-            const bool up = (((lane * E + r) & size) == 0);
-            const uint64_t a = k[r], b = k[q];
-            const bool sw = (a > b) == up;
-            k[r] = sw ? b : a;
-            k[q] = sw ? a : b;
-          }
-        }
-      } else {
-        const int ls = stride / E;
-        const bool lower = (lane & ls) == 0;
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const uint64_t mine = k[r];
-          const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, ls);
-          const bool up = (((lane * E + r) & size) == 0);
-          const bool keep_min = (lower == up);
-          const bool other_smaller = other < mine;
-          k[r] = (keep_min == other_smaller) ? other : mine;
-        }
-      }
-    }
-  }
+__device__ __forceinline__ bool bitonic_up(int lane, int r, int size) {
+  return ((lane * E + r) & size) == 0;
 }
 
-// Same for 32-bit keys (relevance grades of the ideal ranking; no payload needed).
+// ---- warp-wide bitonic sort of 32*E 32-bit keys, element index = lane * E + r, ascending ----
 template <int E>
 __device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&k)[E], int lane) {
 #pragma unroll
@@ -66,7 +40,7 @@ __device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&k)[E], int lane) 
         for (int r = 0; r < E; ++r) {
           const int q = r ^ stride;
           if (q > r) {
-            const bool up = (((lane * E + r) & size) == 0);
+            const bool up = bitonic_up<E>(lane, r, size);
             const uint32_t lo = min(k[r], k[q]), hi = max(k[r], k[q]);
             k[r] = up ? lo : hi;
             k[q] = up ? hi : lo;
@@ -74,82 +48,145 @@ __device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&k)[E], int lane) 
         }
       } else {
         const int ls = stride / E;
-        const bool lower = (lane & ls) == 0;
+        // for stride >= E the direction does not depend on r: (lane * E) & size
+        const bool keep_min = (((lane * E) & size) == 0) == ((lane & ls) == 0);
 #pragma unroll
         for (int r = 0; r < E; ++r) {
           const uint32_t other = __shfl_xor_sync(0xffffffffu, k[r], ls);
-          const bool up = (((lane * E + r) & size) == 0);
-          k[r] = (lower == up) ? min(k[r], other) : max(k[r], other);
+          k[r] = keep_min ? min(k[r], other) : max(k[r], other);
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ float score_from_desc_key(uint32_t key) {
-  const uint32_t asc = ~key;
-  const uint32_t u = (asc & 0x80000000u) ? (asc & 0x7fffffffu) : ~asc;
-  return __uint_as_float(u);
+// ---- same network on 64-bit keys: exact (score key, index) order, used when the packed
+// 32-bit sort cannot separate two scores --------------------------------------------------------
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort64(uint64_t (&k)[E], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride < E) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const int q = r ^ stride;
+          if (q > r) {
+            const bool up = bitonic_up<E>(lane, r, size);
+            const uint64_t a = k[r], b = k[q];
+            const bool sw = (a > b) == up;
+            k[r] = sw ? b : a;
+            k[q] = sw ? a : b;
+          }
+        }
+      } else {
+        const int ls = stride / E;
+        const bool keep_min = (((lane * E) & size) == 0) == ((lane & ls) == 0);
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const uint64_t mine = k[r];
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, ls);
+          k[r] = (keep_min == (other < mine)) ? other : mine;
+        }
+      }
+    }
+  }
 }
 
-struct WarpScratch {
-  PairItem items[kWarpL];   // rank order
-  float gcol[kWarpL];       // column gradients, rank order
-  int raw_y[kWarpL];        // relevance in document order; reused as the document-order gradient
+struct __align__(16) WarpScratch {
+  PairItem items[kWarpL];                  // rank order
+  __align__(16) float gcol[kWarpL];        // column gradients: chunk c owns gcol[4c .. 4c+3]
+  __align__(16) float raw_s[kWarpL];       // scores, document order; reused: rank-order gradient
+  __align__(16) int raw_y[kWarpL];         // relevance, document order; reused: document-order gradient
 };
 
-struct WarpTables {
-  float delta[kWarpL + 8];                 // delta[k] = |1/D(k) - 1/D(k+1)|
-  float disc[kWarpL];                      // D(r) = log2(2 + r)
-  float wtab[4][window_table_floats()];    // window tables for R = 1..4
+// Score-independent tables, computed once per device by init_pair_tables_kernel and read
+// through the read-only path (they stay L1-resident: ~10 KB are touched by the warp kernel).
+struct __align__(16) PairTables {
+  __align__(16) float wtab[4][window_table_floats()];   // delta windows for R = 1..4 (float4 loads)
+  double inv_disc_prefix[LTR_MAX_LIST_SIZE + 1];        // S[p] = sum_{r<p} 1 / D(r)  (ideal DCG)
+  float delta[LTR_MAX_LIST_SIZE + 8];                   // delta[k] = |1/D(k) - 1/D(k+1)|, pairwise_lambda.py:206-211
+  float disc[LTR_MAX_LIST_SIZE + 8];                    // D(r) = log2(2 + r), pairwise_lambda.py:168-170
 };
+
+__global__ void __launch_bounds__(1024) init_pair_tables_kernel(PairTables* __restrict__ t) {
+  for (int k = threadIdx.x; k < LTR_MAX_LIST_SIZE + 8; k += blockDim.x) {
+    const float d0 = log2f(2.0f + static_cast<float>(k));
+    const float d1 = log2f(3.0f + static_cast<float>(k));
+    t->disc[k] = d0;
+    t->delta[k] = fabsf(1.0f / d0 - 1.0f / d1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * window_table_floats(); i += blockDim.x) {
+    const int R = i / window_table_floats() + 1, rem = i % window_table_floats();
+    const int d = (rem >> 3) - kMaxChunks, slot = rem & 7;
+    int k = R * d + slot - (R - 1);
+    k = k < 0 ? -k : k;
+    t->wtab[R - 1][rem] = t->delta[k];
+  }
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int r = 0; r <= LTR_MAX_LIST_SIZE; ++r) {
+      t->inv_disc_prefix[r] = acc;
+      acc += 1.0 / static_cast<double>(t->disc[r]);
+    }
+  }
+}
 
 template <int TW, bool FACTORED, int R>
-__device__ __forceinline__ float ring_dispatch(WarpScratch& ws, const WarpTables& tb, int n, int lane) {
+__device__ __forceinline__ float ring_dispatch(WarpScratch& ws, const PairTables& tb, int n, int lane) {
   const int C = (n + R - 1) / R;
   float racc[R];
   const float l = ring_pass<TW, FACTORED, R>(ws.items, ws.gcol, tb.wtab[R - 1], C, n, lane, racc);
+  // rank-order gradient (unscaled): column part + row part
+  float* glin = ws.raw_s;
   if (lane < C) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) ws.gcol[lane * R + r] += racc[r];
+    for (int r = 0; r < R; ++r) glin[lane * R + r] = ws.gcol[lane * 4 + r] + racc[r];
   }
   return l;
 }
 
+__device__ __forceinline__ int clamp_i64_to_i32(long long v) {
+  const int lo = static_cast<int>(v), hi = static_cast<int>(v >> 32);
+  return hi == (lo >> 31) ? lo : (hi < 0 ? -2147483647 : 2147483647);
+}
+
+// 2^y - 1 in float32 for an integer grade (exact for |y| <= 126, like the reference's 2 ** rel - 1)
+__device__ __forceinline__ float gain_of_grade(int y) {
+  y = y < -126 ? -126 : (y > 127 ? 127 : y);
+  return __int_as_float((y + 127) << 23) - 1.0f;
+}
+
 template <int TW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
 pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, float sigma, int vec_ok,
                  float* __restrict__ loss_out, float* __restrict__ grad_out,
-                 int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum) {
-  __shared__ WarpTables tb;
+                 int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
+                 unsigned int* __restrict__ queue, const PairTables* __restrict__ tabs) {
+  const PairTables& tb = *tabs;
   __shared__ WarpScratch scratch[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
-  if constexpr (TW == TW_DELTA) {
-    for (int k = threadIdx.x; k < kWarpL + 8; k += blockDim.x) {
-      const float d0 = log2f(2.0f + static_cast<float>(k));
-      const float d1 = log2f(3.0f + static_cast<float>(k));
-      tb.delta[k] = fabsf(1.0f / d0 - 1.0f / d1);
-      if (k < kWarpL) tb.disc[k] = d0;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * window_table_floats(); i += blockDim.x) {
-      const int R = i / window_table_floats() + 1;
-      const int rem = i % window_table_floats();
-      const int d = rem / 8 - kMaxChunks, slot = rem % 8;
-      int k = R * d + slot - (R - 1);
-      k = k < 0 ? -k : k;
-      tb.wtab[R - 1][rem] = k < kWarpL + 8 ? tb.delta[k] : 0.0f;
-    }
-    __syncthreads();
-  }
-
   WarpScratch& ws = scratch[warp];
   const float gscale = sigma * kLog2e;   // lambda = sigma / ln 2 * w * sigmoid(-x)
+  // sigma * log2(e) split into two floats: e = c * k exactly to ~2^-48 relative
+  const double kd = static_cast<double>(sigma) * 1.4426950408889634;
+  const float k_hi = static_cast<float>(kd);
+  const float k_lo = static_cast<float>(kd - static_cast<double>(k_hi));
 
-  for (int b = blockIdx.x * kWarpsPerCta + warp; b < B; b += gridDim.x * kWarpsPerCta) {
+  // ---- query schedule: the first query of every warp is static (no start-up burst on the queue
+  // counter), the following ones are pulled from the device-wide queue as warps finish -----------
+  const unsigned int total_warps = gridDim.x * kWarpsPerCta;
+  unsigned int b = blockIdx.x * kWarpsPerCta + warp;
+
+  while (b < static_cast<unsigned int>(B)) {
+    unsigned int b_next = 0;
+    if (lane == 0) b_next = total_warps + atomicAdd(queue, 1u);   // consumed at the end of this iteration
+
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
 
@@ -163,13 +200,8 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         const longlong2* rp = reinterpret_cast<const longlong2*>(
             reinterpret_cast<const long long*>(rel) + base + lane * kWarpE);
         const longlong2 r0 = rp[0], r1 = rp[1];
-        const long long t[4] = {r0.x, r0.y, r1.x, r1.y};
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          long long v = t[r];
-          v = v < -2147483647LL ? -2147483647LL : (v > 2147483647LL ? 2147483647LL : v);
-          yv[r] = static_cast<int>(v);
-        }
+        yv[0] = clamp_i64_to_i32(r0.x); yv[1] = clamp_i64_to_i32(r0.y);
+        yv[2] = clamp_i64_to_i32(r1.x); yv[3] = clamp_i64_to_i32(r1.y);
       } else {
         const int4 r4 = *reinterpret_cast<const int4*>(reinterpret_cast<const int*>(rel) + base + lane * kWarpE);
         yv[0] = r4.x; yv[1] = r4.y; yv[2] = r4.z; yv[3] = r4.w;
@@ -182,54 +214,113 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         yv[r] = j < L ? load_int_clamped(rel, rel_bytes, base + j) : 0;
       }
     }
+#pragma unroll
+    for (int r = 0; r < kWarpE; ++r) {
+      ws.raw_s[lane * kWarpE + r] = sv[r];
+      ws.raw_y[lane * kWarpE + r] = yv[r];
+    }
 
     // ---- argsort by descending score; padding (and the slots beyond L) last, by index ------
-    uint64_t key[kWarpE];
+    // Fast path: 25 key bits + 7 index bits in one register.  The result is then checked
+    // against the exact (32-bit key, index) order; if two scores are closer than 128 ulps and
+    // came out in the wrong order, the exact 64-bit network is run instead.
+    uint32_t ekey[kWarpE];   // exact keys (document order for now)
+    uint32_t pk[kWarpE];
 #pragma unroll
     for (int r = 0; r < kWarpE; ++r) {
       const int j = lane * kWarpE + r;
-      ws.raw_y[j] = yv[r];
-      key[r] = pack_key(j < nb ? desc_key_f32(sv[r]) : kPadKey, j);
+      ekey[r] = j < nb ? desc_key_f32(sv[r]) : kPadKey;
+      pk[r] = (ekey[r] & 0xffffff80u) | static_cast<uint32_t>(j);
     }
-    warp_bitonic_sort64<kWarpE>(key, lane);
+    warp_bitonic_sort32<kWarpE>(pk, lane);
     __syncwarp();
-
-    // ---- ideal DCG: relevance descending over the valid documents ---------------------------
-    float inv_max_dcg = 1.0f;
-    if constexpr (TW == TW_DELTA) {
-      uint32_t yk[kWarpE];
+    int doc[kWarpE];
+    float ss[kWarpE];
+    uint64_t xk[kWarpE];
 #pragma unroll
-      for (int r = 0; r < kWarpE; ++r) yk[r] = lane * kWarpE + r < nb ? desc_key_i32(yv[r]) : kPadKey;
-      warp_bitonic_sort32<kWarpE>(yk, lane);
-      float part = 0.0f;
+    for (int r = 0; r < kWarpE; ++r) {
+      doc[r] = static_cast<int>(pk[r] & 127u);
+      ss[r] = ws.raw_s[doc[r]];
+      const int p = lane * kWarpE + r;
+      xk[r] = pack_key(p < nb ? desc_key_f32(ss[r]) : kPadKey, doc[r]);
+    }
+    {
+      const uint64_t next0 = __shfl_down_sync(0xffffffffu, xk[0], 1);
+      bool bad = (xk[0] > xk[1]) || (xk[1] > xk[2]) || (xk[2] > xk[3]) || (lane < 31 && xk[3] > next0);
+      if (__any_sync(0xffffffffu, bad)) {
+        // exact order needed: redo from the document-order keys
+#pragma unroll
+        for (int r = 0; r < kWarpE; ++r) xk[r] = pack_key(ekey[r], lane * kWarpE + r);
+        warp_bitonic_sort64<kWarpE>(xk, lane);
+#pragma unroll
+        for (int r = 0; r < kWarpE; ++r) {
+          doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
+          ss[r] = ws.raw_s[doc[r]];
+        }
+      }
+    }
+
+    // ---- ideal DCG over the valid documents --------------------------------------------------------
+    float max_dcg = 1.0f;
+    if constexpr (TW == TW_DELTA) {
+      int ymax = -2147483647, ymin = 2147483647;
 #pragma unroll
       for (int r = 0; r < kWarpE; ++r) {
-        const int p = lane * kWarpE + r;
-        if (p < nb) part += exp_gain_f32(static_cast<int>(~yk[r] ^ 0x80000000u)) / tb.disc[p];
+        if (lane * kWarpE + r < nb) { ymax = max(ymax, yv[r]); ymin = min(ymin, yv[r]); }
       }
-      float max_dcg = warp_sum(part);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+      }
+      if (ymin >= 0 && ymax < 32) {
+        // grade histogram by ballots; grade g occupies ideal ranks [start, start + cnt)
+        double acc = 0.0;
+        int start = 0;
+        for (int g = ymax; g >= 1; --g) {
+          int cnt = 0;
+#pragma unroll
+          for (int r = 0; r < kWarpE; ++r)
+            cnt += __popc(__ballot_sync(0xffffffffu, lane * kWarpE + r < nb && yv[r] == g));
+          acc += static_cast<double>(gain_of_grade(g)) *
+                 (tb.inv_disc_prefix[start + cnt] - tb.inv_disc_prefix[start]);
+          start += cnt;
+        }
+        max_dcg = static_cast<float>(acc);
+      } else {
+        uint32_t yk[kWarpE];
+#pragma unroll
+        for (int r = 0; r < kWarpE; ++r) yk[r] = lane * kWarpE + r < nb ? desc_key_i32(yv[r]) : kPadKey;
+        warp_bitonic_sort32<kWarpE>(yk, lane);
+        float part = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kWarpE; ++r) {
+          const int p = lane * kWarpE + r;
+          if (p < nb) part += exp_gain_f32(static_cast<int>(~yk[r] ^ 0x80000000u)) / tb.disc[p];
+        }
+        max_dcg = warp_sum(part);
+      }
       if (max_dcg == 0.0f) max_dcg = 1.0f;
-      inv_max_dcg = max_dcg;   // divided below exactly as the reference does (gain / max_dcg)
     }
+    const float inv_max_dcg = 1.0f / max_dcg;
 
-    // ---- rank-ordered scores / relevance, score range ----------------------------------------
-    float ss[kWarpE];
-    int ys[kWarpE], doc[kWarpE];
+    // ---- rank-ordered relevance, score range ---------------------------------------------------
+    int ys[kWarpE];
     float smax = -INFINITY, smin = INFINITY;
 #pragma unroll
     for (int r = 0; r < kWarpE; ++r) {
       const int p = lane * kWarpE + r;
-      doc[r] = static_cast<int>(key[r] & 0xffffffffu);
-      ss[r] = score_from_desc_key(static_cast<uint32_t>(key[r] >> 32));
       ys[r] = ws.raw_y[doc[r]];
       if (p < nb) { smax = fmaxf(smax, ss[r]); smin = fminf(smin, ss[r]); }
       if (ranking_out && p < L) ranking_out[base + p] = doc[r];
     }
+    // sorted: the extremes sit at ranks 0 and nb - 1, but a reduction is as cheap as finding them
     smax = warp_max(smax);
     smin = -warp_max(-smin);
     const float mid = 0.5f * (smax + smin);
     // NaN / inf scores fail this test and take the stable form
     const bool factored = fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
+    __syncwarp();   // raw_s / raw_y fully consumed: they are reused below
 
     // ---- per-document factors -> shared memory (rank order) ------------------------------------
 #pragma unroll
@@ -237,15 +328,15 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       const int p = lane * kWarpE + r;
       PairItem it;
       if (p < nb) {
-        if constexpr (TW == TW_DELTA) it.g = exp_gain_f32(ys[r]) / inv_max_dcg;
+        if constexpr (TW == TW_DELTA) it.g = gain_of_grade(ys[r]) * inv_max_dcg;
         else it.g = static_cast<float>(ys[r]);
         if (factored) {
-          const double ed = static_cast<double>(ss[r] - mid) * static_cast<double>(sigma) * 1.4426950408889634;
-          const float eh = static_cast<float>(ed);
-          const float el = static_cast<float>(ed - static_cast<double>(eh)) * kLn2;
+          const float c = ss[r] - mid;
+          const float eh = c * k_hi;
+          const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
           it.e = eh;
-          it.a = exp2f(-eh) * (1.0f - el);
-          it.b = exp2f(eh) * (1.0f + el);
+          it.a = ex2_approx(-eh) * (1.0f - el);
+          it.b = ex2_approx(eh) * (1.0f + el);
         } else {
           it.a = sigma * ss[r];
           it.b = 0.0f;
@@ -259,6 +350,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       }
       ws.items[p] = it;
       ws.gcol[p] = 0.0f;
+      ws.raw_s[p] = 0.0f;   // rank-order gradient of the ranks no ring lane owns
     }
     __syncwarp();
 
@@ -285,10 +377,12 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     // ---- gradient back to document order -----------------------------------------------------------
     if (grad_out) {
       float* gdoc = reinterpret_cast<float*>(ws.raw_y);
+      const float4 g4 = *reinterpret_cast<const float4*>(ws.raw_s + lane * kWarpE);
+      const float gl[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
       for (int r = 0; r < kWarpE; ++r) {
         const int p = lane * kWarpE + r;
-        gdoc[doc[r]] = p < nb ? ws.gcol[p] * gscale : 0.0f;
+        gdoc[doc[r]] = p < nb ? gl[r] * gscale : 0.0f;
       }
       __syncwarp();
       if (vec_ok) {
@@ -300,6 +394,17 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       }
     }
     __syncwarp();
+    b = __shfl_sync(0xffffffffu, b_next, 0);
+  }
+
+  // ---- leave the queue clean for the next launch that uses this slot ----------------------------------
+  if (lane == 0) {
+    const unsigned int done = atomicAdd(queue + 1, 1u);
+    if (done == total_warps - 1) {
+      queue[0] = 0u;
+      queue[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
