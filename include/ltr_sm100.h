@@ -122,10 +122,13 @@ int ltr_rank_by_score(const float *scores, const void *n, int n_bytes, int B, in
                       int64_t *ranking_out, void *stream);
 
 /*
- * Backward of every loss above: out[b, j] = g[b] * dscores[b, j]  (the chain rule
- * autograd applies to the saved per-query gradient).  `out` may alias `dscores`.
+ * Backward of every loss above: out[b, j] = g[b * g_stride] * dscores[b, j]  (the chain rule
+ * autograd applies to the saved per-query gradient).  g_stride is 1 for a dense upstream
+ * gradient and 0 for a broadcast one (what `loss.sum().backward()` / `.mean()` produce), which
+ * saves materialising it.  `out` may alias `dscores`.
  */
-int ltr_scale_rows(const float *g, const float *dscores, float *out, int B, int L, void *stream);
+int ltr_scale_rows(const float *g, int g_stride, const float *dscores, float *out, int B, int L,
+                   void *stream);
 
 /*
  * Host-buffer form of the three loss families (the call the reference's CPU path is

@@ -54,7 +54,7 @@ def _declare(lib):
     lib.ltr_rank_by_score.restype = c_int
     lib.ltr_rank_by_score.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.ltr_scale_rows.restype = c_int
-    lib.ltr_scale_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.ltr_scale_rows.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.ltr_host_workspace_bytes.restype = c_size_t
     lib.ltr_host_workspace_bytes.argtypes = [c_int, c_int]
     lib.ltr_loss_host.restype = c_int

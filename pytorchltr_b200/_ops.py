@@ -103,12 +103,19 @@ def launch_loss(family: int, mode: int, s: torch.Tensor, y: torch.Tensor, nn: to
 def scale_rows(g: torch.Tensor, dscores: torch.Tensor) -> torch.Tensor:
     """``g[:, None] * dscores`` on the device (ltr_scale_rows)."""
     B, L = dscores.shape
-    g = g.detach().to(device=dscores.device, dtype=torch.float32).contiguous()
+    g = g.detach().to(device=dscores.device, dtype=torch.float32)
+    # `loss.sum().backward()` hands over a broadcast (stride-0) gradient: read it in place
+    # instead of materialising B copies of the same number
+    if B > 1 and g.stride(0) == 0:
+        g_stride = 0
+    else:
+        g = g.contiguous()
+        g_stride = 1
     out = torch.empty_like(dscores)
     if B == 0:
         return out
     with torch.cuda.device(dscores.device):
-        rc = _lib.lib().ltr_scale_rows(g.data_ptr(), dscores.data_ptr(), out.data_ptr(), B, L,
+        rc = _lib.lib().ltr_scale_rows(g.data_ptr(), g_stride, dscores.data_ptr(), out.data_ptr(), B, L,
                                        _stream(dscores.device))
     _lib.check(rc)
     return out

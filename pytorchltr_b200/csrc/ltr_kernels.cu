@@ -436,8 +436,8 @@ rank_by_score_kernel(const float* __restrict__ scores, const void* __restrict__ 
 
 // out[b, j] = g[b] * d[b, j]: the backward of every loss (HBM-bound streaming pass).
 __global__ void __launch_bounds__(256)
-scale_rows_kernel(const float* __restrict__ g, const float* __restrict__ d, float* __restrict__ out,
-                  int B, int L) {
+scale_rows_kernel(const float* __restrict__ g, int g_stride, const float* __restrict__ d,
+                  float* __restrict__ out, int B, int L) {
   const size_t total = static_cast<size_t>(B) * L;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   if ((L & 3) == 0) {
@@ -446,14 +446,14 @@ scale_rows_kernel(const float* __restrict__ g, const float* __restrict__ d, floa
     const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
     float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4; i += stride) {
-      const float gb = g[i / L4];
+      const float gb = g[(i / L4) * g_stride];
       float4 v = d4[i];
       v.x *= gb; v.y *= gb; v.z *= gb; v.w *= gb;
       o4[i] = v;
     }
   } else {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += stride)
-      out[i] = g[i / L] * d[i];
+      out[i] = g[(i / L) * g_stride] * d[i];
   }
 }
 
@@ -759,8 +759,9 @@ int ltr_rank_by_score(const float* scores, const void* n, int n_bytes, int B, in
   return LTR_OK;
 }
 
-int ltr_scale_rows(const float* g, const float* dscores, float* out, int B, int L, void* stream) {
-  if (B < 0 || L < 1) return LTR_EINVAL;
+int ltr_scale_rows(const float* g, int g_stride, const float* dscores, float* out, int B, int L,
+                   void* stream) {
+  if (B < 0 || L < 1 || (g_stride != 0 && g_stride != 1)) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!g || !dscores || !out) return LTR_EINVAL;
   DeviceInfo di;
@@ -771,7 +772,7 @@ int ltr_scale_rows(const float* g, const float* dscores, float* out, int B, int 
   long long want = static_cast<long long>((work + 255) / 256);
   long long cap = static_cast<long long>(di.sms) * 8;
   const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
-  scale_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, dscores, out, B, L);
+  scale_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, g_stride, dscores, out, B, L);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }

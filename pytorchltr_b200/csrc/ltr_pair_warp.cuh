@@ -181,11 +181,12 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
   // ---- query schedule: the first query of every warp is static (no start-up burst on the queue
   // counter), the following ones are pulled from the device-wide queue as warps finish -----------
   const unsigned int total_warps = gridDim.x * kWarpsPerCta;
+  const bool dynamic = total_warps < static_cast<unsigned int>(B);   // else: one query per warp, no queue traffic
   unsigned int b = blockIdx.x * kWarpsPerCta + warp;
 
   while (b < static_cast<unsigned int>(B)) {
-    unsigned int b_next = 0;
-    if (lane == 0) b_next = total_warps + atomicAdd(queue, 1u);   // consumed at the end of this iteration
+    unsigned int b_next = 0xffffffffu;
+    if (dynamic && lane == 0) b_next = total_warps + atomicAdd(queue, 1u);   // consumed at the end of this iteration
 
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
@@ -394,11 +395,12 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       }
     }
     __syncwarp();
+    if (!dynamic) break;
     b = __shfl_sync(0xffffffffu, b_next, 0);
   }
 
   // ---- leave the queue clean for the next launch that uses this slot ----------------------------------
-  if (lane == 0) {
+  if (dynamic && lane == 0) {
     const unsigned int done = atomicAdd(queue + 1, 1u);
     if (done == total_warps - 1) {
       queue[0] = 0u;

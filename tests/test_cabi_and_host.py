@@ -43,8 +43,9 @@ def test_argument_validation_needs_no_gpu():
     assert lib.ltr_lambda(0, None, None, 8, None, 8, 1, _lib.MAX_LIST_SIZE + 1, 1.0, None, None, None,
                           None, None) == -2
     assert lib.ltr_rank_metrics(5, None, None, 8, None, 8, 1, 4, 1, 1, None, 1, None) == -1
-    assert lib.ltr_scale_rows(None, None, None, 3, 4, None) == -1
-    assert lib.ltr_scale_rows(None, None, None, 0, 4, None) == 0      # empty batch is a no-op
+    assert lib.ltr_scale_rows(None, 1, None, None, 3, 4, None) == -1
+    assert lib.ltr_scale_rows(None, 2, None, None, 3, 4, None) == -1   # stride must be 0 or 1
+    assert lib.ltr_scale_rows(None, 1, None, None, 0, 4, None) == 0   # empty batch is a no-op
     with pytest.raises(_lib.LtrError):
         _lib.check(-2)
 
