@@ -17,6 +17,7 @@
 #include <atomic>
 
 #include "ltr_common.cuh"
+#include "ltr_pair_cta.cuh"
 #include "ltr_pair_warp.cuh"
 #include "ltr_sm100.h"
 
@@ -613,6 +614,25 @@ int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const 
   return LTR_OK;
 }
 
+template <int TW>
+int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                    int B, int L, float sigma, float* loss_out, float* grad_out, int64_t* ranking_out,
+                    float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+  const int P = next_pow2(L);
+  const int threads = kCtaWarps * 32;
+  const size_t smem = cta_smem_bytes(L, P);
+  int grid = 0;
+  int rc = persistent_grid(pair_cta_kernel<TW>, threads, smem, B, di, &grid);
+  if (rc != LTR_OK) return rc;
+  const PairTables* tabs = nullptr;
+  rc = pair_tables(st, &tabs);
+  if (rc != LTR_OK) return rc;
+  pair_cta_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma,
+                                                   loss_out, grad_out, ranking_out, loss_sum, tabs);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,
                   int n_bytes, int B, int L, float sigma, float* loss_out, float* grad_out,
                   int64_t* ranking_out, float* loss_sum, void* stream) {
@@ -636,6 +656,18 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
     if (pm == PM_NDCG2)
       return launch_pair_warp<TW_DELTA>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
                                         ranking_out, loss_sum, st, di);
+  }
+  if (L > kWarpL && !force_generic()) {
+    // longer lists: one CTA per query, 128 x 128 rank tiles, every pair once
+    if (pm == PM_LOGISTIC)
+      return launch_pair_cta<TW_UNIT>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
+                                      ranking_out, loss_sum, st, di);
+    if (pm == PM_ARP2)
+      return launch_pair_cta<TW_DIFF>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
+                                      ranking_out, loss_sum, st, di);
+    if (pm == PM_NDCG2)
+      return launch_pair_cta<TW_DELTA>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
+                                       ranking_out, loss_sum, st, di);
   }
 #define LTR_CASE(M)                                                                               \
   case M:                                                                                         \

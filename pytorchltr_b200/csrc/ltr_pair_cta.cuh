@@ -1,0 +1,248 @@
+// ltr_pair_cta.cuh -- one CTA per query for list sizes 129 .. LTR_MAX_LIST_SIZE (the north-star
+// point (4096, 1024), config (65536, 512)): the sigmoid-weighted pair losses evaluated ONCE per
+// unordered pair on 128 x 128 rank tiles.
+//
+// Per query: coalesced row staging -> CTA-wide bitonic argsort in shared memory
+// (rank_by_score, utils/tensor_operations.py:48-64) -> ideal DCG from a shared-memory grade
+// histogram (_max_dcg, pairwise_lambda.py:231-241; a second sort if the grades do not fit) ->
+// per-document factors in rank order -> the S (S + 1) / 2 rank tiles are handed to the warps of
+// the CTA through a shared counter: diagonal tiles run ring_pass, off-diagonal tiles tile_pass
+// (ltr_pair_tiles.cuh) -> per-tile row / column gradients are added to the CTA's rank-order
+// gradient with shared-memory atomics (8 per lane per 512 pairs) -> scatter to document order,
+// coalesced store.
+#pragma once
+
+#include "ltr_pair_warp.cuh"
+
+namespace ltr {
+
+constexpr int kCtaWarps = 8;
+
+struct CtaSmem {
+  uint64_t* keys;     // [P]      sort keys
+  PairItem* items;    // [Lp]     rank order, Lp = L rounded up to 128
+  float* raw_s;       // [L]      scores, document order; reused: document-order gradient
+  int* raw_y;         // [L]      relevance, document order
+  int* doc;           // [Lp]     rank -> document
+  float* gacc;        // [Lp]     rank-order gradient (unscaled)
+  float* gcol;        // [W*128]  per-warp column accumulators of the current tile
+  float* red;         // [40]
+  int* hist;          // [36]     grade histogram + flags + tile counter
+};
+
+__host__ __device__ inline size_t cta_smem_bytes(int L, int P) {
+  const size_t Lp = (static_cast<size_t>(L) + 127) / 128 * 128;
+  return 8u * P + 16u * Lp + 4u * L + 4u * L + 4u * Lp + 4u * Lp + 4u * kCtaWarps * 128 + 4u * 40 + 4u * 40;
+}
+
+__device__ __forceinline__ CtaSmem cta_carve(unsigned char* base, int L, int P) {
+  const int Lp = (L + 127) / 128 * 128;
+  CtaSmem m;
+  m.keys = reinterpret_cast<uint64_t*>(base);                 base += 8u * P;
+  m.items = reinterpret_cast<PairItem*>(base);                base += 16u * Lp;
+  m.gcol = reinterpret_cast<float*>(base);                    base += 4u * kCtaWarps * 128;
+  m.gacc = reinterpret_cast<float*>(base);                    base += 4u * Lp;
+  m.doc = reinterpret_cast<int*>(base);                       base += 4u * Lp;
+  m.raw_s = reinterpret_cast<float*>(base);                   base += 4u * L;
+  m.raw_y = reinterpret_cast<int*>(base);                     base += 4u * L;
+  m.red = reinterpret_cast<float*>(base);                     base += 4u * 40;
+  m.hist = reinterpret_cast<int*>(base);
+  return m;
+}
+
+template <int TW, bool FACTORED>
+__device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& tb, int nb, int lane, int warp) {
+  const int S = (nb + 127) >> 7;
+  const int T = S * (S + 1) / 2;
+  float* gcol = m.gcol + warp * 128;
+  float wl = 0.0f;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&m.hist[34], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= T) break;
+    // strip A holds the tiles (A, A), (A, A + 1), ..., (A, S - 1)
+    int A = 0, rem = t;
+    while (rem >= S - A) { rem -= S - A; ++A; }
+    const int Bc = A + rem;
+    const int row_base = A << 7, col_base = Bc << 7;
+    *reinterpret_cast<float4*>(gcol + lane * 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncwarp();
+    if (Bc == A) {
+      // diagonal block: ring over the (possibly partial) block with the densest chunking
+      const int nl = min(128, nb - row_base);
+      const int R = (nl + 31) >> 5;
+      const PairItem* it = m.items + row_base;
+      float racc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int C;
+      float l;
+      if (R == 1) { float ra1[1]; C = nl; l = ring_pass<TW, FACTORED, 1>(it, gcol, tb.wtab[0], C, nl, lane, ra1); racc[0] = ra1[0]; }
+      else if (R == 2) { float ra2[2]; C = (nl + 1) / 2; l = ring_pass<TW, FACTORED, 2>(it, gcol, tb.wtab[1], C, nl, lane, ra2); racc[0] = ra2[0]; racc[1] = ra2[1]; }
+      else if (R == 3) { float ra3[3]; C = (nl + 2) / 3; l = ring_pass<TW, FACTORED, 3>(it, gcol, tb.wtab[2], C, nl, lane, ra3); racc[0] = ra3[0]; racc[1] = ra3[1]; racc[2] = ra3[2]; }
+      else { C = (nl + 3) / 4; l = ring_pass<TW, FACTORED, 4>(it, gcol, tb.wtab[3], C, nl, lane, racc); }
+      wl += l;
+      __syncwarp();
+      if (lane < C) {
+        for (int r = 0; r < R; ++r) {
+          const int p = lane * R + r;
+          if (p < nl) atomicAdd(&m.gacc[row_base + p], gcol[lane * 4 + r] + racc[r]);
+        }
+      }
+    } else {
+      float racc[4];
+      wl += tile_pass<TW, FACTORED>(m.items, row_base, col_base, tb.delta, gcol, lane, racc);
+      __syncwarp();
+      const float4 gc = *reinterpret_cast<const float4*>(gcol + lane * 4);
+      const float gcv[4] = {gc.x, gc.y, gc.z, gc.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        atomicAdd(&m.gacc[row_base + lane * 4 + r], racc[r]);
+        if (col_base + lane * 4 + r < nb) atomicAdd(&m.gacc[col_base + lane * 4 + r], gcv[r]);
+      }
+    }
+    __syncwarp();
+  }
+  return wl;
+}
+
+template <int TW>
+__global__ void __launch_bounds__(kCtaWarps * 32)
+pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
+                const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma,
+                float* __restrict__ loss_out, float* __restrict__ grad_out,
+                int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
+                const PairTables* __restrict__ tabs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaSmem m = cta_carve(smem_raw, L, P);
+  const PairTables& tb = *tabs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float gscale = sigma * kLog2e;
+  const double kd = static_cast<double>(sigma) * 1.4426950408889634;
+  const float k_hi = static_cast<float>(kd);
+  const float k_lo = static_cast<float>(kd - static_cast<double>(k_hi));
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();   // previous query fully consumed
+    const int nb = load_n(n, n_bytes, b, L);
+    const size_t base = static_cast<size_t>(b) * L;
+    const int Lp = ((nb + 127) >> 7) << 7;   // ranks covered by tiles
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+      m.raw_s[j] = scores[base + j];
+      m.raw_y[j] = load_int_clamped(rel, rel_bytes, base + j);
+    }
+    if (threadIdx.x < 36) m.hist[threadIdx.x] = 0;
+    __syncthreads();
+
+    // ---- rank_by_score -----------------------------------------------------------------------
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+      uint32_t key = kPadKey;
+      if (j < nb) key = desc_key_f32(m.raw_s[j]);
+      m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
+    }
+    cta_bitonic_sort(m.keys, P);
+
+    // ---- ideal DCG ---------------------------------------------------------------------------------
+    float max_dcg = 1.0f;
+    if constexpr (TW == TW_DELTA) {
+      for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const int y = m.raw_y[j];
+        if (y < 0 || y > 31) m.hist[32] = 1;
+        else if (y > 0) atomicAdd(&m.hist[y], 1);
+      }
+      __syncthreads();
+      if (m.hist[32] == 0) {
+        if (threadIdx.x == 0) {
+          double acc = 0.0;
+          int start = 0;
+          for (int g = 31; g >= 1; --g) {
+            const int cnt = m.hist[g];
+            if (cnt > 0) {
+              acc += static_cast<double>(gain_of_grade(g)) *
+                     (tb.inv_disc_prefix[start + cnt] - tb.inv_disc_prefix[start]);
+              start += cnt;
+            }
+          }
+          m.red[36] = static_cast<float>(acc);
+        }
+        __syncthreads();
+        max_dcg = m.red[36];
+      } else {
+        // grades outside [0, 31]: sort them (the score ranking is saved in m.doc first)
+        for (int r = threadIdx.x; r < L; r += blockDim.x) m.doc[r] = static_cast<int>(m.keys[r] & 0xffffffffu);
+        __syncthreads();
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+          uint32_t key = kPadKey;
+          if (j < nb) key = desc_key_i32(m.raw_y[j]);
+          m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
+        }
+        cta_bitonic_sort(m.keys, P);
+        float part = 0.0f;
+        for (int r = threadIdx.x; r < nb; r += blockDim.x)
+          part += exp_gain_f32(m.raw_y[static_cast<int>(m.keys[r] & 0xffffffffu)]) / tb.disc[r];
+        max_dcg = cta_sum(part, m.red);
+        for (int r = threadIdx.x; r < L; r += blockDim.x) m.keys[r] = static_cast<uint64_t>(m.doc[r]);
+        __syncthreads();
+      }
+      if (max_dcg == 0.0f) max_dcg = 1.0f;
+    }
+    const float inv_max_dcg = 1.0f / max_dcg;
+
+    // ---- score range, per-document factors in rank order ----------------------------------------------
+    float smax = 0.0f, smin = 0.0f;
+    if (nb > 0) {
+      smax = m.raw_s[static_cast<int>(m.keys[0] & 0xffffffffu)];
+      smin = m.raw_s[static_cast<int>(m.keys[nb - 1] & 0xffffffffu)];
+    }
+    const float mid = 0.5f * (smax + smin);
+    const bool factored = fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
+    const int fill = Lp > L ? Lp : L;
+    for (int p = threadIdx.x; p < fill; p += blockDim.x) {
+      PairItem it;
+      it.a = factored ? 0.0f : -1.0e30f; it.b = 0.0f; it.e = 0.0f; it.g = 0.0f;
+      int d = p;
+      if (p < L) {
+        d = static_cast<int>(m.keys[p] & 0xffffffffu);
+        if (ranking_out) ranking_out[base + p] = d;
+      }
+      if (p < nb) {
+        const float s = m.raw_s[d];
+        const int y = m.raw_y[d];
+        if constexpr (TW == TW_DELTA) it.g = gain_of_grade(y) * inv_max_dcg;
+        else it.g = static_cast<float>(y);
+        if (factored) {
+          const float c = s - mid;
+          const float eh = c * k_hi;
+          const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;
+          it.e = eh;
+          it.a = ex2_approx(-eh) * (1.0f - el);
+          it.b = ex2_approx(eh) * (1.0f + el);
+        } else {
+          it.a = sigma * s;
+        }
+      }
+      if (p < Lp) { m.items[p] = it; m.gacc[p] = 0.0f; }
+      if (p < L) m.doc[p] = d;
+    }
+    __syncthreads();
+
+    // ---- all pairs, once ---------------------------------------------------------------------------------
+    float wl = 0.0f;
+    if (nb > 1) wl = factored ? cta_tiles<TW, true>(m, tb, nb, lane, warp) : cta_tiles<TW, false>(m, tb, nb, lane, warp);
+    const float loss = cta_sum(wl, m.red);   // barriers inside also publish gacc
+    if (threadIdx.x == 0) {
+      loss_out[b] = loss;
+      if (loss_sum) atomicAdd(loss_sum, loss);
+    }
+
+    // ---- gradient back to document order ----------------------------------------------------------------
+    if (grad_out) {
+      float* gdoc = m.raw_s;
+      for (int p = threadIdx.x; p < L; p += blockDim.x) gdoc[m.doc[p]] = p < nb ? m.gacc[p] * gscale : 0.0f;
+      __syncthreads();
+      float* __restrict__ go = grad_out + base;
+      for (int j = threadIdx.x; j < L; j += blockDim.x) go[j] = gdoc[j];
+    }
+  }
+}
+
+}  // namespace ltr

@@ -202,4 +202,58 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
   return active ? lacc : 0.0f;
 }
 
+// Off-diagonal 128 x 128 rank tile: rows = the 32 chunks of 4 ranks starting at rank `row_base`
+// (all valid: only a query's last 128-rank block can be partial), columns = the 32 chunks
+// starting at rank `col_base` > row_base.  In step m lane l meets column chunk (l + m) & 31, so
+// the 32 lanes touch 32 different chunks in every step.  Padded columns contribute exact zeros.
+// delta windows come straight from the raw table: rank distances are positive multiples of 4
+// plus (-3..3), i.e. two aligned 128-bit loads.
+//   gcol : warp-private [128] column accumulators of this tile, zero on entry
+template <int TW, bool FACTORED>
+__device__ __forceinline__ float tile_pass(const PairItem* __restrict__ items, int row_base, int col_base,
+                                           const float* __restrict__ delta, float* __restrict__ gcol,
+                                           int lane, float (&racc)[4]) {
+  constexpr int R = 4;
+  float ra[R], re[R], rg[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const PairItem it = items[row_base + lane * R + r];
+    ra[r] = it.a; re[r] = it.e; rg[r] = it.g;
+    racc[r] = 0.0f;
+  }
+  float lacc = 0.0f;
+  const int dist0 = (col_base - row_base) >> 2;   // chunk distance of column chunk 0 from row chunk 0
+  for (int m = 0; m < 32; ++m) {
+    const int pc = (lane + m) & 31;
+    float dwin[8];
+    if constexpr (TW == TW_DELTA) {
+      const float4* w4 = reinterpret_cast<const float4*>(delta) + (dist0 + pc - lane - 1);
+      const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);   // delta[4d - 4 .. 4d + 3], slot e + 4
+      dwin[0] = w0.y; dwin[1] = w0.z; dwin[2] = w0.w;
+      dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w; dwin[7] = 0.0f;
+    }
+    PairItem col[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) col[c] = items[col_base + pc * R + c];
+    float tc[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) tc[c] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        float dw = 1.0f;
+        if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
+        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], col[c], dw, lacc, racc[r], tc[c]);
+      }
+    }
+    float4* g4 = reinterpret_cast<float4*>(gcol) + pc;
+    float4 g = *g4;
+    g.x += tc[0]; g.y += tc[1]; g.z += tc[2]; g.w += tc[3];
+    *g4 = g;
+    __syncwarp();
+  }
+  return lacc;
+}
+
 }  // namespace ltr

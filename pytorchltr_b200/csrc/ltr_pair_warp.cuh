@@ -106,8 +106,8 @@ struct __align__(16) WarpScratch {
 struct __align__(16) PairTables {
   __align__(16) float wtab[4][window_table_floats()];   // delta windows for R = 1..4 (float4 loads)
   double inv_disc_prefix[LTR_MAX_LIST_SIZE + 1];        // S[p] = sum_{r<p} 1 / D(r)  (ideal DCG)
-  float delta[LTR_MAX_LIST_SIZE + 8];                   // delta[k] = |1/D(k) - 1/D(k+1)|, pairwise_lambda.py:206-211
-  float disc[LTR_MAX_LIST_SIZE + 8];                    // D(r) = log2(2 + r), pairwise_lambda.py:168-170
+  __align__(16) float delta[LTR_MAX_LIST_SIZE + 8];     // delta[k] = |1/D(k) - 1/D(k+1)|, pairwise_lambda.py:206-211
+  __align__(16) float disc[LTR_MAX_LIST_SIZE + 8];      // D(r) = log2(2 + r), pairwise_lambda.py:168-170
 };
 
 __global__ void __launch_bounds__(1024) init_pair_tables_kernel(PairTables* __restrict__ t) {
