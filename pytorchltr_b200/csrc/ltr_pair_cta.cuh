@@ -20,7 +20,8 @@ constexpr int kCtaWarps = 8;
 
 struct CtaSmem {
   uint64_t* keys;     // [P]      sort keys
-  PairItem* items;    // [Lp]     rank order, Lp = L rounded up to 128
+  PairSoA it;         // 4 x [Lp] rank order, Lp = L rounded up to 128
+  float* delta;       // [Lp + 8] delta table (copied from PairTables once per CTA)
   float* raw_s;       // [L]      scores, document order; reused: document-order gradient
   int* raw_y;         // [L]      relevance, document order
   int* doc;           // [Lp]     rank -> document
@@ -32,14 +33,19 @@ struct CtaSmem {
 
 __host__ __device__ inline size_t cta_smem_bytes(int L, int P) {
   const size_t Lp = (static_cast<size_t>(L) + 127) / 128 * 128;
-  return 8u * P + 16u * Lp + 4u * L + 4u * L + 4u * Lp + 4u * Lp + 4u * kCtaWarps * 128 + 4u * 40 + 4u * 40;
+  return 8u * P + 16u * Lp + 4u * (Lp + 8) + 4u * L + 4u * L + 4u * Lp + 4u * Lp + 4u * kCtaWarps * 128 +
+         4u * 40 + 4u * 40;
 }
 
 __device__ __forceinline__ CtaSmem cta_carve(unsigned char* base, int L, int P) {
   const int Lp = (L + 127) / 128 * 128;
   CtaSmem m;
   m.keys = reinterpret_cast<uint64_t*>(base);                 base += 8u * P;
-  m.items = reinterpret_cast<PairItem*>(base);                base += 16u * Lp;
+  m.it.a = reinterpret_cast<float*>(base);                    base += 4u * Lp;
+  m.it.b = reinterpret_cast<float*>(base);                    base += 4u * Lp;
+  m.it.e = reinterpret_cast<float*>(base);                    base += 4u * Lp;
+  m.it.g = reinterpret_cast<float*>(base);                    base += 4u * Lp;
+  m.delta = reinterpret_cast<float*>(base);                   base += 4u * (Lp + 8);
   m.gcol = reinterpret_cast<float*>(base);                    base += 4u * kCtaWarps * 128;
   m.gacc = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.doc = reinterpret_cast<int*>(base);                       base += 4u * Lp;
@@ -72,7 +78,7 @@ __device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& t
       // diagonal block: ring over the (possibly partial) block with the densest chunking
       const int nl = min(128, nb - row_base);
       const int R = (nl + 31) >> 5;
-      const PairItem* it = m.items + row_base;
+      const PairSoA it = {m.it.a + row_base, m.it.b + row_base, m.it.e + row_base, m.it.g + row_base};
       float racc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       int C;
       float l;
@@ -90,7 +96,7 @@ __device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& t
       }
     } else {
       float racc[4];
-      wl += tile_pass<TW, FACTORED>(m.items, row_base, col_base, tb.delta, gcol, lane, racc);
+      wl += tile_pass<TW, FACTORED>(m.it, row_base, col_base, m.delta, gcol, lane, racc);
       __syncwarp();
       const float4 gc = *reinterpret_cast<const float4*>(gcol + lane * 4);
       const float gcv[4] = {gc.x, gc.y, gc.z, gc.w};
@@ -120,6 +126,11 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
   const double kd = static_cast<double>(sigma) * 1.4426950408889634;
   const float k_hi = static_cast<float>(kd);
   const float k_lo = static_cast<float>(kd - static_cast<double>(k_hi));
+
+  if constexpr (TW == TW_DELTA) {
+    const int Lp0 = (L + 127) / 128 * 128;
+    for (int k = threadIdx.x; k < Lp0 + 8; k += blockDim.x) m.delta[k] = tb.delta[k];
+  }
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();   // previous query fully consumed
@@ -197,8 +208,7 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
     const bool factored = fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
     const int fill = Lp > L ? Lp : L;
     for (int p = threadIdx.x; p < fill; p += blockDim.x) {
-      PairItem it;
-      it.a = factored ? 0.0f : -1.0e30f; it.b = 0.0f; it.e = 0.0f; it.g = 0.0f;
+      float fa = factored ? 0.0f : -1.0e30f, fb = 0.0f, fe = 0.0f, fg = 0.0f;   // padding
       int d = p;
       if (p < L) {
         d = static_cast<int>(m.keys[p] & 0xffffffffu);
@@ -207,20 +217,20 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
       if (p < nb) {
         const float s = m.raw_s[d];
         const int y = m.raw_y[d];
-        if constexpr (TW == TW_DELTA) it.g = gain_of_grade(y) * inv_max_dcg;
-        else it.g = static_cast<float>(y);
+        if constexpr (TW == TW_DELTA) fg = gain_of_grade(y) * inv_max_dcg;
+        else fg = static_cast<float>(y);
         if (factored) {
           const float c = s - mid;
           const float eh = c * k_hi;
           const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;
-          it.e = eh;
-          it.a = ex2_approx(-eh) * (1.0f - el);
-          it.b = ex2_approx(eh) * (1.0f + el);
+          fe = eh;
+          fa = ex2_approx(-eh) * (1.0f - el);
+          fb = ex2_approx(eh) * (1.0f + el);
         } else {
-          it.a = sigma * s;
+          fa = sigma * s;
         }
       }
-      if (p < Lp) { m.items[p] = it; m.gacc[p] = 0.0f; }
+      if (p < Lp) { m.it.a[p] = fa; m.it.b[p] = fb; m.it.e[p] = fe; m.it.g[p] = fg; m.gacc[p] = 0.0f; }
       if (p < L) m.doc[p] = d;
     }
     __syncthreads();

@@ -43,40 +43,41 @@ namespace ltr {
 constexpr float kFactoredRange = 64.0f;    // max |sigma| * (max - min) * log2(e) for q = a_i * b_j
 constexpr float kBigGain = 1.0e30f;
 
-// What a column (and, before it is pulled into registers, a row) looks like in shared memory.
-struct __align__(16) PairItem {
-  float a;   // exp(-sigma (s - mid))   [stable form: sigma * s]
-  float b;   // exp(+sigma (s - mid))   [stable form: unused]
-  float e;   // sigma (s - mid) log2 e  [stable form: unused]
-  float g;   // weight basis: normalised gain G (NDCG2) or float(rel) (ARP2, logistic)
+// Per-document factors of one query in shared memory, RANK order, structure of arrays so that
+// the 32 lanes of a step read 32 consecutive chunks (conflict-free 128-bit loads).
+struct PairSoA {
+  float* a;   // exp(-sigma (s - mid))   [stable form: sigma * s]
+  float* b;   // exp(+sigma (s - mid))   [stable form: unused]
+  float* e;   // sigma (s - mid) log2 e  [stable form: unused]
+  float* g;   // weight basis: normalised gain G (NDCG2) or float(rel) (ARP2, logistic)
 };
 
 enum : int { TW_UNIT = 0, TW_DIFF = 1, TW_DELTA = 2 };   // w = 1 | |g_i - g_j| | delta |g_i - g_j|
 
-// One pair.  racc/cacc receive +lambda' for the column and -lambda' for the row, where
-// lambda' > 0 when the row wins; the caller scales by sigma / ln 2 at the end.
+// One pair: row (ra, re, rg) against column (cx, ce, cg), cx = b_j (factored) or sigma s_j
+// (stable).  racc / cacc receive -lambda' / +lambda', lambda' > 0 when the row wins; the caller
+// scales by sigma / ln 2 at the end.
 template <int TW, bool FACTORED>
-__device__ __forceinline__ void pair_once(float ra, float re, float rg, const PairItem& c, float dw,
-                                          float& lacc, float& racc, float& cacc) {
-  const float gd = rg - c.g;
+__device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx, float ce, float cg,
+                                          float dw, float& lacc, float& racc, float& cacc) {
+  const float gd = rg - cg;
   float ws;   // signed weight, > 0 when the row (i) wins
   if constexpr (TW == TW_DELTA) ws = dw * gd;
   else if constexpr (TW == TW_DIFF) ws = gd;
   else ws = fminf(fmaxf(gd, -1.0f), 1.0f);   // integer grades: sign(gd)
   float sg, lp;
   if constexpr (FACTORED) {
-    const float q = ra * c.b;
+    const float q = ra * cx;
     const float p = q + 1.0f;
     const float r = rcp_approx(p);
     const float lg = lg2_approx(p);
     const float qr = q * r;
     const bool iwins = gd > 0.0f;
     sg = iwins ? qr : r;
-    const float t1 = (c.e - re) - lg;        // -(lg2(p) + (e_i - e_j))
+    const float t1 = (ce - re) - lg;         // -(lg2(p) + (e_i - e_j))
     lp = iwins ? lg : t1;                    // ws * lp == |ws| * log2(1 + e^-x)
   } else {
-    // stable form: ra = sigma * s_i, c.a = sigma * s_j
-    const float d = ra - c.a;                // x if the row wins, -x otherwise
+    const float d = ra - cx;                 // x if the row wins, -x otherwise
     const float u = -fabsf(d) * kLog2e;
     const float t = ex2_approx(u);
     const float p = 1.0f + t;
@@ -94,35 +95,57 @@ __device__ __forceinline__ void pair_once(float ra, float re, float rg, const Pa
   cacc += lam;
 }
 
+// R consecutive floats starting at p[first] (first is a multiple of R; p is 16-byte aligned)
+template <int R>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ p, int first, float (&v)[R]) {
+  if constexpr (R == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + first);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (R == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p + first);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = p[first + r];
+  }
+}
+
 // Window tables: for R rows per chunk and chunk distance d in (-kMaxChunks, kMaxChunks), entry
 // (d + kMaxChunks) holds delta[|R d + e|] at slot e + R - 1 (8 floats, the last ones unused).
 constexpr int kMaxChunks = 32;
 __host__ __device__ constexpr int window_table_floats() { return (2 * kMaxChunks + 1) * 8; }
 
+__device__ __forceinline__ void load_window(const float4* __restrict__ w4, float (&dwin)[8]) {
+  const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+  dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
+  dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
+}
+
 // All-pairs pass over one "ring" of C <= 32 chunks of R ranks held by one warp (C*R >= n).
-//   items : rank-ordered PairItems of this query in shared memory, padded to C*R entries
+//   it    : rank-ordered factors of this block in shared memory, padded to C*R entries
 //   gcol  : warp-private column-gradient accumulators, chunk c at gcol[4c .. 4c+R), zero on entry
 //   wtab  : window table for this R (TW_DELTA only)
 // Returns per-lane partial loss; racc[r] holds -sum lambda' of the lane's rows.
 template <int TW, bool FACTORED, int R>
-__device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, float* __restrict__ gcol,
+__device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict__ gcol,
                                            const float* __restrict__ wtab, int C, int n, int lane,
                                            float (&racc)[R]) {
   const bool active = lane < C;
   const int me = active ? lane : 0;
+  const float* colx = FACTORED ? it.b : it.a;
   float ra[R], re[R], rg[R];
+  load_chunk<R>(it.a, me * R, ra);
+  load_chunk<R>(it.g, me * R, rg);
+  if constexpr (FACTORED) load_chunk<R>(it.e, me * R, re);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const PairItem it = items[me * R + r];
-    const bool valid = active && (me * R + r < n);
     if constexpr (FACTORED) {
-      ra[r] = valid ? it.a : 0.0f;
-      rg[r] = valid ? it.g : kBigGain;
+      const bool valid = active && (me * R + r < n);
+      ra[r] = valid ? ra[r] : 0.0f;
+      rg[r] = valid ? rg[r] : kBigGain;
     } else {
-      ra[r] = it.a;                          // stable form: padding is already (-1e30, gain 0)
-      rg[r] = it.g;
+      re[r] = 0.0f;                          // stable form: padding is already (-1e30, gain 0)
     }
-    re[r] = it.e;
     racc[r] = 0.0f;
   }
   float lacc = 0.0f;
@@ -130,20 +153,19 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
   // within-chunk triangle (rank distance c - r > 0)
   {
     float dwin[8];
-    if constexpr (TW == TW_DELTA) {
-      const float4* w4 = reinterpret_cast<const float4*>(wtab + kMaxChunks * 8);
-      const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-      dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
-      dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
-    }
+    if constexpr (TW == TW_DELTA) load_window(reinterpret_cast<const float4*>(wtab) + kMaxChunks * 2, dwin);
+    float cx[R], ce[R], cg[R];
+    load_chunk<R>(colx, me * R, cx);
+    load_chunk<R>(it.g, me * R, cg);
+    if constexpr (FACTORED) load_chunk<R>(it.e, me * R, ce);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = r + 1; c < R; ++c) {
-        const PairItem col = items[me * R + c];
         float dw = 1.0f;
         if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
-        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], col, dw, lacc, racc[r], racc[c]);
+        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], FACTORED ? ce[c] : 0.0f, cg[c], dw, lacc,
+                                racc[r], racc[c]);
       }
     }
   }
@@ -156,15 +178,12 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
     pc = pc + 1 == C ? 0 : pc + 1;
     const bool commit = active && !(dup_last && m == steps);
     float dwin[8];
-    if constexpr (TW == TW_DELTA) {
-      const float4* w4 = reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2;
-      const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-      dwin[0] = w0.x; dwin[1] = w0.y; dwin[2] = w0.z; dwin[3] = w0.w;
-      dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
-    }
-    PairItem col[R];
-#pragma unroll
-    for (int c = 0; c < R; ++c) col[c] = items[pc * R + c];
+    if constexpr (TW == TW_DELTA)
+      load_window(reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2, dwin);
+    float cx[R], ce[R], cg[R];
+    load_chunk<R>(colx, pc * R, cx);
+    load_chunk<R>(it.g, pc * R, cg);
+    if constexpr (FACTORED) load_chunk<R>(it.e, pc * R, ce);
     float tl = 0.0f, tr[R], tc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { tr[r] = 0.0f; tc[r] = 0.0f; }
@@ -174,7 +193,8 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
       for (int c = 0; c < R; ++c) {
         float dw = 1.0f;
         if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
-        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], col[c], dw, tl, tr[r], tc[c]);
+        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], FACTORED ? ce[c] : 0.0f, cg[c], dw, tl, tr[r],
+                                tc[c]);
       }
     }
     if (commit) {
@@ -210,15 +230,18 @@ __device__ __forceinline__ float ring_pass(const PairItem* __restrict__ items, f
 // plus (-3..3), i.e. two aligned 128-bit loads.
 //   gcol : warp-private [128] column accumulators of this tile, zero on entry
 template <int TW, bool FACTORED>
-__device__ __forceinline__ float tile_pass(const PairItem* __restrict__ items, int row_base, int col_base,
+__device__ __forceinline__ float tile_pass(const PairSoA& it, int row_base, int col_base,
                                            const float* __restrict__ delta, float* __restrict__ gcol,
                                            int lane, float (&racc)[4]) {
   constexpr int R = 4;
+  const float* colx = FACTORED ? it.b : it.a;
   float ra[R], re[R], rg[R];
+  load_chunk<R>(it.a, row_base + lane * R, ra);
+  load_chunk<R>(it.g, row_base + lane * R, rg);
+  if constexpr (FACTORED) load_chunk<R>(it.e, row_base + lane * R, re);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const PairItem it = items[row_base + lane * R + r];
-    ra[r] = it.a; re[r] = it.e; rg[r] = it.g;
+    if constexpr (!FACTORED) re[r] = 0.0f;
     racc[r] = 0.0f;
   }
   float lacc = 0.0f;
@@ -227,14 +250,16 @@ __device__ __forceinline__ float tile_pass(const PairItem* __restrict__ items, i
     const int pc = (lane + m) & 31;
     float dwin[8];
     if constexpr (TW == TW_DELTA) {
+      // delta[4d - 4 .. 4d + 3]: slot e + 4, so the window (e = -3..3) starts one float in
       const float4* w4 = reinterpret_cast<const float4*>(delta) + (dist0 + pc - lane - 1);
-      const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);   // delta[4d - 4 .. 4d + 3], slot e + 4
+      const float4 w0 = *w4, w1 = *(w4 + 1);
       dwin[0] = w0.y; dwin[1] = w0.z; dwin[2] = w0.w;
       dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w; dwin[7] = 0.0f;
     }
-    PairItem col[R];
-#pragma unroll
-    for (int c = 0; c < R; ++c) col[c] = items[col_base + pc * R + c];
+    float cx[R], ce[R], cg[R];
+    load_chunk<R>(colx, col_base + pc * R, cx);
+    load_chunk<R>(it.g, col_base + pc * R, cg);
+    if constexpr (FACTORED) load_chunk<R>(it.e, col_base + pc * R, ce);
     float tc[R];
 #pragma unroll
     for (int c = 0; c < R; ++c) tc[c] = 0.0f;
@@ -244,7 +269,8 @@ __device__ __forceinline__ float tile_pass(const PairItem* __restrict__ items, i
       for (int c = 0; c < R; ++c) {
         float dw = 1.0f;
         if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
-        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], col[c], dw, lacc, racc[r], tc[c]);
+        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], FACTORED ? ce[c] : 0.0f, cg[c], dw, lacc,
+                                racc[r], tc[c]);
       }
     }
     float4* g4 = reinterpret_cast<float4*>(gcol) + pc;

@@ -95,7 +95,10 @@ __device__ __forceinline__ void warp_bitonic_sort64(uint64_t (&k)[E], int lane) 
 }
 
 struct __align__(16) WarpScratch {
-  PairItem items[kWarpL];                  // rank order
+  __align__(16) float fa[kWarpL];          // per-document factors, rank order (PairSoA)
+  __align__(16) float fb[kWarpL];
+  __align__(16) float fe[kWarpL];
+  __align__(16) float fg[kWarpL];
   __align__(16) float gcol[kWarpL];        // column gradients: chunk c owns gcol[4c .. 4c+3]
   __align__(16) float raw_s[kWarpL];       // scores, document order; reused: rank-order gradient
   __align__(16) int raw_y[kWarpL];         // relevance, document order; reused: document-order gradient
@@ -138,7 +141,8 @@ template <int TW, bool FACTORED, int R>
 __device__ __forceinline__ float ring_dispatch(WarpScratch& ws, const PairTables& tb, int n, int lane) {
   const int C = (n + R - 1) / R;
   float racc[R];
-  const float l = ring_pass<TW, FACTORED, R>(ws.items, ws.gcol, tb.wtab[R - 1], C, n, lane, racc);
+  const PairSoA it = {ws.fa, ws.fb, ws.fe, ws.fg};
+  const float l = ring_pass<TW, FACTORED, R>(it, ws.gcol, tb.wtab[R - 1], C, n, lane, racc);
   // rank-order gradient (unscaled): column part + row part
   float* glin = ws.raw_s;
   if (lane < C) {
@@ -324,34 +328,35 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     __syncwarp();   // raw_s / raw_y fully consumed: they are reused below
 
     // ---- per-document factors -> shared memory (rank order) ------------------------------------
+    {
+      float fa[kWarpE], fb[kWarpE], fe[kWarpE], fg[kWarpE];
 #pragma unroll
-    for (int r = 0; r < kWarpE; ++r) {
-      const int p = lane * kWarpE + r;
-      PairItem it;
-      if (p < nb) {
-        if constexpr (TW == TW_DELTA) it.g = gain_of_grade(ys[r]) * inv_max_dcg;
-        else it.g = static_cast<float>(ys[r]);
-        if (factored) {
-          const float c = ss[r] - mid;
-          const float eh = c * k_hi;
-          const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
-          it.e = eh;
-          it.a = ex2_approx(-eh) * (1.0f - el);
-          it.b = ex2_approx(eh) * (1.0f + el);
-        } else {
-          it.a = sigma * ss[r];
-          it.b = 0.0f;
-          it.e = 0.0f;
+      for (int r = 0; r < kWarpE; ++r) {
+        const int p = lane * kWarpE + r;
+        fa[r] = factored ? 0.0f : -1.0e30f;   // padding
+        fb[r] = 0.0f; fe[r] = 0.0f; fg[r] = 0.0f;
+        if (p < nb) {
+          if constexpr (TW == TW_DELTA) fg[r] = gain_of_grade(ys[r]) * inv_max_dcg;
+          else fg[r] = static_cast<float>(ys[r]);
+          if (factored) {
+            const float c = ss[r] - mid;
+            const float eh = c * k_hi;
+            const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
+            fe[r] = eh;
+            fa[r] = ex2_approx(-eh) * (1.0f - el);
+            fb[r] = ex2_approx(eh) * (1.0f + el);
+          } else {
+            fa[r] = sigma * ss[r];
+          }
         }
-      } else {
-        it.a = factored ? 0.0f : -1.0e30f;
-        it.b = 0.0f;
-        it.e = 0.0f;
-        it.g = 0.0f;
       }
-      ws.items[p] = it;
-      ws.gcol[p] = 0.0f;
-      ws.raw_s[p] = 0.0f;   // rank-order gradient of the ranks no ring lane owns
+      const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      reinterpret_cast<float4*>(ws.fa)[lane] = make_float4(fa[0], fa[1], fa[2], fa[3]);
+      reinterpret_cast<float4*>(ws.fb)[lane] = make_float4(fb[0], fb[1], fb[2], fb[3]);
+      reinterpret_cast<float4*>(ws.fe)[lane] = make_float4(fe[0], fe[1], fe[2], fe[3]);
+      reinterpret_cast<float4*>(ws.fg)[lane] = make_float4(fg[0], fg[1], fg[2], fg[3]);
+      reinterpret_cast<float4*>(ws.gcol)[lane] = zero;
+      reinterpret_cast<float4*>(ws.raw_s)[lane] = zero;   // rank-order gradient of ranks no ring lane owns
     }
     __syncwarp();
 
