@@ -48,6 +48,13 @@ CONFIGS = {
                workload="LambdaNDCGLoss2 synthetic (B=65536, L=512) query-sharded"),
     "ns": dict(loss="LambdaNDCGLoss2", B=4096, L=1024,
                workload="LambdaNDCGLoss2 synthetic (B=4096, L=1024) fp32 (north-star point)"),
+    # forward-only ranking metrics (second half of config 4): 12 L + 12 algorithmic bytes / query
+    "c4m": dict(metric="ndcg", k=10, B=8192, L=200, skew=True,
+                workload="ndcg@10 synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
+    "c4a": dict(metric="arp", k=None, B=8192, L=200, skew=True,
+                workload="arp synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
+    "c4d": dict(metric="dcg", k=None, B=8192, L=200, skew=True,
+                workload="dcg at every rank synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
 }
 ORACLE_MODE = {"LambdaNDCGLoss2": ("lambda", "ndcg2"), "LambdaNDCGLoss1": ("lambda", "ndcg1"),
                "LambdaARPLoss1": ("lambda", "arp1"), "LambdaARPLoss2": ("lambda", "arp2"),
@@ -83,10 +90,27 @@ def make_batch_numpy(seed, B, L, skew=False):
     return scores, rel, n
 
 
+def metric_name(cfg):
+    return "loss fwd+bwd queries/sec" if "loss" in cfg else "ranking metric queries/sec"
+
+
 def valid_pairs(n):
     import numpy as np
     n = np.asarray(n, dtype=np.float64)
     return float((n * (n - 1) / 2).sum())
+
+
+def oracle_step(oracle, family, mode, cfg, s, y, n):
+    """One pass of the CPU oracle port over a batch (loss + gradient, or metric)."""
+    if family == "lambda":
+        return oracle.lambda_loss(mode, s, y, n)
+    if family == "additive":
+        return oracle.pairwise_additive(mode, s, y, n, f32="hinge" in mode)
+    if family == "listnet":
+        return oracle.listnet(s, y, n)
+    if mode == "arp":
+        return oracle.arp(s, y, n), None
+    return oracle.dcg(s, y, n, k=cfg.get("k"), normalized=mode == "ndcg"), None
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -98,18 +122,14 @@ def run_reference(args, cfg, rank, world):
     import oracle
     oracle.build()
     threads = oracle.max_threads()
-    family, mode = ORACLE_MODE[cfg["loss"]]
+    family, mode = ORACLE_MODE[cfg["loss"]] if "loss" in cfg else ("metric", cfg["metric"])
     L = cfg["L"]
     # bounded sample: a slice of the workload's batch sized for ~1 s per step
     probe_B = 64
     s, y, n = make_batch_numpy(1234, probe_B, L, cfg.get("skew", False))
 
     def step(s, y, n):
-        if family == "lambda":
-            return oracle.lambda_loss(mode, s, y, n)
-        if family == "additive":
-            return oracle.pairwise_additive(mode, s, y, n)
-        return oracle.listnet(s, y, n)
+        return oracle_step(oracle, family, mode, cfg, s, y, n)
 
     step(s, y, n)
     t0 = time.perf_counter()
@@ -128,11 +148,12 @@ def run_reference(args, cfg, rank, world):
     sample = (f"{sample_B} of the {cfg['B']} queries of one batch per step, {steps} steps; "
               f"oracle/ltr_oracle.c (C port of the reference algorithm, OpenMP over queries)")
     line = {
-        "impl": "reference", "metric": "loss fwd+bwd queries/sec", "value": qps, "unit": "queries/s",
+        "impl": "reference", "metric": metric_name(cfg), "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
         "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "loss": cfg["loss"], "B_per_step": sample_B, "L": L},
+        "config": {"workload": cfg["workload"], "loss": cfg.get("loss", cfg.get("metric")),
+                   "B_per_step": sample_B, "L": L},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -214,6 +235,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
+    import pytorchltr_b200.evaluation as ltr_eval
     import pytorchltr_b200.loss as ltr_loss
     from pytorchltr_b200 import _lib, _ops
     from pytorchltr_b200.distributed import global_sum_count, shard_bounds
@@ -231,8 +253,17 @@ def run_ours(args, cfg, rank, local_rank, world):
     else:
         B = cfg["B"]
         scaling = "weak"
-    loss_fn = getattr(ltr_loss, cfg["loss"])()
-    family, mode = ORACLE_MODE[cfg["loss"]]
+    is_metric = "metric" in cfg
+    if is_metric:
+        family, mode = "metric", cfg["metric"]
+        if mode == "arp":
+            loss_fn = ltr_eval.arp
+        else:
+            _fn, _k = getattr(ltr_eval, mode), cfg.get("k")
+            loss_fn = lambda s, y, n: _fn(s, y, n, k=_k)  # noqa: E731
+    else:
+        loss_fn = getattr(ltr_loss, cfg["loss"])()
+        family, mode = ORACLE_MODE[cfg["loss"]]
 
     # ---- resident pool of distinct batches, larger than L2 ---------------------------------
     in_bytes = B * L * 12 + B * 8
@@ -242,15 +273,20 @@ def run_ours(args, cfg, rank, local_rank, world):
     for i in range(pool_n):
         s, y, n = make_batch_numpy(1234 + 1000 * rank + i, B, L, cfg.get("skew", False))
         pairs_per_batch.append(valid_pairs(n))
-        pool.append((torch.from_numpy(s).to(dev).requires_grad_(True), torch.from_numpy(y).to(dev),
+        pool.append((torch.from_numpy(s).to(dev).requires_grad_(not is_metric), torch.from_numpy(y).to(dev),
                      torch.from_numpy(n).to(dev)))
     pool_bytes = pool_n * in_bytes
     torch.cuda.synchronize()
 
     red = torch.zeros(2, device=dev)
 
+    metric_out = [None] * pool_n
+
     def step(i):
         s, y, n = pool[i % pool_n]
+        if is_metric:
+            metric_out[i % pool_n] = loss_fn(s, y, n)
+            return metric_out[i % pool_n]
         s.grad = None
         out = loss_fn(s, y, n)
         if world > 1:
@@ -338,29 +374,34 @@ def run_ours(args, cfg, rank, local_rank, world):
         run_step(0)
         torch.cuda.synchronize()
         sn, yn, nn = s.detach().cpu().numpy()[idx], y.cpu().numpy()[idx], n.cpu().numpy()[idx]
-        if family == "lambda":
-            rl, rg = oracle.lambda_loss(mode, sn, yn, nn)
-        elif family == "additive":
-            # hinge: float32 restatement (pairs on the kink flip between f32 and f64 rounding)
-            rl, rg = oracle.pairwise_additive(mode, sn, yn, nn, f32="hinge" in mode)
+        # (hinge: float32 restatement -- pairs on the kink flip between f32 and f64 rounding)
+        rl, rg = oracle_step(oracle, family, mode, cfg, sn, yn, nn)
+        if is_metric:
+            got = metric_out[0].detach().cpu().double().numpy()[idx]
+            err = float(np.abs(got - rl).max())
+            parity = {"max_abs_err": err, "queries_checked": int(len(idx)), "ok": err <= 1e-5}
         else:
-            rl, rg = oracle.listnet(sn, yn, nn)
-        got = s.grad.detach().cpu().double().numpy()[idx]
-        gerr = float((np.abs(got - rg) / (np.abs(rg).max(axis=1, keepdims=True) + 1e-30)).max())
-        parity = {"max_grad_err_rel_to_rowmax": gerr, "queries_checked": int(len(idx)), "ok": gerr <= 1e-5}
+            got = s.grad.detach().cpu().double().numpy()[idx]
+            gerr = float((np.abs(got - rg) / (np.abs(rg).max(axis=1, keepdims=True) + 1e-30)).max())
+            parity = {"max_grad_err_rel_to_rowmax": gerr, "queries_checked": int(len(idx)), "ok": gerr <= 1e-5}
 
     # ---- dominant kernel alone: the fused loss + gradient kernel -----------------------------
     lib_family = {"lambda": _lib.FAMILY_LAMBDA, "additive": _lib.FAMILY_ADDITIVE,
-                  "listnet": _lib.FAMILY_LISTNET}[family]
+                  "listnet": _lib.FAMILY_LISTNET, "metric": -1}[family]
     lib_mode = {"ndcg2": _lib.LAM_NDCG2, "ndcg1": _lib.LAM_NDCG1, "arp1": _lib.LAM_ARP1,
                 "arp2": _lib.LAM_ARP2, "hinge": _lib.ADD_HINGE, "dcg_hinge": _lib.ADD_DCG_HINGE,
-                "logistic": _lib.ADD_LOGISTIC, None: 0}[mode]
+                "logistic": _lib.ADD_LOGISTIC, None: 0, "dcg": _lib.METRIC_DCG,
+                "ndcg": _lib.METRIC_NDCG, "arp": _lib.METRIC_ARP}[mode]
+    metric_k = 1 if mode == "arp" else (cfg.get("k") or 0) if is_metric else 0
+    metric_ld = L if (is_metric and mode != "arp" and not cfg.get("k")) else 1
+    metric_buf = torch.empty(B * metric_ld, device=dev) if is_metric else None
     lib = _lib.lib()
     loss_buf = torch.empty(B, device=dev)
     grad_buf = torch.empty(B, L, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
     def kernel_only(i):
+        nonlocal st
         s, y, n = pool[i % pool_n]
         if lib_family == _lib.FAMILY_LAMBDA:
             rc = lib.ltr_lambda(lib_mode, s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L, 1.0,
@@ -368,9 +409,12 @@ def run_ours(args, cfg, rank, local_rank, world):
         elif lib_family == _lib.FAMILY_ADDITIVE:
             rc = lib.ltr_pairwise_additive(lib_mode, s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L,
                                            1.0, loss_buf.data_ptr(), grad_buf.data_ptr(), None, st)
-        else:
+        elif lib_family == _lib.FAMILY_LISTNET:
             rc = lib.ltr_listnet(s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L,
                                  loss_buf.data_ptr(), grad_buf.data_ptr(), None, st)
+        else:
+            rc = lib.ltr_rank_metrics(lib_mode, s.data_ptr(), y.data_ptr(), 8, n.data_ptr(), 8, B, L,
+                                      min(metric_k, L), 1, metric_buf.data_ptr(), metric_ld, st)
         _lib.check(rc)
 
     for i in range(8):
@@ -378,14 +422,33 @@ def run_ours(args, cfg, rank, local_rank, world):
     torch.cuda.synchronize()
     reps = max(1, min(20, 2000 // pool_n))
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kgraph = None
+    if not args.no_graph:
+        # one graph holding a launch per pool entry: device-side back-to-back, no host launch gaps
+        try:
+            kgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(kgraph):
+                st = torch.cuda.current_stream().cuda_stream
+                for i in range(pool_n):
+                    kernel_only(i)
+            st = torch.cuda.current_stream().cuda_stream
+            kgraph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"[bench] kernel-only graph capture failed ({e!r}); timing eager launches\n")
+            kgraph = None
+            st = torch.cuda.current_stream().cuda_stream
     k0.record()
     for r in range(reps):
-        for i in range(pool_n):
-            kernel_only(i)
+        if kgraph is not None:
+            kgraph.replay()
+        else:
+            for i in range(pool_n):
+                kernel_only(i)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / (reps * pool_n)
-    alg_bytes = B * (16 * L + 16)
+    alg_bytes = B * (12 * L + 8 + 4 * metric_ld) if is_metric else B * (16 * L + 16)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -397,18 +460,20 @@ def run_ours(args, cfg, rank, local_rank, world):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.config, {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "fused loss+gradient kernel (ltr_lambda / ltr_pairwise_additive / ltr_listnet)",
+    roofline = {"bound": "hbm", "kernel": "ltr_rank_metrics kernel" if is_metric else
+                "fused loss+gradient kernel (ltr_lambda / ltr_pairwise_additive / ltr_listnet)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src}
     issue = None
-    if family != "listnet":
+    if family not in ("listnet", "metric"):
         mean_pairs = sum(pairs_per_batch) / len(pairs_per_batch)
         sm_hz = (sampler.max_mhz or 1965) * 1e6
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        # 3 MUFU (ex2, rcp, lg2) per unordered pair at 16 MUFU lanes / clk / SM (hinge: FP32 issue,
-        # ~6 lane-ops per pair at 128 lanes / clk / SM)
-        per_pair_clk = (6.0 / 128.0) if "Hinge" in cfg["loss"] else (3.0 / 16.0)
+        # sigmoid losses: the tile kernels spend 2 MUFU (rcp, lg2) per unordered pair at 16 MUFU
+        # lanes / clk / SM (a naive evaluation needs 3: ex2, rcp, lg2); hinge: FP32 issue, ~6
+        # lane-ops per pair at 128 lanes / clk / SM
+        per_pair_clk = (6.0 / 128.0) if "Hinge" in cfg["loss"] else (2.0 / 16.0)
         peak_pairs = sms * sm_hz / per_pair_clk
         ach_pairs = mean_pairs / (kernel_ms * 1e-3)
         issue = {"bound": "mufu" if "Hinge" not in cfg["loss"] else "fp32_issue",
@@ -424,11 +489,13 @@ def run_ours(args, cfg, rank, local_rank, world):
         host_pool = []
         for i in range(host_n):
             s, y, n = make_batch_numpy(99 + 1000 * rank + i, B, L, cfg.get("skew", False))
-            host_pool.append((torch.from_numpy(s).pin_memory().requires_grad_(True),
+            host_pool.append((torch.from_numpy(s).pin_memory().requires_grad_(not is_metric),
                               torch.from_numpy(y).pin_memory(), torch.from_numpy(n).pin_memory()))
 
         def e2e_step(i):
             s, y, n = host_pool[i % host_n]
+            if is_metric:
+                return loss_fn(s, y, n)     # H2D scores/relevance/n, kernel, D2H metric
             s.grad = None
             out = loss_fn(s, y, n)          # H2D scores/relevance/n, kernel, D2H loss
             out.sum().backward()            # H2D g, scale kernel, D2H gradient
@@ -448,7 +515,8 @@ def run_ours(args, cfg, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": total_queries * e_steps / dt, "unit": "queries/s",
-               "h2d_bytes_per_step": B * L * 12 + B * 8 + B * 4, "d2h_bytes_per_step": B * 4 + B * L * 4,
+               "h2d_bytes_per_step": B * L * 12 + B * 8 + (0 if is_metric else B * 4),
+               "d2h_bytes_per_step": B * 4 * metric_ld if is_metric else B * 4 + B * L * 4,
                "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
                "path": "loss_fn(pinned CPU tensors).sum().backward(): results returned as CPU tensors"}
 
@@ -460,12 +528,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         s, y, n = make_batch_numpy(1234, min(B, 64), L, cfg.get("skew", False))
 
         def ostep(s, y, n):
-            if family == "lambda":
-                oracle.lambda_loss(mode, s, y, n)
-            elif family == "additive":
-                oracle.pairwise_additive(mode, s, y, n)
-            else:
-                oracle.listnet(s, y, n)
+            oracle_step(oracle, family, mode, cfg, s, y, n)
 
         ostep(s, y, n)
         t0 = time.perf_counter()
@@ -481,13 +544,13 @@ def run_ours(args, cfg, rank, local_rank, world):
                                   f"({dt:.1f} s wall), oracle/ltr_oracle.c with OpenMP over queries"}
 
     if rank == 0:
-        launches_per_step = 2  # fused loss+gradient kernel, backward row-scale kernel
+        launches_per_step = 1 if is_metric else 2  # fused kernel (+ backward row-scale kernel)
         line = {
-            "metric": "loss fwd+bwd queries/sec", "value": value, "unit": "queries/s",
+            "metric": metric_name(cfg), "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": cfg["workload"], "loss": cfg["loss"], "B_per_gpu": B, "L": L,
+            "config": {"workload": cfg["workload"], "loss": cfg.get("loss", cfg.get("metric")), "B_per_gpu": B, "L": L,
                        "global_batch": total_queries, "parallelism": f"query-sharded dp{world}",
                        "launch": launch,
                        "l2_policy": f"inputs larger than L2: {pool_n} distinct resident batches "
@@ -496,7 +559,7 @@ def run_ours(args, cfg, rank, local_rank, world):
             "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "clocks": sampler.summary(clock_window),
             "gpu_launches": launches_per_step * args.steps,
-            "gpu_launches_note": "per step: 1 fused loss+gradient kernel + 1 row-scale kernel of "
+            "gpu_launches_note": "per step: 1 fused kernel (+ 1 row-scale kernel in the backward pass) of "
                                  "libltr_sm100.so (plus torch's sum / ones_like fill)",
             "parity_spot_check": parity,
         }

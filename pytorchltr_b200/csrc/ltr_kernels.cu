@@ -17,6 +17,7 @@
 #include <atomic>
 
 #include "ltr_common.cuh"
+#include "ltr_metrics_warp.cuh"
 #include "ltr_pair_cta.cuh"
 #include "ltr_pair_warp.cuh"
 #include "ltr_sm100.h"
@@ -318,6 +319,78 @@ listnet_kernel(const float* __restrict__ scores, const void* __restrict__ rel, i
           g = expf(scores[base + j] - ms) * izs - ey * izy;
         }
         grad_out[base + j] = g;
+      }
+    }
+  }
+}
+
+// Register-resident form for L <= 32 K: the row is read ONCE (K coalesced loads per lane, all
+// in flight together), reduced with shuffles and the gradient written once: 12 L bytes read and
+// 4 L written per query, which is the algorithmic minimum (HBM-bound).
+template <int K>
+__global__ void __launch_bounds__(256)
+listnet_reg_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
+                   const void* __restrict__ n, int n_bytes, int B, int L,
+                   float* __restrict__ loss_out, float* __restrict__ grad_out,
+                   float* __restrict__ loss_sum) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  for (int b = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_cta) {
+    const int nb = load_n(n, n_bytes, b, L);
+    const size_t base = static_cast<size_t>(b) * L;
+    float s[K], y[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = lane + 32 * k;
+      s[k] = j < nb ? scores[base + j] : -INFINITY;
+    }
+    if (rel_bytes == 8) {
+      const long long* r8 = reinterpret_cast<const long long*>(rel) + base;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        y[k] = j < nb ? static_cast<float>(r8[j]) : -INFINITY;
+      }
+    } else {
+      const int* r4 = reinterpret_cast<const int*>(rel) + base;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        y[k] = j < nb ? static_cast<float>(r4[j]) : -INFINITY;
+      }
+    }
+    float ms = -INFINITY, my = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { ms = fmaxf(ms, s[k]); my = fmaxf(my, y[k]); }
+    ms = warp_max(ms);
+    my = warp_max(my);
+    float zs = 0.0f, zy = 0.0f, a = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool valid = lane + 32 * k < nb;
+      const float ds = valid ? s[k] - ms : 0.0f;
+      const float es = valid ? ex2_approx(ds * kLog2e) : 0.0f;
+      const float ey = valid ? ex2_approx((y[k] - my) * kLog2e) : 0.0f;
+      s[k] = es;
+      y[k] = ey;
+      zs += es;
+      zy += ey;
+      a = fmaf(ey, ds, a);
+    }
+    zs = warp_sum(zs);
+    zy = warp_sum(zy);
+    a = warp_sum(a);
+    const float loss = nb > 0 ? logf(zs) - a / zy : 0.0f;
+    if (lane == 0) {
+      loss_out[b] = loss;
+      if (loss_sum) atomicAdd(loss_sum, loss);
+    }
+    if (grad_out) {
+      const float izs = nb > 0 ? 1.0f / zs : 0.0f, izy = nb > 0 ? 1.0f / zy : 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        if (j < L) grad_out[base + j] = s[k] * izs - y[k] * izy;   // exactly 0 on padding
       }
     }
   }
@@ -737,8 +810,20 @@ int ltr_listnet(const float* scores, const void* rel, int rel_bytes, const void*
   long long want = (static_cast<long long>(B) + wpc - 1) / wpc;
   long long cap = static_cast<long long>(di.sms) * 8;
   const int grid = static_cast<int>(want < cap ? want : cap);
-  listnet_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      scores, rel, rel_bytes, n, n_bytes, B, L, loss_out, dscores_out, loss_sum);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LTR_LISTNET(K)                                                                              \
+  listnet_reg_kernel<K><<<grid, threads, 0, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, loss_out, \
+                                                  dscores_out, loss_sum)
+  if (L <= 32) LTR_LISTNET(1);
+  else if (L <= 64) LTR_LISTNET(2);
+  else if (L <= 128) LTR_LISTNET(4);
+  else if (L <= 256) LTR_LISTNET(8);
+  else if (L <= 512) LTR_LISTNET(16);
+  else if (L <= 1024) LTR_LISTNET(32);
+  else
+    listnet_kernel<<<grid, threads, 0, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, loss_out,
+                                             dscores_out, loss_sum);
+#undef LTR_LISTNET
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }
@@ -758,6 +843,24 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
   DeviceInfo di;
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
+  if (L <= 256 && !force_generic()) {
+    // short lists: one warp per query, in-register ranking
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const PairTables* tabs = nullptr;
+    rc = pair_tables(st, &tabs);
+    if (rc != LTR_OK) return rc;
+    const long long want = (static_cast<long long>(B) + kMetricWarps - 1) / kMetricWarps;
+    const long long cap = static_cast<long long>(di.sms) * 12;
+    const int grid = static_cast<int>(want < cap ? want : cap);
+    if (L <= 128)
+      rank_metrics_warp_kernel<4><<<grid, kMetricWarps * 32, 0, st>>>(
+          metric, scores, rel, rel_bytes, n, n_bytes, B, L, k, exp_gain, out, out_ld, tabs);
+    else
+      rank_metrics_warp_kernel<8><<<grid, kMetricWarps * 32, 0, st>>>(
+          metric, scores, rel, rel_bytes, n, n_bytes, B, L, k, exp_gain, out, out_ld, tabs);
+    LTR_CUDA(cudaGetLastError());
+    return LTR_OK;
+  }
   const int P = next_pow2(L);
   const int threads = cta_threads_for(L);
   const size_t smem = row_smem_bytes(L, P);
@@ -779,6 +882,18 @@ int ltr_rank_by_score(const float* scores, const void* n, int n_bytes, int B, in
   DeviceInfo di;
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
+  if (L <= 256 && !force_generic()) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long want = (static_cast<long long>(B) + kMetricWarps - 1) / kMetricWarps;
+    const long long cap = static_cast<long long>(di.sms) * 12;
+    const int grid = static_cast<int>(want < cap ? want : cap);
+    if (L <= 128)
+      rank_by_score_warp_kernel<4><<<grid, kMetricWarps * 32, 0, st>>>(scores, n, n_bytes, B, L, ranking_out);
+    else
+      rank_by_score_warp_kernel<8><<<grid, kMetricWarps * 32, 0, st>>>(scores, n, n_bytes, B, L, ranking_out);
+    LTR_CUDA(cudaGetLastError());
+    return LTR_OK;
+  }
   const int P = next_pow2(L);
   const int threads = cta_threads_for(L);
   const size_t smem = row_smem_bytes(L, P);
