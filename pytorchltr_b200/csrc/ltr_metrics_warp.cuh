@@ -78,7 +78,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
   __shared__ MetricScratch<E> scratch[kMetricWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   MetricScratch<E>& ws = scratch[warp];
-  const float* __restrict__ disc = tabs->disc;
+  const float* __restrict__ inv_disc = tabs->inv_disc;
   for (int b = blockIdx.x * kMetricWarps + warp; b < B; b += gridDim.x * kMetricWarps) {
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
@@ -103,11 +103,13 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 
     // relevance per rank; ranks >= nb are the padded documents in index order, whose relevance
     // the reference does not mask (dcg.py:85)
+    int iy[E];
     float ry[E];
 #pragma unroll
     for (int r = 0; r < E; ++r) {
       const int p = lane * E + r;
-      ry[r] = p < L ? static_cast<float>(ws.raw_y[p < nb ? doc[r] : p]) : 0.0f;
+      iy[r] = p < L ? ws.raw_y[p < nb ? doc[r] : p] : 0;
+      ry[r] = static_cast<float>(iy[r]);
     }
 
     if (metric == LTR_METRIC_ARP) {
@@ -126,14 +128,13 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
       continue;
     }
 
-    // dcg.py:91-93: gain / log2(rank + 2)
+    // dcg.py:91-93: gain / log2(rank + 2)  (as gain * (1 / log2(rank + 2)): <= 1 ulp apart)
     float term[E];
 #pragma unroll
     for (int r = 0; r < E; ++r) {
       const int p = lane * E + r;
-      float g = ry[r];
-      if (exp_gain) g = exp2f(g) - 1.0f;
-      term[r] = p < L ? g / __ldg(disc + p) : 0.0f;
+      const float g = exp_gain ? gain_of_grade(iy[r]) : ry[r];
+      term[r] = p < L ? g * __ldg(inv_disc + p) : 0.0f;
     }
     float iterm[E];
     if (metric == LTR_METRIC_NDCG) {
@@ -148,11 +149,11 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         const int p = lane * E + r;
-        float g = 0.0f;
-        if (p < nb) g = static_cast<float>(static_cast<int>(~yk[r] ^ 0x80000000u));
-        else if (p < L) g = static_cast<float>(ws.raw_y[p]);
-        if (exp_gain) g = exp2f(g) - 1.0f;
-        iterm[r] = p < L ? g / __ldg(disc + p) : 0.0f;
+        int gy = 0;
+        if (p < nb) gy = static_cast<int>(~yk[r] ^ 0x80000000u);
+        else if (p < L) gy = ws.raw_y[p];
+        const float g = exp_gain ? gain_of_grade(gy) : static_cast<float>(gy);
+        iterm[r] = p < L ? g * __ldg(inv_disc + p) : 0.0f;
       }
     }
 

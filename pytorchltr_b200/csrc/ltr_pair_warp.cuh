@@ -40,10 +40,11 @@ __device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&k)[E], int lane) 
         for (int r = 0; r < E; ++r) {
           const int q = r ^ stride;
           if (q > r) {
+            // one predicated min/max per output (VIMNMX takes the min/max choice as a predicate)
             const bool up = bitonic_up<E>(lane, r, size);
-            const uint32_t lo = min(k[r], k[q]), hi = max(k[r], k[q]);
-            k[r] = up ? lo : hi;
-            k[q] = up ? hi : lo;
+            const uint32_t a = k[r], b = k[q];
+            k[r] = up ? min(a, b) : max(a, b);
+            k[q] = up ? max(a, b) : min(a, b);
           }
         }
       } else {
@@ -111,6 +112,7 @@ struct __align__(16) PairTables {
   double inv_disc_prefix[LTR_MAX_LIST_SIZE + 1];        // S[p] = sum_{r<p} 1 / D(r)  (ideal DCG)
   __align__(16) float delta[LTR_MAX_LIST_SIZE + 8];     // delta[k] = |1/D(k) - 1/D(k+1)|, pairwise_lambda.py:206-211
   __align__(16) float disc[LTR_MAX_LIST_SIZE + 8];      // D(r) = log2(2 + r), pairwise_lambda.py:168-170
+  __align__(16) float inv_disc[LTR_MAX_LIST_SIZE + 8];  // 1 / D(r)
 };
 
 __global__ void __launch_bounds__(1024) init_pair_tables_kernel(PairTables* __restrict__ t) {
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(1024) init_pair_tables_kernel(PairTables* __re
     const float d0 = log2f(2.0f + static_cast<float>(k));
     const float d1 = log2f(3.0f + static_cast<float>(k));
     t->disc[k] = d0;
+    t->inv_disc[k] = 1.0f / d0;
     t->delta[k] = fabsf(1.0f / d0 - 1.0f / d1);
   }
   __syncthreads();
