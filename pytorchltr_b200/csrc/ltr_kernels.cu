@@ -665,7 +665,7 @@ inline int pair_tables(cudaStream_t st, const PairTables** out) {
 
 template <int TW>
 int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
-                     int B, int L, float sigma, float* loss_out, float* grad_out, int64_t* ranking_out,
+                     int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
                      float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
   const int threads = kWarpsPerCta * 32;
   int per_sm = 0;
@@ -682,14 +682,14 @@ int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const 
   rc = pair_tables(st, &tabs);
   if (rc != LTR_OK) return rc;
   pair_warp_kernel<TW><<<grid, threads, 0, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, vec_ok,
-                                                 loss_out, grad_out, ranking_out, loss_sum, queue, tabs);
+                                                 dcg_mod, loss_out, grad_out, ranking_out, loss_sum, queue, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }
 
 template <int TW>
 int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
-                    int B, int L, float sigma, float* loss_out, float* grad_out, int64_t* ranking_out,
+                    int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
                     float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
   const int P = next_pow2(L);
   const int threads = kCtaWarps * 32;
@@ -700,7 +700,7 @@ int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const v
   const PairTables* tabs = nullptr;
   rc = pair_tables(st, &tabs);
   if (rc != LTR_OK) return rc;
-  pair_cta_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma,
+  pair_cta_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma, dcg_mod,
                                                    loss_out, grad_out, ranking_out, loss_sum, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
@@ -718,29 +718,21 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (L <= kWarpL && !force_generic()) {
-    // sigmoid-weighted pair losses on short lists: one warp per query, every pair once
-    if (pm == PM_LOGISTIC)
-      return launch_pair_warp<TW_UNIT>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
-                                       ranking_out, loss_sum, st, di);
-    if (pm == PM_ARP2)
-      return launch_pair_warp<TW_DIFF>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
-                                       ranking_out, loss_sum, st, di);
-    if (pm == PM_NDCG2)
-      return launch_pair_warp<TW_DELTA>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
-                                        ranking_out, loss_sum, st, di);
-  }
-  if (L > kWarpL && !force_generic()) {
-    // longer lists: one CTA per query, 128 x 128 rank tiles, every pair once
-    if (pm == PM_LOGISTIC)
-      return launch_pair_cta<TW_UNIT>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
-                                      ranking_out, loss_sum, st, di);
-    if (pm == PM_ARP2)
-      return launch_pair_cta<TW_DIFF>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
-                                      ranking_out, loss_sum, st, di);
-    if (pm == PM_NDCG2)
-      return launch_pair_cta<TW_DELTA>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out, grad_out,
-                                       ranking_out, loss_sum, st, di);
+  if (!force_generic()) {
+    // every unordered pair once: one warp per query for short lists, one CTA per query and
+    // 128 x 128 rank tiles for longer ones (ARP1 / NDCG1 stay on the generic kernel for now)
+#define LTR_TILED(TWMODE, DCG)                                                                          \
+  return L <= kWarpL                                                                                    \
+             ? launch_pair_warp<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \
+                                        grad_out, ranking_out, loss_sum, st, di)                        \
+             : launch_pair_cta<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,   \
+                                       grad_out, ranking_out, loss_sum, st, di)
+    if (pm == PM_LOGISTIC) LTR_TILED(TW_UNIT, 0);
+    if (pm == PM_ARP2) LTR_TILED(TW_DIFF, 0);
+    if (pm == PM_NDCG2) LTR_TILED(TW_DELTA, 0);
+    if (pm == PM_HINGE) LTR_TILED(TW_HINGE, 0);
+    if (pm == PM_DCG_HINGE) LTR_TILED(TW_HINGE, 1);
+#undef LTR_TILED
   }
 #define LTR_CASE(M)                                                                               \
   case M:                                                                                         \

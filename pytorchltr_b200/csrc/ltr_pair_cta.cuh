@@ -114,7 +114,7 @@ __device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& t
 template <int TW>
 __global__ void __launch_bounds__(kCtaWarps * 32)
 pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
-                const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma,
+                const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int dcg_mod,
                 float* __restrict__ loss_out, float* __restrict__ grad_out,
                 int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
                 const PairTables* __restrict__ tabs) {
@@ -144,13 +144,20 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
     if (threadIdx.x < 36) m.hist[threadIdx.x] = 0;
     __syncthreads();
 
-    // ---- rank_by_score -----------------------------------------------------------------------
-    for (int j = threadIdx.x; j < P; j += blockDim.x) {
-      uint32_t key = kPadKey;
-      if (j < nb) key = desc_key_f32(m.raw_s[j]);
-      m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
+    // ---- rank_by_score (only LambdaNDCGLoss2 needs rank order; the other losses are permutation
+    // invariant and stay in document order unless the ranking was asked for) -----------------------
+    const bool sorted = TW == TW_DELTA || ranking_out != nullptr;
+    if (sorted) {
+      for (int j = threadIdx.x; j < P; j += blockDim.x) {
+        uint32_t key = kPadKey;
+        if (j < nb) key = desc_key_f32(m.raw_s[j]);
+        m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
+      }
+      cta_bitonic_sort(m.keys, P);
+    } else {
+      for (int j = threadIdx.x; j < L; j += blockDim.x) m.keys[j] = static_cast<uint64_t>(j);
+      __syncthreads();
     }
-    cta_bitonic_sort(m.keys, P);
 
     // ---- ideal DCG ---------------------------------------------------------------------------------
     float max_dcg = 1.0f;
@@ -200,15 +207,31 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
 
     // ---- score range, per-document factors in rank order ----------------------------------------------
     float smax = 0.0f, smin = 0.0f;
-    if (nb > 0) {
-      smax = m.raw_s[static_cast<int>(m.keys[0] & 0xffffffffu)];
-      smin = m.raw_s[static_cast<int>(m.keys[nb - 1] & 0xffffffffu)];
+    if (sorted) {
+      if (nb > 0) {
+        smax = m.raw_s[static_cast<int>(m.keys[0] & 0xffffffffu)];
+        smin = m.raw_s[static_cast<int>(m.keys[nb - 1] & 0xffffffffu)];
+      }
+    } else if constexpr (TW != TW_HINGE) {
+      float lmax = -INFINITY, lmin = INFINITY;
+      for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        lmax = fmaxf(lmax, m.raw_s[j]);
+        lmin = fminf(lmin, m.raw_s[j]);
+      }
+      lmax = warp_max(lmax);
+      lmin = -warp_max(-lmin);
+      if (lane == 0) { m.red[warp] = lmax; m.red[8 + warp] = lmin; }
+      __syncthreads();
+      smax = m.red[0]; smin = m.red[8];
+      for (int w = 1; w < kCtaWarps; ++w) { smax = fmaxf(smax, m.red[w]); smin = fminf(smin, m.red[8 + w]); }
+      __syncthreads();
     }
     const float mid = 0.5f * (smax + smin);
-    const bool factored = fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
+    const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
     const int fill = Lp > L ? Lp : L;
     for (int p = threadIdx.x; p < fill; p += blockDim.x) {
-      float fa = factored ? 0.0f : -1.0e30f, fb = 0.0f, fe = 0.0f, fg = 0.0f;   // padding
+      float fa = factored ? 0.0f : -1.0e30f, fb = 0.0f, fe = 0.0f;                // padding
+      float fg = TW == TW_HINGE ? -1.0e30f : 0.0f;
       int d = p;
       if (p < L) {
         d = static_cast<int>(m.keys[p] & 0xffffffffu);
@@ -219,7 +242,9 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
         const int y = m.raw_y[d];
         if constexpr (TW == TW_DELTA) fg = gain_of_grade(y) * inv_max_dcg;
         else fg = static_cast<float>(y);
-        if (factored) {
+        if constexpr (TW == TW_HINGE) {
+          fa = s;                                // raw score: the hinge works on s_i - s_j itself
+        } else if (factored) {
           const float c = s - mid;
           const float eh = c * k_hi;
           const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;
@@ -237,8 +262,21 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
 
     // ---- all pairs, once ---------------------------------------------------------------------------------
     float wl = 0.0f;
-    if (nb > 1) wl = factored ? cta_tiles<TW, true>(m, tb, nb, lane, warp) : cta_tiles<TW, false>(m, tb, nb, lane, warp);
-    const float loss = cta_sum(wl, m.red);   // barriers inside also publish gacc
+    if (nb > 1) {
+      if constexpr (TW == TW_HINGE) wl = cta_tiles<TW, false>(m, tb, nb, lane, warp);
+      else wl = factored ? cta_tiles<TW, true>(m, tb, nb, lane, warp) : cta_tiles<TW, false>(m, tb, nb, lane, warp);
+    }
+    float loss = cta_sum(wl, m.red);   // barriers inside also publish gacc
+    float gmul = gscale;
+    if constexpr (TW == TW_HINGE) {
+      gmul = 1.0f;
+      if (dcg_mod) {
+        // pairwise_additive.py:132-133: -1 / ln(2 + h); d/dh = 1 / ((2 + h) ln^2(2 + h))
+        const float lg = logf(2.0f + loss);
+        gmul = 1.0f / ((2.0f + loss) * lg * lg);
+        loss = -1.0f / lg;
+      }
+    }
     if (threadIdx.x == 0) {
       loss_out[b] = loss;
       if (loss_sum) atomicAdd(loss_sum, loss);
@@ -247,7 +285,7 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
     // ---- gradient back to document order ----------------------------------------------------------------
     if (grad_out) {
       float* gdoc = m.raw_s;
-      for (int p = threadIdx.x; p < L; p += blockDim.x) gdoc[m.doc[p]] = p < nb ? m.gacc[p] * gscale : 0.0f;
+      for (int p = threadIdx.x; p < L; p += blockDim.x) gdoc[m.doc[p]] = p < nb ? m.gacc[p] * gmul : 0.0f;
       __syncthreads();
       float* __restrict__ go = grad_out + base;
       for (int j = threadIdx.x; j < L; j += blockDim.x) go[j] = gdoc[j];

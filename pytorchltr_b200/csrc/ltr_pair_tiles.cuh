@@ -52,7 +52,7 @@ struct PairSoA {
   float* g;   // weight basis: normalised gain G (NDCG2) or float(rel) (ARP2, logistic)
 };
 
-enum : int { TW_UNIT = 0, TW_DIFF = 1, TW_DELTA = 2 };   // w = 1 | |g_i - g_j| | delta |g_i - g_j|
+enum : int { TW_UNIT = 0, TW_DIFF = 1, TW_DELTA = 2, TW_HINGE = 3 };   // w = 1 | |g_i - g_j| | delta |g_i - g_j|; hinge
 
 // One pair: row (ra, re, rg) against column (cx, ce, cg), cx = b_j (factored) or sigma s_j
 // (stable).  racc / cacc receive -lambda' / +lambda', lambda' > 0 when the row wins; the caller
@@ -61,6 +61,21 @@ template <int TW, bool FACTORED>
 __device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx, float ce, float cg,
                                           float dw, float& lacc, float& racc, float& cacc) {
   const float gd = rg - cg;
+  if constexpr (TW == TW_HINGE) {
+    // pairwise_additive.py:108-112 with ra = s_i, cx = s_j (raw scores): loss = 1.0 - (s_winner -
+    // s_loser) in float32 with the reference's two roundings (negating a float32 difference is
+    // exact), inactive when it is < 0; the kink loss == 0 stays active (gradient -1 / +1).
+    // Padding is (score -1e30, relevance -1e30): it always loses with loss < 0.
+    const float d = ra - cx;
+    const float sd = gd > 0.0f ? d : -d;
+    const float l = 1.0f - sd;
+    const bool act = (gd != 0.0f) && !(l < 0.0f);
+    lacc += act ? l : 0.0f;
+    const float cnt = act ? (gd > 0.0f ? 1.0f : -1.0f) : 0.0f;   // +1: the row wins
+    racc -= cnt;
+    cacc += cnt;
+    return;
+  }
   float ws;   // signed weight, > 0 when the row (i) wins
   if constexpr (TW == TW_DELTA) ws = dw * gd;
   else if constexpr (TW == TW_DIFF) ws = gd;

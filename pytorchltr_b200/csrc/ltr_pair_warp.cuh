@@ -170,7 +170,7 @@ template <int TW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
 pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, float sigma, int vec_ok,
-                 float* __restrict__ loss_out, float* __restrict__ grad_out,
+                 int dcg_mod, float* __restrict__ loss_out, float* __restrict__ grad_out,
                  int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
                  unsigned int* __restrict__ queue, const PairTables* __restrict__ tabs) {
   const PairTables& tb = *tabs;
@@ -229,30 +229,34 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
 
     // ---- argsort by descending score; padding (and the slots beyond L) last, by index ------
+    // Only LambdaNDCGLoss2 depends on the rank positions; the other losses are permutation
+    // invariant and stay in document order unless the caller asked for the ranking.
     // Fast path: 25 key bits + 7 index bits in one register.  The result is then checked
     // against the exact (32-bit key, index) order; if two scores are closer than 128 ulps and
     // came out in the wrong order, the exact 64-bit network is run instead.
-    uint32_t ekey[kWarpE];   // exact keys (document order for now)
-    uint32_t pk[kWarpE];
-#pragma unroll
-    for (int r = 0; r < kWarpE; ++r) {
-      const int j = lane * kWarpE + r;
-      ekey[r] = j < nb ? desc_key_f32(sv[r]) : kPadKey;
-      pk[r] = (ekey[r] & 0xffffff80u) | static_cast<uint32_t>(j);
-    }
-    warp_bitonic_sort32<kWarpE>(pk, lane);
-    __syncwarp();
     int doc[kWarpE];
     float ss[kWarpE];
-    uint64_t xk[kWarpE];
 #pragma unroll
-    for (int r = 0; r < kWarpE; ++r) {
-      doc[r] = static_cast<int>(pk[r] & 127u);
-      ss[r] = ws.raw_s[doc[r]];
-      const int p = lane * kWarpE + r;
-      xk[r] = pack_key(p < nb ? desc_key_f32(ss[r]) : kPadKey, doc[r]);
-    }
-    {
+    for (int r = 0; r < kWarpE; ++r) { doc[r] = lane * kWarpE + r; ss[r] = sv[r]; }
+    if (TW == TW_DELTA || ranking_out != nullptr) {
+      uint32_t ekey[kWarpE];   // exact keys (document order for now)
+      uint32_t pk[kWarpE];
+#pragma unroll
+      for (int r = 0; r < kWarpE; ++r) {
+        const int j = lane * kWarpE + r;
+        ekey[r] = j < nb ? desc_key_f32(sv[r]) : kPadKey;
+        pk[r] = (ekey[r] & 0xffffff80u) | static_cast<uint32_t>(j);
+      }
+      warp_bitonic_sort32<kWarpE>(pk, lane);
+      __syncwarp();
+      uint64_t xk[kWarpE];
+#pragma unroll
+      for (int r = 0; r < kWarpE; ++r) {
+        doc[r] = static_cast<int>(pk[r] & 127u);
+        ss[r] = ws.raw_s[doc[r]];
+        const int p = lane * kWarpE + r;
+        xk[r] = pack_key(p < nb ? desc_key_f32(ss[r]) : kPadKey, doc[r]);
+      }
       const uint64_t next0 = __shfl_down_sync(0xffffffffu, xk[0], 1);
       bool bad = (xk[0] > xk[1]) || (xk[1] > xk[2]) || (xk[2] > xk[3]) || (lane < 31 && xk[3] > next0);
       if (__any_sync(0xffffffffu, bad)) {
@@ -267,6 +271,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         }
       }
     }
+    __syncwarp();
 
     // ---- ideal DCG over the valid documents --------------------------------------------------------
     float max_dcg = 1.0f;
@@ -327,7 +332,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     smin = -warp_max(-smin);
     const float mid = 0.5f * (smax + smin);
     // NaN / inf scores fail this test and take the stable form
-    const bool factored = fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
+    const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
     __syncwarp();   // raw_s / raw_y fully consumed: they are reused below
 
     // ---- per-document factors -> shared memory (rank order) ------------------------------------
@@ -337,11 +342,13 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       for (int r = 0; r < kWarpE; ++r) {
         const int p = lane * kWarpE + r;
         fa[r] = factored ? 0.0f : -1.0e30f;   // padding
-        fb[r] = 0.0f; fe[r] = 0.0f; fg[r] = 0.0f;
+        fb[r] = 0.0f; fe[r] = 0.0f; fg[r] = TW == TW_HINGE ? -1.0e30f : 0.0f;
         if (p < nb) {
           if constexpr (TW == TW_DELTA) fg[r] = gain_of_grade(ys[r]) * inv_max_dcg;
           else fg[r] = static_cast<float>(ys[r]);
-          if (factored) {
+          if constexpr (TW == TW_HINGE) {
+            fa[r] = ss[r];                       // raw score: the hinge works on s_i - s_j itself
+          } else if (factored) {
             const float c = ss[r] - mid;
             const float eh = c * k_hi;
             const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
@@ -372,12 +379,28 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         else if (R == 2) lacc = ring_dispatch<TW, true, 2>(ws, tb, nb, lane);
         else if (R == 3) lacc = ring_dispatch<TW, true, 3>(ws, tb, nb, lane);
         else lacc = ring_dispatch<TW, true, 4>(ws, tb, nb, lane);
+      } else if constexpr (TW == TW_HINGE) {
+        const int R = (nb + 31) >> 5;
+        if (R == 1) lacc = ring_dispatch<TW, false, 1>(ws, tb, nb, lane);
+        else if (R == 2) lacc = ring_dispatch<TW, false, 2>(ws, tb, nb, lane);
+        else if (R == 3) lacc = ring_dispatch<TW, false, 3>(ws, tb, nb, lane);
+        else lacc = ring_dispatch<TW, false, 4>(ws, tb, nb, lane);
       } else {
         lacc = ring_dispatch<TW, false, 4>(ws, tb, nb, lane);
       }
     }
     __syncwarp();
-    const float loss = warp_sum(lacc);
+    float loss = warp_sum(lacc);
+    float gmul = gscale;
+    if constexpr (TW == TW_HINGE) {
+      gmul = 1.0f;
+      if (dcg_mod) {
+        // pairwise_additive.py:132-133: -1 / ln(2 + h); d/dh = 1 / ((2 + h) ln^2(2 + h))
+        const float lg = logf(2.0f + loss);
+        gmul = 1.0f / ((2.0f + loss) * lg * lg);
+        loss = -1.0f / lg;
+      }
+    }
     if (lane == 0) {
       loss_out[b] = loss;
       if (loss_sum) atomicAdd(loss_sum, loss);
@@ -391,7 +414,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
 #pragma unroll
       for (int r = 0; r < kWarpE; ++r) {
         const int p = lane * kWarpE + r;
-        gdoc[doc[r]] = p < nb ? gl[r] * gscale : 0.0f;
+        gdoc[doc[r]] = p < nb ? gl[r] * gmul : 0.0f;
       }
       __syncwarp();
       if (vec_ok) {
