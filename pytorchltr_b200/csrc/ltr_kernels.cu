@@ -720,7 +720,7 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!force_generic()) {
     // every unordered pair once: one warp per query for short lists, one CTA per query and
-    // 128 x 128 rank tiles for longer ones (ARP1 / NDCG1 stay on the generic kernel for now)
+    // 128 x 128 rank tiles for longer ones
 #define LTR_TILED(TWMODE, DCG)                                                                          \
   return L <= kWarpL                                                                                    \
              ? launch_pair_warp<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \
@@ -732,6 +732,8 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
     if (pm == PM_NDCG2) LTR_TILED(TW_DELTA, 0);
     if (pm == PM_HINGE) LTR_TILED(TW_HINGE, 0);
     if (pm == PM_DCG_HINGE) LTR_TILED(TW_HINGE, 1);
+    if (pm == PM_ARP1) LTR_TILED(TW_TWO, 0);
+    if (pm == PM_NDCG1) LTR_TILED(TW_TWO, 1);
 #undef LTR_TILED
   }
 #define LTR_CASE(M)                                                                               \

@@ -114,7 +114,7 @@ __device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& t
 template <int TW>
 __global__ void __launch_bounds__(kCtaWarps * 32)
 pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
-                const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int dcg_mod,
+                const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                 float* __restrict__ loss_out, float* __restrict__ grad_out,
                 int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
                 const PairTables* __restrict__ tabs) {
@@ -127,6 +127,7 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
   const float k_hi = static_cast<float>(kd);
   const float k_lo = static_cast<float>(kd - static_cast<double>(k_hi));
 
+  const bool rank_weighted = TW == TW_DELTA || (TW == TW_TWO && variant != 0);   // NDCG losses
   if constexpr (TW == TW_DELTA) {
     const int Lp0 = (L + 127) / 128 * 128;
     for (int k = threadIdx.x; k < Lp0 + 8; k += blockDim.x) m.delta[k] = tb.delta[k];
@@ -146,7 +147,7 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
 
     // ---- rank_by_score (only LambdaNDCGLoss2 needs rank order; the other losses are permutation
     // invariant and stay in document order unless the ranking was asked for) -----------------------
-    const bool sorted = TW == TW_DELTA || ranking_out != nullptr;
+    const bool sorted = rank_weighted || ranking_out != nullptr;
     if (sorted) {
       for (int j = threadIdx.x; j < P; j += blockDim.x) {
         uint32_t key = kPadKey;
@@ -161,7 +162,7 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
 
     // ---- ideal DCG ---------------------------------------------------------------------------------
     float max_dcg = 1.0f;
-    if constexpr (TW == TW_DELTA) {
+    if (rank_weighted) {
       for (int j = threadIdx.x; j < nb; j += blockDim.x) {
         const int y = m.raw_y[j];
         if (y < 0 || y > 31) m.hist[32] = 1;
@@ -229,6 +230,7 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
     const float mid = 0.5f * (smax + smin);
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
     const int fill = Lp > L ? Lp : L;
+    float diag = 0.0f;
     for (int p = threadIdx.x; p < fill; p += blockDim.x) {
       float fa = factored ? 0.0f : -1.0e30f, fb = 0.0f, fe = 0.0f;                // padding
       float fg = TW == TW_HINGE ? -1.0e30f : 0.0f;
@@ -241,7 +243,9 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
         const float s = m.raw_s[d];
         const int y = m.raw_y[d];
         if constexpr (TW == TW_DELTA) fg = gain_of_grade(y) * inv_max_dcg;
+        else if (TW == TW_TWO && variant != 0) fg = gain_of_grade(y) * inv_max_dcg / tb.disc[p];
         else fg = static_cast<float>(y);
+        if constexpr (TW == TW_TWO) diag += fg;   // the pairs (i, i): w_i * log2(1 + e^0)
         if constexpr (TW == TW_HINGE) {
           fa = s;                                // raw score: the hinge works on s_i - s_j itself
         } else if (factored) {
@@ -266,11 +270,11 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
       if constexpr (TW == TW_HINGE) wl = cta_tiles<TW, false>(m, tb, nb, lane, warp);
       else wl = factored ? cta_tiles<TW, true>(m, tb, nb, lane, warp) : cta_tiles<TW, false>(m, tb, nb, lane, warp);
     }
-    float loss = cta_sum(wl, m.red);   // barriers inside also publish gacc
+    float loss = cta_sum(wl + diag, m.red);   // barriers inside also publish gacc
     float gmul = gscale;
     if constexpr (TW == TW_HINGE) {
       gmul = 1.0f;
-      if (dcg_mod) {
+      if (variant) {
         // pairwise_additive.py:132-133: -1 / ln(2 + h); d/dh = 1 / ((2 + h) ln^2(2 + h))
         const float lg = logf(2.0f + loss);
         gmul = 1.0f / ((2.0f + loss) * lg * lg);

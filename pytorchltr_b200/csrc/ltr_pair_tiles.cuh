@@ -52,7 +52,8 @@ struct PairSoA {
   float* g;   // weight basis: normalised gain G (NDCG2) or float(rel) (ARP2, logistic)
 };
 
-enum : int { TW_UNIT = 0, TW_DIFF = 1, TW_DELTA = 2, TW_HINGE = 3 };   // w = 1 | |g_i - g_j| | delta |g_i - g_j|; hinge
+// pair weight: 1 | |g_i - g_j| | delta |g_i - g_j| (winner by relevance); hinge; two-sided w_i, w_j
+enum : int { TW_UNIT = 0, TW_DIFF = 1, TW_DELTA = 2, TW_HINGE = 3, TW_TWO = 4 };
 
 // One pair: row (ra, re, rg) against column (cx, ce, cg), cx = b_j (factored) or sigma s_j
 // (stable).  racc / cacc receive -lambda' / +lambda', lambda' > 0 when the row wins; the caller
@@ -74,6 +75,44 @@ __device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx
     const float cnt = act ? (gd > 0.0f ? 1.0f : -1.0f) : 0.0f;   // +1: the row wins
     racc -= cnt;
     cacc += cnt;
+    return;
+  }
+  if constexpr (TW == TW_TWO) {
+    // LambdaARPLoss1 / LambdaNDCGLoss1 (pairwise_lambda.py:114-117, :165-173): every ORDERED pair
+    // carries the weight of its first document, so an unordered pair contributes
+    //   w_i log2(1 + e^-x) + w_j log2(1 + e^+x),   x = sigma (s_i - s_j),
+    // and d/ds_i = sigma / ln 2 * (w_j sigmoid(x) - w_i sigmoid(-x)) = -d/ds_j.
+    // rg / cg hold the weights; dw is the row's validity (1, or 0 for a padded row, whose weight
+    // is 0 as well); padded columns have b = 0 and weight 0.
+    if constexpr (FACTORED) {
+      const float q = ra * cx;               // e^-x
+      const float p = q + 1.0f;
+      const float r = rcp_approx(p);         // sigmoid(x)
+      const float lg = lg2_approx(p);        // log2(1 + e^-x); log2(1 + e^x) = lg + (e_i - e_j)
+      const float wj = cg * dw;
+      lacc = fmaf(rg + wj, lg, lacc);
+      lacc = fmaf(wj, re - ce, lacc);
+      const float gc = r * fmaf(-rg, q, wj);
+      racc += gc;
+      cacc -= gc;
+    } else {
+      // stable form; padding is (score -1e30, weight 0): every term is 0 * finite
+      const float x = ra - cx;
+      const float u = -fabsf(x) * kLog2e;
+      const float t = ex2_approx(u);
+      const float p = 1.0f + t;
+      const float r = rcp_approx(p);
+      const float lg = lg2_approx(p);
+      const float tr = t * r;
+      const bool xpos = x >= 0.0f;
+      const float l_ij = xpos ? lg : lg - u;
+      const float l_ji = xpos ? lg - u : lg;
+      lacc = fmaf(rg, l_ij, lacc);
+      lacc = fmaf(cg, l_ji, lacc);
+      const float gc = cg * (xpos ? r : tr) - rg * (xpos ? tr : r);
+      racc += gc;
+      cacc -= gc;
+    }
     return;
   }
   float ws;   // signed weight, > 0 when the row (i) wins
@@ -148,16 +187,18 @@ __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict_
   const bool active = lane < C;
   const int me = active ? lane : 0;
   const float* colx = FACTORED ? it.b : it.a;
-  float ra[R], re[R], rg[R];
+  float ra[R], re[R], rg[R], rv[R];
   load_chunk<R>(it.a, me * R, ra);
   load_chunk<R>(it.g, me * R, rg);
   if constexpr (FACTORED) load_chunk<R>(it.e, me * R, re);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
+    rv[r] = 1.0f;
     if constexpr (FACTORED) {
       const bool valid = active && (me * R + r < n);
       ra[r] = valid ? ra[r] : 0.0f;
-      rg[r] = valid ? rg[r] : kBigGain;
+      rg[r] = valid ? rg[r] : (TW == TW_TWO ? 0.0f : kBigGain);
+      rv[r] = valid ? 1.0f : 0.0f;
     } else {
       re[r] = 0.0f;                          // stable form: padding is already (-1e30, gain 0)
     }
@@ -177,7 +218,7 @@ __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict_
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = r + 1; c < R; ++c) {
-        float dw = 1.0f;
+        float dw = rv[r];
         if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
         pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], FACTORED ? ce[c] : 0.0f, cg[c], dw, lacc,
                                 racc[r], racc[c]);
@@ -206,7 +247,7 @@ __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict_
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = 0; c < R; ++c) {
-        float dw = 1.0f;
+        float dw = rv[r];
         if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
         pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], FACTORED ? ce[c] : 0.0f, cg[c], dw, tl, tr[r],
                                 tc[c]);

@@ -170,7 +170,7 @@ template <int TW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
 pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, float sigma, int vec_ok,
-                 int dcg_mod, float* __restrict__ loss_out, float* __restrict__ grad_out,
+                 int variant, float* __restrict__ loss_out, float* __restrict__ grad_out,
                  int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
                  unsigned int* __restrict__ queue, const PairTables* __restrict__ tabs) {
   const PairTables& tb = *tabs;
@@ -238,7 +238,8 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     float ss[kWarpE];
 #pragma unroll
     for (int r = 0; r < kWarpE; ++r) { doc[r] = lane * kWarpE + r; ss[r] = sv[r]; }
-    if (TW == TW_DELTA || ranking_out != nullptr) {
+    const bool rank_weighted = TW == TW_DELTA || (TW == TW_TWO && variant != 0);   // NDCG losses
+    if (rank_weighted || ranking_out != nullptr) {
       uint32_t ekey[kWarpE];   // exact keys (document order for now)
       uint32_t pk[kWarpE];
 #pragma unroll
@@ -275,7 +276,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
 
     // ---- ideal DCG over the valid documents --------------------------------------------------------
     float max_dcg = 1.0f;
-    if constexpr (TW == TW_DELTA) {
+    if (rank_weighted) {
       int ymax = -2147483647, ymin = 2147483647;
 #pragma unroll
       for (int r = 0; r < kWarpE; ++r) {
@@ -345,6 +346,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         fb[r] = 0.0f; fe[r] = 0.0f; fg[r] = TW == TW_HINGE ? -1.0e30f : 0.0f;
         if (p < nb) {
           if constexpr (TW == TW_DELTA) fg[r] = gain_of_grade(ys[r]) * inv_max_dcg;
+          else if (TW == TW_TWO && variant != 0) fg[r] = gain_of_grade(ys[r]) * inv_max_dcg / tb.disc[p];
           else fg[r] = static_cast<float>(ys[r]);
           if constexpr (TW == TW_HINGE) {
             fa[r] = ss[r];                       // raw score: the hinge works on s_i - s_j itself
@@ -372,6 +374,11 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
 
     // ---- all pairs, once ----------------------------------------------------------------------------
     float lacc = 0.0f;
+    float diag = 0.0f;   // ARP1 / NDCG1 also count the pairs (i, i): w_i * log2(1 + e^0) = w_i
+    if constexpr (TW == TW_TWO) {
+      const float4 w4 = reinterpret_cast<const float4*>(ws.fg)[lane];
+      diag = (w4.x + w4.y) + (w4.z + w4.w);   // padding carries weight 0
+    }
     if (nb > 1) {
       if (factored) {
         const int R = (nb + 31) >> 5;
@@ -390,11 +397,11 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       }
     }
     __syncwarp();
-    float loss = warp_sum(lacc);
+    float loss = warp_sum(lacc + diag);
     float gmul = gscale;
     if constexpr (TW == TW_HINGE) {
       gmul = 1.0f;
-      if (dcg_mod) {
+      if (variant) {
         // pairwise_additive.py:132-133: -1 / ln(2 + h); d/dh = 1 / ((2 + h) ln^2(2 + h))
         const float lg = logf(2.0f + loss);
         gmul = 1.0f / ((2.0f + loss) * lg * lg);

@@ -411,7 +411,7 @@ def test_cuda_full_size_ranking_and_ndcg():
 
 
 # ------------------------------------------------------------------ slow paths of the tile kernels
-@pytest.mark.parametrize("mode", ["logistic", "arp2", "ndcg2"])
+@pytest.mark.parametrize("mode", ["logistic", "arp1", "arp2", "ndcg1", "ndcg2"])
 @pytest.mark.parametrize("B,L", [(6, 37), (8, 128), (4, 300), (2, 1024)])
 def test_cuda_large_score_range_uses_stable_form(mode, B, L):
     """sigma * (max - min) * log2(e) > 64: the factored exponential is replaced by exp(-|x|)."""
@@ -465,3 +465,17 @@ def test_cuda_lambda_ranking_out_matches_rank_by_score():
         for mode in (_lib.LAM_ARP1, _lib.LAM_ARP2, _lib.LAM_NDCG1, _lib.LAM_NDCG2):
             _, _, ranking = _ops.launch_loss(_lib.FAMILY_LAMBDA, mode, st, yt, nt, 1.0, True, want_ranking=True)
             assert torch.equal(ranking, rank_by_score(st, nt))
+
+
+@pytest.mark.parametrize("mode", ADDITIVE + LAMBDA)
+@pytest.mark.parametrize("B,L", [(9, 5), (6, 100), (3, 300)])
+def test_cuda_generic_kernel_vs_oracle(mode, B, L, monkeypatch):
+    """LTR_KERNEL=generic routes every loss through the one-CTA-per-query reference kernel (the
+    second, independent CUDA implementation of the pair losses)."""
+    monkeypatch.setenv("LTR_KERNEL", "generic")
+    s, y, n = make_batch(500 + L, B, L)
+    n[0] = 0
+    y[np.arange(L)[None, :] >= n[:, None]] = 0
+    loss, grad = _run_cuda(mode, s, y, n, sigma=0.8)
+    ref_loss, ref_grad = _oracle_loss(mode, s, y, n, 0.8)
+    _assert_parity(loss, grad, ref_loss, ref_grad)
