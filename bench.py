@@ -121,6 +121,7 @@ def run_reference(args, cfg, rank, world):
     import numpy as np
     import oracle
     oracle.build()
+    oracle.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: use every host core
     threads = oracle.max_threads()
     family, mode = ORACLE_MODE[cfg["loss"]] if "loss" in cfg else ("metric", cfg["metric"])
     L = cfg["L"]
@@ -238,7 +239,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     import pytorchltr_b200.evaluation as ltr_eval
     import pytorchltr_b200.loss as ltr_loss
     from pytorchltr_b200 import _lib, _ops
-    from pytorchltr_b200.distributed import global_sum_count, shard_bounds
+    from pytorchltr_b200.distributed import shard_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -278,22 +279,34 @@ def run_ours(args, cfg, rank, local_rank, world):
     pool_bytes = pool_n * in_bytes
     torch.cuda.synchronize()
 
-    red = torch.zeros(2, device=dev)
+    # N > 1: the path's only exchange is the 2-element [sum loss, #queries] all-reduce behind the
+    # global mean.  Its input is produced inside the (graph-captured) step; the collective itself
+    # is enqueued after the step, asynchronously, so it overlaps the next step's kernels.
+    red = [torch.tensor([0.0, float(B)], device=dev) for _ in range(pool_n)] if world > 1 else None
+    pending = []
 
     metric_out = [None] * pool_n
 
     def step(i):
         s, y, n = pool[i % pool_n]
         if is_metric:
-            metric_out[i % pool_n] = loss_fn(s, y, n)
-            return metric_out[i % pool_n]
-        s.grad = None
-        out = loss_fn(s, y, n)
+            out = loss_fn(s, y, n)
+            metric_out[i % pool_n] = out
+        else:
+            s.grad = None
+            out = loss_fn(s, y, n)
         if world > 1:
-            # the path's only exchange: [sum loss, #queries] across the query shards
-            red.copy_(global_sum_count(out))
-        out.sum().backward()
+            r = red[i % pool_n]
+            torch.sum(out.detach(), dim=0, keepdim=True, out=r[:1])   # r[1] (the count) is constant
+        if not is_metric:
+            out.sum().backward()
         return out
+
+    def exchange(i):
+        if world > 1:
+            pending.append(dist.all_reduce(red[i % pool_n], async_op=True))
+            if len(pending) > 8:
+                pending.pop(0).wait()
 
     # ---- CUDA graphs: one per pool entry (launch-bound otherwise: ~25 us of GPU work/step) ---
     graphs = None
@@ -320,11 +333,13 @@ def run_ours(args, cfg, rank, local_rank, world):
             graphs = None
             torch.cuda.synchronize()
 
-    def run_step(i):
+    def run_step(i, collective=True):
         if graphs is not None:
             graphs[i % pool_n].replay()
         else:
             step(i)
+        if collective:
+            exchange(i)
 
     def barrier():
         if world > 1:
@@ -342,6 +357,8 @@ def run_ours(args, cfg, rank, local_rank, world):
     ev0.record()
     for i in range(args.steps):
         run_step(args.warmup + i)
+    while pending:
+        pending.pop(0).wait()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -351,10 +368,12 @@ def run_ours(args, cfg, rank, local_rank, world):
         t_end = time.perf_counter() + 0.5
         i = 0
         while time.perf_counter() < t_end:
-            run_step(i)
+            run_step(i, collective=False)   # time-bounded: ranks may differ in step count
             i += 1
             if i % 64 == 0:
                 torch.cuda.synchronize()
+        while pending:
+            pending.pop(0).wait()
         torch.cuda.synchronize()
         clock_window = "timed region + 0.5 s of the same load"
     sampler.stop()
@@ -371,7 +390,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         import oracle
         s, y, n = pool[0]
         idx = np.arange(0, B, max(1, B // 16))
-        run_step(0)
+        run_step(0, collective=False)   # rank 0 only: must not enqueue an unmatched collective
         torch.cuda.synchronize()
         sn, yn, nn = s.detach().cpu().numpy()[idx], y.cpu().numpy()[idx], n.cpu().numpy()[idx]
         # (hinge: float32 restatement -- pairs on the kink flip between f32 and f64 rounding)
@@ -524,6 +543,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
+        oracle.set_threads(os.cpu_count() or 1)
         threads = oracle.max_threads()
         s, y, n = make_batch_numpy(1234, min(B, 64), L, cfg.get("skew", False))
 

@@ -46,8 +46,8 @@ def global_sum_count(per_query: torch.Tensor, group=None) -> torch.Tensor:
     dtype = torch.float32 if per_query.is_cuda else torch.float64
     # built from device-side fills only (no host->device copy): CUDA-graph capturable
     buf = torch.empty(2, dtype=dtype, device=per_query.device)
-    buf[0] = per_query.detach().sum().to(dtype)
-    buf[1] = float(per_query.numel())
+    buf[:1].copy_(per_query.detach().sum().to(dtype).reshape(1))
+    buf[1:].fill_(float(per_query.numel()))
     if _world(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf
