@@ -61,6 +61,15 @@ def normalise(scores: torch.Tensor, relevance: Optional[torch.Tensor], n: torch.
     return s, y, nn, B, L
 
 
+def to_host(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Device -> host copy for callers that passed CPU tensors: staged through pinned memory
+    (torch's caching host allocator) so the copy runs at full PCIe rate, then one stream sync."""
+    host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host
+
+
 def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -103,13 +112,18 @@ def launch_loss(family: int, mode: int, s: torch.Tensor, y: torch.Tensor, nn: to
 def scale_rows(g: torch.Tensor, dscores: torch.Tensor) -> torch.Tensor:
     """``g[:, None] * dscores`` on the device (ltr_scale_rows)."""
     B, L = dscores.shape
-    g = g.detach().to(device=dscores.device, dtype=torch.float32)
+    g = g.detach()
     # `loss.sum().backward()` hands over a broadcast (stride-0) gradient: read it in place
     # instead of materialising B copies of the same number
     if B > 1 and g.stride(0) == 0:
         g_stride = 0
+        if not g.is_cuda:
+            # CPU caller: the scalar is already on the host -- ship it as a fill, not as a copy
+            g = torch.full((1,), float(g[0]), dtype=torch.float32, device=dscores.device)
+        else:
+            g = g.to(device=dscores.device, dtype=torch.float32)
     else:
-        g = g.contiguous()
+        g = g.to(device=dscores.device, dtype=torch.float32).contiguous()
         g_stride = 1
     out = torch.empty_like(dscores)
     if B == 0:
@@ -150,7 +164,7 @@ class _FusedLoss(torch.autograd.Function):
         if out.dtype != scores.dtype and scores.dtype.is_floating_point:
             out = out.to(scores.dtype)
         if out.device != scores.device:
-            out = out.to(scores.device)   # synchronising D2H copy: CPU callers get CPU results
+            out = to_host(out, scores)    # synchronising D2H copy: CPU callers get CPU results
         return out
 
     @staticmethod
@@ -161,7 +175,7 @@ class _FusedLoss(torch.autograd.Function):
         if out.dtype != ctx.scores_dtype:
             out = out.to(ctx.scores_dtype)
         if out.device != ctx.scores_device:
-            out = out.to(ctx.scores_device)
+            out = to_host(out, g)
         return out.reshape(ctx.scores_shape), None, None, None, None, None
 
 
@@ -191,7 +205,7 @@ def rank_metric(metric: int, scores, relevance, n, k: Optional[int], exp: bool):
                                              _stream(dev))
         _lib.check(rc)
     if out.device != scores.device:
-        out = out.to(scores.device)
+        out = to_host(out, scores)
     return out
 
 
@@ -205,5 +219,5 @@ def rank_by_score(scores, n):
                                               out.data_ptr(), _stream(dev))
         _lib.check(rc)
     if out.device != scores.device:
-        out = out.to(scores.device)
+        out = to_host(out, scores)
     return out
