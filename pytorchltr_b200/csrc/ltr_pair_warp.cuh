@@ -167,7 +167,7 @@ __device__ __forceinline__ float gain_of_grade(int y) {
 }
 
 template <int TW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8)
 pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, float sigma, int vec_ok,
                  int variant, float* __restrict__ loss_out, float* __restrict__ grad_out,
@@ -250,25 +250,39 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       }
       warp_bitonic_sort32<kWarpE>(pk, lane);
       __syncwarp();
-      uint64_t xk[kWarpE];
 #pragma unroll
       for (int r = 0; r < kWarpE; ++r) {
         doc[r] = static_cast<int>(pk[r] & 127u);
         ss[r] = ws.raw_s[doc[r]];
-        const int p = lane * kWarpE + r;
-        xk[r] = pack_key(p < nb ? desc_key_f32(ss[r]) : kPadKey, doc[r]);
       }
-      const uint64_t next0 = __shfl_down_sync(0xffffffffu, xk[0], 1);
-      bool bad = (xk[0] > xk[1]) || (xk[1] > xk[2]) || (xk[2] > xk[3]) || (lane < 31 && xk[3] > next0);
-      if (__any_sync(0xffffffffu, bad)) {
-        // exact order needed: redo from the document-order keys
+      // The packed order is exact unless two neighbouring valid keys share their 25 key bits.
+      const uint32_t pk_next = __shfl_down_sync(0xffffffffu, pk[0], 1);
+      bool ambiguous = false;
 #pragma unroll
-        for (int r = 0; r < kWarpE; ++r) xk[r] = pack_key(ekey[r], lane * kWarpE + r);
-        warp_bitonic_sort64<kWarpE>(xk, lane);
+      for (int r = 0; r < kWarpE; ++r) {
+        const uint32_t nxt = r + 1 < kWarpE ? pk[(r + 1) % kWarpE] : pk_next;
+        ambiguous = ambiguous || (((pk[r] ^ nxt) < 128u) && (lane * kWarpE + r + 1 < nb));
+      }
+      if (__any_sync(0xffffffffu, ambiguous)) {
+        // compare against the exact (32-bit key, index) order; redo with the 64-bit network if
+        // the packed sort put two close scores the wrong way round
+        uint64_t xk[kWarpE];
 #pragma unroll
         for (int r = 0; r < kWarpE; ++r) {
-          doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
-          ss[r] = ws.raw_s[doc[r]];
+          const int p = lane * kWarpE + r;
+          xk[r] = pack_key(p < nb ? desc_key_f32(ss[r]) : kPadKey, doc[r]);
+        }
+        const uint64_t next0 = __shfl_down_sync(0xffffffffu, xk[0], 1);
+        const bool bad = (xk[0] > xk[1]) || (xk[1] > xk[2]) || (xk[2] > xk[3]) || (lane < 31 && xk[3] > next0);
+        if (__any_sync(0xffffffffu, bad)) {
+#pragma unroll
+          for (int r = 0; r < kWarpE; ++r) xk[r] = pack_key(ekey[r], lane * kWarpE + r);
+          warp_bitonic_sort64<kWarpE>(xk, lane);
+#pragma unroll
+          for (int r = 0; r < kWarpE; ++r) {
+            doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
+            ss[r] = ws.raw_s[doc[r]];
+          }
         }
       }
     }
@@ -277,16 +291,46 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     // ---- ideal DCG over the valid documents --------------------------------------------------------
     float max_dcg = 1.0f;
     if (rank_weighted) {
-      int ymax = -2147483647, ymin = 2147483647;
+      // Fast path, grades 0..7: a packed 8 x 8-bit histogram summed across the warp.
+      bool wide = false;
+      unsigned long long hist = 0ull;
 #pragma unroll
       for (int r = 0; r < kWarpE; ++r) {
-        if (lane * kWarpE + r < nb) { ymax = max(ymax, yv[r]); ymin = min(ymin, yv[r]); }
+        const bool valid = lane * kWarpE + r < nb;
+        wide = wide || (valid && static_cast<unsigned int>(yv[r]) > 7u);
+        if (valid) hist += 1ull << (8 * (yv[r] & 7));
       }
+      const bool small_grades = !__any_sync(0xffffffffu, wide);
+      int ymax = -2147483647, ymin = 2147483647;
+      if (small_grades) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        for (int o = 16; o > 0; o >>= 1) hist += __shfl_xor_sync(0xffffffffu, hist, o);   // counts <= 128 < 256
+        double acc = 0.0;
+        int start = 0;
+#pragma unroll
+        for (int g = 7; g >= 1; --g) {
+          const int cnt = static_cast<int>((hist >> (8 * g)) & 0xffull);
+          if (cnt > 0) {
+            acc += static_cast<double>(gain_of_grade(g)) *
+                   (tb.inv_disc_prefix[start + cnt] - tb.inv_disc_prefix[start]);
+            start += cnt;
+          }
+        }
+        max_dcg = static_cast<float>(acc);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kWarpE; ++r) {
+          if (lane * kWarpE + r < nb) { ymax = max(ymax, yv[r]); ymin = min(ymin, yv[r]); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+          ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        }
       }
+      if (small_grades) {
+        // done above
+      } else
       if (ymin >= 0 && ymax < 32) {
         // grade histogram by ballots; grade g occupies ideal ranks [start, start + cnt)
         double acc = 0.0;
