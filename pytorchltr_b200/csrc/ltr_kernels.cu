@@ -693,7 +693,11 @@ int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const v
                     float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
   const int P = next_pow2(L);
   const int threads = kCtaWarps * 32;
-  const size_t smem = cta_smem_bytes(L, P);
+  // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes, and room for the
+  // double buffer next to everything else
+  int tma = (L % 4 == 0) && aligned16(scores) && aligned16(rel) && cta_smem_bytes(L, P, rel_bytes) <= 200u * 1024u;
+  if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
+  const size_t smem = cta_smem_bytes(L, P, tma ? rel_bytes : 0);
   int grid = 0;
   int rc = persistent_grid(pair_cta_kernel<TW>, threads, smem, B, di, &grid);
   if (rc != LTR_OK) return rc;
@@ -701,7 +705,7 @@ int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const v
   rc = pair_tables(st, &tabs);
   if (rc != LTR_OK) return rc;
   pair_cta_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma, dcg_mod,
-                                                   loss_out, grad_out, ranking_out, loss_sum, tabs);
+                                                   tma, loss_out, grad_out, ranking_out, loss_sum, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }

@@ -2,7 +2,10 @@
 // point (4096, 1024), config (65536, 512)): the sigmoid-weighted pair losses evaluated ONCE per
 // unordered pair on 128 x 128 rank tiles.
 //
-// Per query: coalesced row staging -> CTA-wide bitonic argsort in shared memory
+// Per query: the padded row (scores + relevance) is staged into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier), double buffered so that the NEXT query's row is in flight while
+// the current one is being processed (plain coalesced loads when the row is not 16-byte
+// aligned or shared memory is short) -> CTA-wide bitonic argsort in shared memory
 // (rank_by_score, utils/tensor_operations.py:48-64) -> ideal DCG from a shared-memory grade
 // histogram (_max_dcg, pairwise_lambda.py:231-241; a second sort if the grades do not fit) ->
 // per-document factors in rank order -> the S (S + 1) / 2 rank tiles are handed to the warps of
@@ -29,15 +32,25 @@ struct CtaSmem {
   float* gcol;        // [W*128]  per-warp column accumulators of the current tile
   float* red;         // [40]
   int* hist;          // [36]     grade histogram + flags + tile counter
+  // TMA staging (tma != 0): two row buffers and their mbarriers; raw_s then aliases tma_s[cur]
+  float* tma_s1;          // [L]  second score buffer (the first one is raw_s)
+  unsigned char* tma_y0;  // [L * rel_bytes] relevance as stored in HBM, buffer 0
+  unsigned char* tma_y1;  // buffer 1
+  uint64_t* bars;         // [2]
 };
 
-__host__ __device__ inline size_t cta_smem_bytes(int L, int P) {
+__host__ __device__ inline size_t cta_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
+
+// rel_bytes = 0: no TMA staging buffers
+__host__ __device__ inline size_t cta_smem_bytes(int L, int P, int tma_rel_bytes) {
   const size_t Lp = (static_cast<size_t>(L) + 127) / 128 * 128;
-  return 8u * P + 16u * Lp + 4u * (Lp + 8) + 4u * L + 4u * L + 4u * Lp + 4u * Lp + 4u * kCtaWarps * 128 +
-         4u * 40 + 4u * 40;
+  size_t bytes = 8u * P + 16u * Lp + 4u * (Lp + 8) + 4u * kCtaWarps * 128 + 4u * Lp + 4u * Lp +
+                 cta_align16(4u * L) + cta_align16(4u * L) + 4u * 40 + 4u * 40;
+  if (tma_rel_bytes) bytes += cta_align16(4u * L) + 2u * cta_align16(static_cast<size_t>(tma_rel_bytes) * L) + 16u;
+  return bytes;
 }
 
-__device__ __forceinline__ CtaSmem cta_carve(unsigned char* base, int L, int P) {
+__device__ __forceinline__ CtaSmem cta_carve(unsigned char* base, int L, int P, int tma_rel_bytes) {
   const int Lp = (L + 127) / 128 * 128;
   CtaSmem m;
   m.keys = reinterpret_cast<uint64_t*>(base);                 base += 8u * P;
@@ -49,10 +62,17 @@ __device__ __forceinline__ CtaSmem cta_carve(unsigned char* base, int L, int P) 
   m.gcol = reinterpret_cast<float*>(base);                    base += 4u * kCtaWarps * 128;
   m.gacc = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.doc = reinterpret_cast<int*>(base);                       base += 4u * Lp;
-  m.raw_s = reinterpret_cast<float*>(base);                   base += 4u * L;
-  m.raw_y = reinterpret_cast<int*>(base);                     base += 4u * L;
+  m.raw_s = reinterpret_cast<float*>(base);                   base += cta_align16(4u * L);
+  m.raw_y = reinterpret_cast<int*>(base);                     base += cta_align16(4u * L);
   m.red = reinterpret_cast<float*>(base);                     base += 4u * 40;
-  m.hist = reinterpret_cast<int*>(base);
+  m.hist = reinterpret_cast<int*>(base);                      base += 4u * 40;
+  m.tma_s1 = nullptr; m.tma_y0 = nullptr; m.tma_y1 = nullptr; m.bars = nullptr;
+  if (tma_rel_bytes) {
+    m.tma_s1 = reinterpret_cast<float*>(base);                base += cta_align16(4u * L);
+    m.tma_y0 = base;                                          base += cta_align16(static_cast<size_t>(tma_rel_bytes) * L);
+    m.tma_y1 = base;                                          base += cta_align16(static_cast<size_t>(tma_rel_bytes) * L);
+    m.bars = reinterpret_cast<uint64_t*>(base);
+  }
   return m;
 }
 
@@ -112,14 +132,14 @@ __device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& t
 }
 
 template <int TW>
-__global__ void __launch_bounds__(kCtaWarps * 32)
+__global__ void __launch_bounds__(kCtaWarps * 32, 3)
 pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                 const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
-                float* __restrict__ loss_out, float* __restrict__ grad_out,
+                int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,
                 int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
                 const PairTables* __restrict__ tabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const CtaSmem m = cta_carve(smem_raw, L, P);
+  CtaSmem m = cta_carve(smem_raw, L, P, tma ? rel_bytes : 0);
   const PairTables& tb = *tabs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float gscale = sigma * kLog2e;
@@ -133,14 +153,49 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
     for (int k = threadIdx.x; k < Lp0 + 8; k += blockDim.x) m.delta[k] = tb.delta[k];
   }
 
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  // TMA row staging: one thread arms the buffer's mbarrier with the byte count and issues the two
+  // bulk copies; everybody waits on the barrier's phase before touching the row.
+  const uint32_t row_s_bytes = 4u * L, row_y_bytes = static_cast<uint32_t>(rel_bytes) * L;
+  float* const buf_s0 = m.raw_s;
+  float* const buf_s1 = m.tma_s1;
+  auto issue_row = [&](int q, int buf) {
+    uint64_t* bar = m.bars + buf;
+    mbar_arrive_expect_tx(bar, row_s_bytes + row_y_bytes);
+    tma_load_1d(buf ? buf_s1 : buf_s0, scores + static_cast<size_t>(q) * L, row_s_bytes, bar);
+    tma_load_1d(buf ? m.tma_y1 : m.tma_y0,
+                static_cast<const unsigned char*>(rel) + static_cast<size_t>(q) * row_y_bytes, row_y_bytes, bar);
+  };
+  if (tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(m.bars, 1);
+      mbar_init(m.bars + 1, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < B) issue_row(blockIdx.x, 0);
+  }
+
+  int iter = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x, ++iter) {
     __syncthreads();   // previous query fully consumed
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
     const int Lp = ((nb + 127) >> 7) << 7;   // ranks covered by tiles
-    for (int j = threadIdx.x; j < L; j += blockDim.x) {
-      m.raw_s[j] = scores[base + j];
-      m.raw_y[j] = load_int_clamped(rel, rel_bytes, base + j);
+    if (tma) {
+      const int cur = iter & 1;
+      if (threadIdx.x == 0 && b + static_cast<int>(gridDim.x) < B) {
+        fence_proxy_async();   // the other buffer was last written through the generic proxy
+        issue_row(b + gridDim.x, cur ^ 1);
+      }
+      mbar_wait(m.bars + cur, (iter >> 1) & 1);
+      m.raw_s = cur ? buf_s1 : buf_s0;
+      const unsigned char* ybuf = cur ? m.tma_y1 : m.tma_y0;
+      for (int j = threadIdx.x; j < L; j += blockDim.x) m.raw_y[j] = load_int_clamped(ybuf, rel_bytes, j);
+    } else {
+      for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        m.raw_s[j] = scores[base + j];
+        m.raw_y[j] = load_int_clamped(rel, rel_bytes, base + j);
+      }
     }
     if (threadIdx.x < 36) m.hist[threadIdx.x] = 0;
     __syncthreads();
