@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libltr_sm100.so")
+# LTR_SM100_LIB overrides the in-tree build (A/B testing of kernel variants)
+LIB_PATH = os.environ.get("LTR_SM100_LIB") or os.path.join(_HERE, "csrc", "libltr_sm100.so")
 
 # every symbol include/ltr_sm100.h declares
 SYMBOLS = (

@@ -51,6 +51,25 @@ def rank_by_score(scores: _torch.FloatTensor, n: _torch.LongTensor,
     return _ops.rank_by_score(scores, n)
 
 
+def rank_by_plackettluce(scores: _torch.FloatTensor, n: _torch.LongTensor,
+                         generator: Optional[_torch.Generator] = None) -> _torch.LongTensor:
+    """Samples a ranking from the Plackett-Luce distribution of the scores, padded documents
+    last (reference :67-91).
+
+    The reference sorts ``log(-log(u)) - log_softmax(scores)`` in ascending order; the
+    log-softmax normaliser is constant within a query, so that order is the descending order of
+    ``scores - log(-log(u))`` (Gumbel-max).  The uniform draws come from torch's generator, the
+    ranking itself from the ``ltr_rank_by_score`` kernel.
+    """
+    if scores.dim() == 3:
+        scores = scores.reshape(scores.shape[0], scores.shape[1])
+    kwargs = {} if generator is None else {"generator": generator}
+    u = _torch.rand(scores.shape, device=scores.device, dtype=_torch.float32, **kwargs)
+    u = u.clamp_(min=1e-38)
+    perturbed = scores.to(_torch.float32) - _torch.log(-_torch.log(u))
+    return _ops.rank_by_score(perturbed, n)
+
+
 def batch_pairs(x: _torch.Tensor) -> _torch.Tensor:
     """``p[b, i, j, 0] = x[b, i]``, ``p[b, i, j, 1] = x[b, j]`` (reference :94-119).
 

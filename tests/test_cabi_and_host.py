@@ -66,6 +66,7 @@ def test_public_surface_mirrors_reference():
                        (p.utils.rank_by_score, ["scores", "n", "generator"]),
                        (p.utils.mask_padded_values, ["xs", "n", "mask_value", "mutate"]),
                        (p.utils.tiebreak_argsort, ["x", "descending", "generator"]),
+                       (p.utils.rank_by_plackettluce, ["scores", "n", "generator"]),
                        (p.utils.batch_pairs, ["x"])):
         assert list(inspect.signature(fn).parameters) == params
 

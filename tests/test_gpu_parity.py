@@ -496,3 +496,25 @@ def test_cuda_warp_kernel_dynamic_queue_many_queries():
     # so compare two full runs bit for bit (the kernel is deterministic per query)
     loss2, grad2 = _run_cuda("ndcg2", s, y, n)
     assert np.array_equal(loss, loss2) and np.array_equal(grad, grad2)
+
+
+def test_cuda_rank_by_plackettluce_statistics():
+    """Plackett-Luce sampling (reference tests/utils/test_tensor_operations.py:24-127 style):
+    the first rank follows softmax(scores), padded documents always come last."""
+    from pytorchltr_b200.utils import rank_by_plackettluce
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(42)
+    runs = 4000
+    scores = torch.tensor([[5.0, 3.0, 2.0, 1.0, 9.0]], device=dev).repeat(runs, 1)
+    n = torch.full((runs,), 4, dtype=torch.int32, device=dev)
+    rk = rank_by_plackettluce(scores.reshape(runs, 5, 1), n, generator=gen)
+    assert rk.shape == (runs, 5) and rk.dtype == torch.int64
+    assert bool((rk[:, 4] == 4).all())                       # the padded document is last
+    first = torch.bincount(rk[:, 0], minlength=5).float().cpu().numpy()[:4] / runs
+    expected = torch.softmax(torch.tensor([5.0, 3.0, 2.0, 1.0]), dim=0).numpy()
+    assert first == approx(expected, abs=0.03)
+    # second rank given the first: P(second = j) = sum_i p_i p_j / (1 - p_i)
+    second = torch.bincount(rk[:, 1], minlength=5).float().cpu().numpy()[:4] / runs
+    p = expected.astype(np.float64)
+    exp2 = np.array([sum(p[i] * p[j] / (1 - p[i]) for i in range(4) if i != j) for j in range(4)])
+    assert second == approx(exp2, abs=0.03)
