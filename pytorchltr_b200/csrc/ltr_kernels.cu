@@ -19,6 +19,7 @@
 #include "ltr_common.cuh"
 #include "ltr_metrics_warp.cuh"
 #include "ltr_pair_cta.cuh"
+#include "ltr_pair_ring.cuh"
 #include "ltr_pair_warp.cuh"
 #include "ltr_sm100.h"
 
@@ -710,6 +711,34 @@ int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const v
   return LTR_OK;
 }
 
+// LTR_KERNEL=tiles keeps the 128 x 128 rank-tile kernel for every L > 128 (A-B timing).
+inline bool force_tiles() {
+  const char* v = getenv("LTR_KERNEL");
+  return v && strcmp(v, "tiles") == 0;
+}
+
+template <int TW>
+int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                     int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
+                     float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+  const int P = next_pow2(L);
+  const int threads = kRingWarps * 32;
+  // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes
+  int tma = (L % 4 == 0) && aligned16(scores) && aligned16(rel);
+  if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
+  const size_t smem = ring_smem_bytes(L, tma ? rel_bytes : 0);
+  int grid = 0;
+  int rc = persistent_grid(pair_ring_kernel<TW>, threads, smem, B, di, &grid);
+  if (rc != LTR_OK) return rc;
+  const PairTables* tabs = nullptr;
+  rc = pair_tables(st, &tabs);
+  if (rc != LTR_OK) return rc;
+  pair_ring_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma, dcg_mod,
+                                                    tma, loss_out, grad_out, ranking_out, loss_sum, tabs);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,
                   int n_bytes, int B, int L, float sigma, float* loss_out, float* grad_out,
                   int64_t* ranking_out, float* loss_sum, void* stream) {
@@ -723,11 +752,15 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!force_generic()) {
-    // every unordered pair once: one warp per query for short lists, one CTA per query and
-    // 128 x 128 rank tiles for longer ones
+    // every unordered pair once: one warp per query for short lists, one CTA per query on a
+    // query-wide chunk ring up to 1024 documents, 128 x 128 rank tiles beyond
+    const bool ring = L <= kRingMaxL && !force_tiles();
 #define LTR_TILED(TWMODE, DCG)                                                                          \
   return L <= kWarpL                                                                                    \
              ? launch_pair_warp<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \
+                                        grad_out, ranking_out, loss_sum, st, di)                        \
+         : ring                                                                                         \
+             ? launch_pair_ring<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \
                                         grad_out, ranking_out, loss_sum, st, di)                        \
              : launch_pair_cta<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,   \
                                        grad_out, ranking_out, loss_sum, st, di)

@@ -119,17 +119,24 @@ __device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx
   if constexpr (TW == TW_DELTA) ws = dw * gd;
   else if constexpr (TW == TW_DIFF) ws = gd;
   else ws = fminf(fmaxf(gd, -1.0f), 1.0f);   // integer grades: sign(gd)
-  float sg, lp;
   if constexpr (FACTORED) {
+    // Branch-free in the winner (12 FP32 + 2 MUFU per pair).  With w = |ws|, r = 1 / p:
+    //   row wins:     loss w lg2(p),               row gradient -w q / p = w r - w
+    //   column wins:  loss w (lg2(p) + e_i - e_j), row gradient +w / p   = w r
+    // so with K = max(ws, 0) (= w iff the row wins):
+    //   loss += w lg2(p) + (K - ws) (e_i - e_j),   row += w r - K,   column -= w r - K.
+    // Padding (q = 0, p = r = 1, lg = 0, ws >= 0) gives fma(w, 1, -w) = 0 exactly.
     const float q = ra * cx;
     const float p = q + 1.0f;
     const float r = rcp_approx(p);
     const float lg = lg2_approx(p);
-    const float qr = q * r;
-    const bool iwins = gd > 0.0f;
-    sg = iwins ? qr : r;
-    const float t1 = (ce - re) - lg;         // -(lg2(p) + (e_i - e_j))
-    lp = iwins ? lg : t1;                    // ws * lp == |ws| * log2(1 + e^-x)
+    const float K = fmaxf(ws, 0.0f);
+    lacc = fmaf(fabsf(ws), lg, lacc);
+    lacc = fmaf(K - ws, re - ce, lacc);
+    const float v = fmaf(fabsf(ws), r, -K);
+    racc += v;
+    cacc -= v;
+    return;
   } else {
     const float d = ra - cx;                 // x if the row wins, -x otherwise
     const float u = -fabsf(d) * kLog2e;
@@ -139,14 +146,14 @@ __device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx
     const float lg = lg2_approx(p);
     const bool iwins = gd > 0.0f;
     const bool xneg = iwins ? d < 0.0f : d > 0.0f;   // x = sigma (s_winner - s_loser) < 0
-    sg = xneg ? r : t * r;
+    const float sg = xneg ? r : t * r;
     const float l = xneg ? lg - u : lg;
-    lp = iwins ? l : -l;
+    const float lp = iwins ? l : -l;           // ws * lp == |ws| * log2(1 + e^-x)
+    lacc = fmaf(ws, lp, lacc);
+    const float lam = ws * sg;
+    racc -= lam;
+    cacc += lam;
   }
-  lacc = fmaf(ws, lp, lacc);
-  const float lam = ws * sg;
-  racc -= lam;
-  cacc += lam;
 }
 
 // R consecutive floats starting at p[first] (first is a multiple of R; p is 16-byte aligned)
