@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LTR_VERSION 100            /* major*100 + minor */
+#define LTR_VERSION 101            /* major*100 + minor */
 #define LTR_MAX_LIST_SIZE 4096
 
 /* error codes */
@@ -97,6 +97,26 @@ int ltr_pairwise_additive(int mode, const float *scores, const void *rel, int re
 int ltr_lambda(int mode, const float *scores, const void *rel, int rel_bytes, const void *n,
                int n_bytes, int B, int L, float sigma, float *loss_out, float *dscores_out,
                int64_t *ranking_out, float *loss_sum, void *stream);
+
+/*
+ * Same two entry points with a caller-owned SCHEDULING WORKSPACE (device memory, 16-byte
+ * aligned, at least ltr_schedule_workspace_bytes(B) bytes, contents irrelevant on entry and
+ * undefined on return; it must not be shared by launches that may run concurrently).
+ * The cost of a query grows with n^2, so a batch mixes queries that differ 4x and more in work.
+ * With the workspace the launch first sorts the queries by decreasing n (one small kernel on
+ * `stream`) and the loss kernel starts the long ones first, handing the rest out dynamically:
+ * same results, shorter tail.  Without it (or workspace == NULL) the queries are taken in
+ * batch order.  Still no allocation, no synchronisation, CUDA-graph capturable.
+ */
+size_t ltr_schedule_workspace_bytes(int B);
+int ltr_pairwise_additive_ws(int mode, const float *scores, const void *rel, int rel_bytes,
+                             const void *n, int n_bytes, int B, int L, float sigma,
+                             float *loss_out, float *dscores_out, float *loss_sum,
+                             void *workspace, size_t workspace_bytes, void *stream);
+int ltr_lambda_ws(int mode, const float *scores, const void *rel, int rel_bytes, const void *n,
+                  int n_bytes, int B, int L, float sigma, float *loss_out, float *dscores_out,
+                  int64_t *ranking_out, float *loss_sum, void *workspace, size_t workspace_bytes,
+                  void *stream);
 
 /*
  * ListNet (top-1 softmax cross entropy).  Named by the task, absent from the reference

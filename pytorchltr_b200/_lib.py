@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("LTR_SM100_LIB") or os.path.join(_HERE, "csrc", "liblt
 SYMBOLS = (
     "ltr_version", "ltr_strerror", "ltr_last_cuda_error", "ltr_pairwise_additive", "ltr_lambda",
     "ltr_listnet", "ltr_rank_metrics", "ltr_rank_by_score", "ltr_scale_rows",
-    "ltr_host_workspace_bytes", "ltr_loss_host",
+    "ltr_host_workspace_bytes", "ltr_loss_host", "ltr_schedule_workspace_bytes",
+    "ltr_pairwise_additive_ws", "ltr_lambda_ws",
 )
 
 ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
@@ -46,6 +47,16 @@ def _declare(lib):
     lib.ltr_lambda.restype = c_int
     lib.ltr_lambda.argtypes = [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ltr_schedule_workspace_bytes.restype = c_size_t
+    lib.ltr_schedule_workspace_bytes.argtypes = [c_int]
+    lib.ltr_pairwise_additive_ws.restype = c_int
+    lib.ltr_pairwise_additive_ws.argtypes = [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                             c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_size_t, c_void_p]
+    lib.ltr_lambda_ws.restype = c_int
+    lib.ltr_lambda_ws.argtypes = [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]
     lib.ltr_listnet.restype = c_int
     lib.ltr_listnet.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_void_p]

@@ -91,14 +91,21 @@ def launch_loss(family: int, mode: int, s: torch.Tensor, y: torch.Tensor, nn: to
     lib = _lib.lib()
     with torch.cuda.device(dev):
         st = _stream(dev)
+        if family != _lib.FAMILY_LISTNET:
+            # scheduling workspace of the O(L^2) losses (longest queries first): scratch from the
+            # caching allocator, stream-ordered like the outputs
+            ws_bytes = lib.ltr_schedule_workspace_bytes(B)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if family == _lib.FAMILY_ADDITIVE:
-            rc = lib.ltr_pairwise_additive(mode, s.data_ptr(), y.data_ptr(), y.element_size(),
-                                           nn.data_ptr(), nn.element_size(), B, L, float(sigma),
-                                           loss.data_ptr(), _ptr(grad), _ptr(loss_sum), st)
+            rc = lib.ltr_pairwise_additive_ws(mode, s.data_ptr(), y.data_ptr(), y.element_size(),
+                                              nn.data_ptr(), nn.element_size(), B, L, float(sigma),
+                                              loss.data_ptr(), _ptr(grad), _ptr(loss_sum),
+                                              ws.data_ptr(), ws_bytes, st)
         elif family == _lib.FAMILY_LAMBDA:
-            rc = lib.ltr_lambda(mode, s.data_ptr(), y.data_ptr(), y.element_size(),
-                                nn.data_ptr(), nn.element_size(), B, L, float(sigma),
-                                loss.data_ptr(), _ptr(grad), _ptr(ranking), _ptr(loss_sum), st)
+            rc = lib.ltr_lambda_ws(mode, s.data_ptr(), y.data_ptr(), y.element_size(),
+                                   nn.data_ptr(), nn.element_size(), B, L, float(sigma),
+                                   loss.data_ptr(), _ptr(grad), _ptr(ranking), _ptr(loss_sum),
+                                   ws.data_ptr(), ws_bytes, st)
         elif family == _lib.FAMILY_LISTNET:
             rc = lib.ltr_listnet(s.data_ptr(), y.data_ptr(), y.element_size(), nn.data_ptr(),
                                  nn.element_size(), B, L, loss.data_ptr(), _ptr(grad),

@@ -664,26 +664,120 @@ inline int pair_tables(cudaStream_t st, const PairTables** out) {
   return LTR_OK;
 }
 
+// ---- longest-first query schedule ------------------------------------------------------------------
+// Pair counts grow with n^2, so the queries of one batch differ 4x and more in cost.  With a
+// scheduling workspace the launch is preceded by a counting sort of the queries by decreasing n
+// (one CTA: shared-memory histogram, scan, scatter); the loss kernels then start the long queries
+// first and hand out the rest through a device-wide counter, which turns the tail of the launch
+// into short queries (longest-processing-time-first list scheduling).
+// Workspace layout: queue {next, done} + padding (16 bytes) | order uint32 [B].
+constexpr int kOrderThreads = 1024;
+__global__ void __launch_bounds__(kOrderThreads)
+order_queries_kernel(const void* __restrict__ n, int n_bytes, int B, int L, unsigned int* __restrict__ queue,
+                     unsigned int* __restrict__ order) {
+  __shared__ unsigned int hist[LTR_MAX_LIST_SIZE + 1];
+  __shared__ unsigned int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i <= L; i += kOrderThreads) hist[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < B; i += kOrderThreads) atomicAdd(&hist[load_n(n, n_bytes, i, L)], 1u);
+  __syncthreads();
+  // exclusive scan in order of DECREASING n: entry e stands for n = L - e
+  const int K = (L + kOrderThreads) / kOrderThreads;   // ceil((L + 1) / threads)
+  unsigned int local = 0u;
+  for (int e = tid * K; e < (tid + 1) * K && e <= L; ++e) local += hist[L - e];
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  unsigned int run = incl - local + (warp > 0 ? wsum[warp - 1] : 0u);
+  for (int e = tid * K; e < (tid + 1) * K && e <= L; ++e) {
+    const unsigned int cnt = hist[L - e];
+    hist[L - e] = run;
+    run += cnt;
+  }
+  __syncthreads();
+  for (int i = tid; i < B; i += kOrderThreads) {
+    const unsigned int pos = atomicAdd(&hist[load_n(n, n_bytes, i, L)], 1u);
+    order[pos] = static_cast<unsigned int>(i);
+  }
+  if (tid == 0) { queue[0] = 0u; queue[1] = 0u; }
+}
+
+struct Schedule {
+  unsigned int* queue;          // {next query, finished CTAs / warps}
+  const unsigned int* order;    // queries by decreasing n, or nullptr (natural order)
+};
+
+inline size_t schedule_bytes(int B) { return 16u + 4u * static_cast<size_t>(B > 0 ? B : 0); }
+
+// `slots` = queries that start at once (resident CTAs / warps): below that nothing queues and the
+// order is irrelevant.  LTR_SCHEDULE=natural disables the sort (A-B timing).
+inline int make_schedule(const void* n, int n_bytes, int B, int L, long long slots, void* ws, size_t ws_bytes,
+                         cudaStream_t st, Schedule* out) {
+  out->order = nullptr;
+  static const bool natural = [] {
+    const char* v = getenv("LTR_SCHEDULE");
+    return v && strcmp(v, "natural") == 0;
+  }();
+  if (ws && ws_bytes >= schedule_bytes(B) && B > slots && !natural &&
+      (reinterpret_cast<uintptr_t>(ws) & 15u) == 0) {
+    unsigned int* q = static_cast<unsigned int*>(ws);
+    order_queries_kernel<<<1, kOrderThreads, 0, st>>>(n, n_bytes, B, L, q, q + 4);
+    LTR_CUDA(cudaGetLastError());
+    out->queue = q;
+    out->order = q + 4;
+    return LTR_OK;
+  }
+  return next_queue(&out->queue);
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 template <int TW>
 int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
                      int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
-                     float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+                     float* loss_sum, void* ws, size_t ws_bytes, cudaStream_t st, const DeviceInfo& di) {
   const int threads = kWarpsPerCta * 32;
   int per_sm = 0;
   LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_warp_kernel<TW>, threads, 0));
   if (per_sm < 1) return LTR_EUNSUPPORTED;
+  // LTR_WARP_CTAS caps the resident CTAs per SM so that more of the batch is handed out
+  // dynamically (measured on (4096, 128): 26 us all-resident vs 34 - 39 us with 3 - 6 CTAs per
+  // SM, so the default keeps every warp slot busy and queues only what does not fit).
+  static const int sched_ctas = env_int("LTR_WARP_CTAS", kWarpSchedCtas);
+  const bool can_order = ws && ws_bytes >= schedule_bytes(B);
+  if (can_order && per_sm > sched_ctas && sched_ctas > 0) per_sm = sched_ctas;
   const long long want = (static_cast<long long>(B) + kWarpsPerCta - 1) / kWarpsPerCta;
   const long long cap = static_cast<long long>(per_sm) * di.sms;
   const int grid = static_cast<int>(want < cap ? want : cap);
   const int vec_ok = (L % 4 == 0) && aligned16(scores) && aligned16(rel) && (!grad_out || aligned16(grad_out));
-  unsigned int* queue = nullptr;
-  int rc = next_queue(&queue);
+  Schedule sc;
+  int rc = make_schedule(n, n_bytes, B, L, static_cast<long long>(grid) * kWarpsPerCta, ws, ws_bytes, st, &sc);
   if (rc != LTR_OK) return rc;
   const PairTables* tabs = nullptr;
   rc = pair_tables(st, &tabs);
   if (rc != LTR_OK) return rc;
   pair_warp_kernel<TW><<<grid, threads, 0, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, vec_ok,
-                                                 dcg_mod, loss_out, grad_out, ranking_out, loss_sum, queue, tabs);
+                                                 dcg_mod, loss_out, grad_out, ranking_out, loss_sum, sc.queue,
+                                                 sc.order, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }
@@ -691,7 +785,7 @@ int launch_pair_warp(const float* scores, const void* rel, int rel_bytes, const 
 template <int TW>
 int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
                     int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
-                    float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+                    float* loss_sum, void*, size_t, cudaStream_t st, const DeviceInfo& di) {
   const int P = next_pow2(L);
   const int threads = kCtaWarps * 32;
   // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes, and room for the
@@ -720,7 +814,7 @@ inline bool force_tiles() {
 template <int TW>
 int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
                      int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
-                     float* loss_sum, cudaStream_t st, const DeviceInfo& di) {
+                     float* loss_sum, void* ws, size_t ws_bytes, cudaStream_t st, const DeviceInfo& di) {
   const int P = next_pow2(L);
   const int threads = kRingWarps * 32;
   // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes
@@ -730,18 +824,22 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
   int grid = 0;
   int rc = persistent_grid(pair_ring_kernel<TW>, threads, smem, B, di, &grid);
   if (rc != LTR_OK) return rc;
+  Schedule sc;
+  rc = make_schedule(n, n_bytes, B, L, grid, ws, ws_bytes, st, &sc);
+  if (rc != LTR_OK) return rc;
   const PairTables* tabs = nullptr;
   rc = pair_tables(st, &tabs);
   if (rc != LTR_OK) return rc;
   pair_ring_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma, dcg_mod,
-                                                    tma, loss_out, grad_out, ranking_out, loss_sum, tabs);
+                                                    tma, loss_out, grad_out, ranking_out, loss_sum, sc.queue,
+                                                    sc.order, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }
 
 int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,
                   int n_bytes, int B, int L, float sigma, float* loss_out, float* grad_out,
-                  int64_t* ranking_out, float* loss_sum, void* stream) {
+                  int64_t* ranking_out, float* loss_sum, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_common(scores, n, n_bytes, B, L);
   if (rc != LTR_OK) return rc;
   if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
@@ -758,12 +856,12 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
 #define LTR_TILED(TWMODE, DCG)                                                                          \
   return L <= kWarpL                                                                                    \
              ? launch_pair_warp<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \
-                                        grad_out, ranking_out, loss_sum, st, di)                        \
+                                        grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di)          \
          : ring                                                                                         \
              ? launch_pair_ring<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \
-                                        grad_out, ranking_out, loss_sum, st, di)                        \
+                                        grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di)          \
              : launch_pair_cta<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,   \
-                                       grad_out, ranking_out, loss_sum, st, di)
+                                       grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di)
     if (pm == PM_LOGISTIC) LTR_TILED(TW_UNIT, 0);
     if (pm == PM_ARP2) LTR_TILED(TW_DIFF, 0);
     if (pm == PM_NDCG2) LTR_TILED(TW_DELTA, 0);
@@ -816,15 +914,35 @@ int ltr_pairwise_additive(int mode, const float* scores, const void* rel, int re
                           float* dscores_out, float* loss_sum, void* stream) {
   if (mode < LTR_ADD_HINGE || mode > LTR_ADD_LOGISTIC) return LTR_EINVAL;
   return dispatch_pair(PM_HINGE + mode, scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out,
-                       dscores_out, nullptr, loss_sum, stream);
+                       dscores_out, nullptr, loss_sum, nullptr, 0, stream);
 }
+
+int ltr_pairwise_additive_ws(int mode, const float* scores, const void* rel, int rel_bytes,
+                             const void* n, int n_bytes, int B, int L, float sigma, float* loss_out,
+                             float* dscores_out, float* loss_sum, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (mode < LTR_ADD_HINGE || mode > LTR_ADD_LOGISTIC) return LTR_EINVAL;
+  return dispatch_pair(PM_HINGE + mode, scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out,
+                       dscores_out, nullptr, loss_sum, workspace, workspace_bytes, stream);
+}
+
+size_t ltr_schedule_workspace_bytes(int B) { return schedule_bytes(B); }
 
 int ltr_lambda(int mode, const float* scores, const void* rel, int rel_bytes, const void* n,
                int n_bytes, int B, int L, float sigma, float* loss_out, float* dscores_out,
                int64_t* ranking_out, float* loss_sum, void* stream) {
   if (mode < LTR_LAM_ARP1 || mode > LTR_LAM_NDCG2) return LTR_EINVAL;
   return dispatch_pair(PM_ARP1 + mode, scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out,
-                       dscores_out, ranking_out, loss_sum, stream);
+                       dscores_out, ranking_out, loss_sum, nullptr, 0, stream);
+}
+
+int ltr_lambda_ws(int mode, const float* scores, const void* rel, int rel_bytes, const void* n,
+                  int n_bytes, int B, int L, float sigma, float* loss_out, float* dscores_out,
+                  int64_t* ranking_out, float* loss_sum, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (mode < LTR_LAM_ARP1 || mode > LTR_LAM_NDCG2) return LTR_EINVAL;
+  return dispatch_pair(PM_ARP1 + mode, scores, rel, rel_bytes, n, n_bytes, B, L, sigma, loss_out,
+                       dscores_out, ranking_out, loss_sum, workspace, workspace_bytes, stream);
 }
 
 int ltr_listnet(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
@@ -962,7 +1080,7 @@ size_t ltr_host_workspace_bytes(int B, int L) {
   const size_t bl = static_cast<size_t>(B) * L;
   // scores f32 | relevance i64 | n i64 | loss f32 | dscores f32
   return align256(bl * 4) + align256(bl * 8) + align256(static_cast<size_t>(B) * 8) +
-         align256(static_cast<size_t>(B) * 4) + align256(bl * 4);
+         align256(static_cast<size_t>(B) * 4) + align256(bl * 4) + align256(schedule_bytes(B));
 }
 
 int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_rel,
@@ -980,7 +1098,9 @@ int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_
   int64_t* d_rel = reinterpret_cast<int64_t*>(p);           p += align256(bl * 8);
   int64_t* d_n = reinterpret_cast<int64_t*>(p);             p += align256(static_cast<size_t>(B) * 8);
   float* d_loss = reinterpret_cast<float*>(p);              p += align256(static_cast<size_t>(B) * 4);
-  float* d_grad = reinterpret_cast<float*>(p);
+  float* d_grad = reinterpret_cast<float*>(p);              p += align256(bl * 4);
+  void* d_sched = p;
+  const size_t sched_bytes = schedule_bytes(B);
   LTR_CUDA(cudaMemcpyAsync(d_scores, h_scores, bl * 4, cudaMemcpyHostToDevice, st));
   LTR_CUDA(cudaMemcpyAsync(d_rel, h_rel, bl * 8, cudaMemcpyHostToDevice, st));
   LTR_CUDA(cudaMemcpyAsync(d_n, h_n, static_cast<size_t>(B) * 8, cudaMemcpyHostToDevice, st));
@@ -988,10 +1108,12 @@ int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_
   int rc;
   switch (family) {
     case LTR_FAMILY_ADDITIVE:
-      rc = ltr_pairwise_additive(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, stream);
+      rc = ltr_pairwise_additive_ws(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, d_sched,
+                                    sched_bytes, stream);
       break;
     case LTR_FAMILY_LAMBDA:
-      rc = ltr_lambda(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, nullptr, stream);
+      rc = ltr_lambda_ws(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, nullptr, d_sched,
+                         sched_bytes, stream);
       break;
     case LTR_FAMILY_LISTNET:
       rc = ltr_listnet(d_scores, d_rel, 8, d_n, 8, B, L, d_loss, gptr, nullptr, stream);

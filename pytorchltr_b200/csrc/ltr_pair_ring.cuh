@@ -394,6 +394,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
                  const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                  int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,
                  int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
+                 unsigned int* __restrict__ queue, const unsigned int* __restrict__ order,
                  const PairTables* __restrict__ tabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const RingSmem m = ring_carve(smem_raw, L, P, tma ? rel_bytes : 0);
@@ -426,12 +427,25 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < B) issue_row(blockIdx.x);
   }
 
-  int iter = 0;
-  for (int b = blockIdx.x; b < B; b += gridDim.x, ++iter) {
+  // ---- query schedule: the first query of every CTA is static, the following ones come from a
+  // device-wide queue.  `order` (optional) lists the queries by decreasing size: the long ones
+  // start first and the tail of the launch is made of short ones -----------------------------------
+  const bool dynamic = gridDim.x < static_cast<unsigned int>(B);
+  int b = static_cast<int>(blockIdx.x) < B ? static_cast<int>(order ? order[blockIdx.x] : blockIdx.x) : -1;
+  if (tma && threadIdx.x == 0 && b >= 0) issue_row(b);
+
+  for (int iter = 0; b >= 0; ++iter) {
     __syncthreads();   // previous query fully consumed (gw / keys, raw_s, red, hist)
+    if (threadIdx.x == 0) {
+      int b_next = -1;
+      if (dynamic) {
+        const unsigned int qn = gridDim.x + atomicAdd(queue, 1u);
+        if (qn < static_cast<unsigned int>(B)) b_next = static_cast<int>(order ? order[qn] : qn);
+      }
+      m.hist[38] = b_next;
+    }
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
 
@@ -450,9 +464,10 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
     if (threadIdx.x < 36) m.hist[threadIdx.x] = 0;
     __syncthreads();
-    if (tma && threadIdx.x == 0 && b + static_cast<int>(gridDim.x) < B) {
+    const int b_next = m.hist[38];
+    if (tma && threadIdx.x == 0 && b_next >= 0) {
       fence_proxy_async();   // the staging buffer was just read through the generic proxy
-      issue_row(b + gridDim.x);
+      issue_row(b_next);
     }
 
     // ---- rank_by_score ----------------------------------------------------------------------------------
@@ -610,6 +625,17 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       __syncthreads();
       float* __restrict__ go = grad_out + base;
       for (int j = threadIdx.x; j < L; j += blockDim.x) go[j] = gdoc[j];
+    }
+    b = b_next;
+  }
+
+  // ---- leave the queue clean for the next launch that uses this slot ----------------------------------
+  if (dynamic && threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(queue + 1, 1u);
+    if (done == gridDim.x - 1) {
+      queue[0] = 0u;
+      queue[1] = 0u;
+      __threadfence();
     }
   }
 }

@@ -21,6 +21,7 @@ namespace ltr {
 constexpr int kWarpL = 128;          // max list size of the warp-per-query kernel
 constexpr int kWarpE = 4;            // elements per lane in the sort (32 * 4 = 128)
 constexpr int kWarpsPerCta = 4;
+constexpr int kWarpSchedCtas = 0;    // cap on resident CTAs per SM under a longest-first schedule (0 = none)
 
 // direction predicates of the bitonic network for element index lane * E + r
 template <int E>
@@ -172,7 +173,8 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
                  const void* __restrict__ n, int n_bytes, int B, int L, float sigma, int vec_ok,
                  int variant, float* __restrict__ loss_out, float* __restrict__ grad_out,
                  int64_t* __restrict__ ranking_out, float* __restrict__ loss_sum,
-                 unsigned int* __restrict__ queue, const PairTables* __restrict__ tabs) {
+                 unsigned int* __restrict__ queue, const unsigned int* __restrict__ order,
+                 const PairTables* __restrict__ tabs) {
   const PairTables& tb = *tabs;
   __shared__ WarpScratch scratch[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
@@ -186,12 +188,15 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
   const float k_lo = static_cast<float>(kd - static_cast<double>(k_hi));
 
   // ---- query schedule: the first query of every warp is static (no start-up burst on the queue
-  // counter), the following ones are pulled from the device-wide queue as warps finish -----------
+  // counter), the following ones are pulled from the device-wide queue as warps finish.  `order`
+  // (optional) lists the queries by decreasing size, so the long ones start first and the tail of
+  // the launch is made of short ones (longest-processing-time-first list scheduling) --------------
   const unsigned int total_warps = gridDim.x * kWarpsPerCta;
   const bool dynamic = total_warps < static_cast<unsigned int>(B);   // else: one query per warp, no queue traffic
-  unsigned int b = blockIdx.x * kWarpsPerCta + warp;
+  unsigned int q = blockIdx.x * kWarpsPerCta + warp;
 
-  while (b < static_cast<unsigned int>(B)) {
+  while (q < static_cast<unsigned int>(B)) {
+    const unsigned int b = order ? order[q] : q;
     unsigned int b_next = 0xffffffffu;
     if (dynamic && lane == 0) b_next = total_warps + atomicAdd(queue, 1u);   // consumed at the end of this iteration
 
@@ -478,7 +483,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
     __syncwarp();
     if (!dynamic) break;
-    b = __shfl_sync(0xffffffffu, b_next, 0);
+    q = __shfl_sync(0xffffffffu, b_next, 0);
   }
 
   // ---- leave the queue clean for the next launch that uses this slot ----------------------------------

@@ -518,3 +518,67 @@ def test_cuda_rank_by_plackettluce_statistics():
     p = expected.astype(np.float64)
     exp2 = np.array([sum(p[i] * p[j] / (1 - p[i]) for i in range(4) if i != j) for j in range(4)])
     assert second == approx(exp2, abs=0.03)
+
+
+@pytest.mark.parametrize("mode", ADDITIVE + LAMBDA)
+@pytest.mark.parametrize("B,L", [(4, 200), (2, 1000)])
+def test_cuda_tile_kernel_vs_oracle(mode, B, L, monkeypatch):
+    """LTR_KERNEL=tiles keeps the 128 x 128 rank-tile kernel (the path of lists longer than 1024)
+    for every L > 128, so it stays covered at sizes the oracle finishes quickly."""
+    monkeypatch.setenv("LTR_KERNEL", "tiles")
+    s, y, n = make_batch(700 + L, B, L)
+    n[0] = 1
+    y[np.arange(L)[None, :] >= n[:, None]] = 0
+    loss, grad = _run_cuda(mode, s, y, n, sigma=1.2)
+    ref_loss, ref_grad = _oracle_loss(mode, s, y, n, 1.2)
+    _assert_parity(loss, grad, ref_loss, ref_grad)
+
+
+@pytest.mark.parametrize("mode", ["ndcg2", "hinge", "arp1"])
+def test_cuda_ring_kernel_scheduled_many_queries(mode):
+    """More queries than resident CTAs: the ring kernel orders the queries longest-first (counting
+    sort in the scheduling workspace) and hands them out through the device-wide queue.  Every
+    query must be visited exactly once, whatever n it has (0, 1, short, long)."""
+    B, L = 6000, 160
+    s, y, n = make_batch(321, B, L)
+    n[::7] = torch.randint(0, 40, n[::7].shape, generator=torch.Generator().manual_seed(5))
+    n[1], n[2] = 0, 1
+    y[np.arange(L)[None, :] >= n[:, None]] = 0
+    idx = np.arange(0, B, 53)
+    ref_loss, ref_grad = _oracle_loss(mode, s[idx], y[idx], n[idx])
+    loss, grad = _run_cuda(mode, s, y, n)
+    assert np.isfinite(loss).all()
+    _assert_parity(loss[idx], grad[idx], ref_loss, ref_grad)
+    loss2, grad2 = _run_cuda(mode, s, y, n)
+    # per query the kernel is deterministic (static split over the warps, no atomics)
+    assert np.array_equal(loss, loss2) and np.array_equal(grad, grad2)
+
+
+@pytest.mark.parametrize("B,L", [(9000, 96), (3000, 300)])
+def test_cabi_schedule_workspace_is_optional_and_does_not_change_results(B, L):
+    """ltr_lambda (batch order) and ltr_lambda_ws (longest-first) return the same bits; a
+    workspace that is too small or NULL falls back to batch order."""
+    from pytorchltr_b200 import _lib
+    lib = _lib.lib()
+    dev = torch.device("cuda", 0)
+    s, y, n = make_batch(11 + L, B, L)
+    st, yt, nt = (torch.as_tensor(a).to(dev) for a in (s, y, n))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    outs = []
+    need = lib.ltr_schedule_workspace_bytes(B)
+    assert need >= 4 * B
+    for ws_bytes in (None, need, 8):
+        loss = torch.empty(B, device=dev)
+        grad = torch.empty(B, L, device=dev)
+        if ws_bytes is None:
+            rc = lib.ltr_lambda(_lib.LAM_NDCG2, st.data_ptr(), yt.data_ptr(), 8, nt.data_ptr(), 8, B, L, 1.0,
+                                loss.data_ptr(), grad.data_ptr(), None, None, stream)
+        else:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            rc = lib.ltr_lambda_ws(_lib.LAM_NDCG2, st.data_ptr(), yt.data_ptr(), 8, nt.data_ptr(), 8, B, L, 1.0,
+                                   loss.data_ptr(), grad.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        outs.append((loss.cpu().numpy(), grad.cpu().numpy()))
+    for l, g in outs[1:]:
+        assert np.array_equal(l, outs[0][0]) and np.array_equal(g, outs[0][1])
