@@ -992,6 +992,41 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
   DeviceInfo di;
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
+  static const bool no_topk = [] {
+    const char* v = getenv("LTR_TOPK");
+    return v && strcmp(v, "0") == 0;
+  }();
+  if (metric != LTR_METRIC_ARP && k > 0 && k <= 32 && L <= 1024 && !force_generic() && !no_topk) {
+    // dcg@k / ndcg@k with a small cut-off: top-k selection, one warp per query, no full sort
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const PairTables* tabs = nullptr;
+    rc = pair_tables(st, &tabs);
+    if (rc != LTR_OK) return rc;
+    const long long want = (static_cast<long long>(B) + kTopkWarps - 1) / kTopkWarps;
+    // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes
+    int tma = (L % 4 == 0) && aligned16(scores) && aligned16(rel);
+    if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
+#define LTR_TOPK_LAUNCH(E)                                                                                  \
+  do {                                                                                                      \
+    int per_sm = 0;                                                                                         \
+    LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_metrics_warp_kernel<E>,            \
+                                                           kTopkWarps * 32, 0));                            \
+    if (per_sm < 1) return LTR_EUNSUPPORTED;                                                                \
+    const long long cap = static_cast<long long>(per_sm) * di.sms;                                          \
+    const int grid = static_cast<int>(want < cap ? want : cap);                                             \
+    topk_metrics_warp_kernel<E><<<grid, kTopkWarps * 32, 0, st>>>(metric, scores, rel, rel_bytes, n, n_bytes, B, \
+                                                                  L, k, exp_gain, tma, out, out_ld, tabs);  \
+  } while (0)
+    if (L <= 32) LTR_TOPK_LAUNCH(1);
+    else if (L <= 64) LTR_TOPK_LAUNCH(2);
+    else if (L <= 128) LTR_TOPK_LAUNCH(4);
+    else if (L <= 256) LTR_TOPK_LAUNCH(8);
+    else if (L <= 512) LTR_TOPK_LAUNCH(16);
+    else LTR_TOPK_LAUNCH(32);
+#undef LTR_TOPK_LAUNCH
+    LTR_CUDA(cudaGetLastError());
+    return LTR_OK;
+  }
   if (L <= 256 && !force_generic()) {
     // short lists: one warp per query, in-register ranking
     cudaStream_t st = static_cast<cudaStream_t>(stream);

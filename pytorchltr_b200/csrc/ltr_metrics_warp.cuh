@@ -238,4 +238,258 @@ rank_by_score_warp_kernel(const float* __restrict__ scores, const void* __restri
   }
 }
 
+
+// ---- dcg@k / ndcg@k for small cut-offs (0 < k <= 32): top-k selection instead of a full sort ----------
+//
+// evaluation/dcg.py:85-98 needs the relevance at the first k ranks only, and the ideal DCG of
+// ndcg (:36) only the k largest grades.  One warp per query, documents j = q * 32 + lane in
+// registers straight from coalesced loads:
+//   top-k by score : every lane finds its best key; the k-th best of those 32 lane minima (one
+//                    32-key bitonic sort) is a threshold T that at least k documents reach; the
+//                    documents with key <= T -- k plus a few -- are compacted by ballots into
+//                    <= 32 candidates and ordered exactly by (key, index) in one more 32-element
+//                    network.  More than 32 candidates (massive ties): one warp argmin per rank.
+//   ideal DCG      : 16-bit grade counters packed in two 64-bit words and summed by shuffles
+//                    (grades 0..7), grade g then owns the ideal ranks [start, start + count), cut at
+//                    k, and contributes gain(g) * (S[end] - S[start]) with S the prefix sums of
+//                    1 / log2(2 + r); other grades: one warp max + count per distinct grade.
+// Ranks >= n hold the padded documents in index order with their relevance NOT masked, as in the
+// reference (dcg.py:85); they enter dcg and ideal dcg alike.
+__device__ __forceinline__ void sort32_u32(uint32_t& k, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const bool keep_min = ((lane & size) == 0) == ((lane & stride) == 0);
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, k, stride);
+      k = keep_min ? min(k, other) : max(k, other);
+    }
+  }
+}
+__device__ __forceinline__ void sort32_u64(uint64_t& k, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const bool keep_min = ((lane & size) == 0) == ((lane & stride) == 0);
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, k, stride);
+      k = (keep_min == (other < k)) ? other : k;
+    }
+  }
+}
+
+constexpr int kTopkWarps = 4;
+
+// Rows are staged by TMA bulk copies (cp.async.bulk + one mbarrier per warp) when they are 16-byte
+// aligned: a warp unpacks its row into registers / int32 grades at once and immediately re-arms
+// the buffer with the row of its NEXT query, which is in flight while the current one is ranked.
+template <int E>
+__global__ void __launch_bounds__(kTopkWarps * 32)
+topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const void* __restrict__ rel,
+                         int rel_bytes, const void* __restrict__ n, int n_bytes, int B, int L, int k,
+                         int exp_gain, int tma, float* __restrict__ out, int out_ld,
+                         const PairTables* __restrict__ tabs) {
+  constexpr bool kCanStage = E <= 16;     // 12 bytes per document and warp of static shared memory
+  __shared__ int s_rel[kTopkWarps][32 * E];
+  __shared__ uint64_t s_cand[kTopkWarps][32];
+  __shared__ __align__(16) unsigned char s_stage[kCanStage ? kTopkWarps : 1][kCanStage ? 32 * E * 12 : 16];
+  __shared__ uint64_t s_bar[kTopkWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* raw_y = s_rel[warp];
+  uint64_t* cand = s_cand[warp];
+  const float* __restrict__ inv_disc = tabs->inv_disc;
+  const double* __restrict__ prefix = tabs->inv_disc_prefix;
+  const int kk = k < L ? k : L;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  const bool staged = kCanStage && tma != 0;
+  unsigned char* stage = s_stage[kCanStage ? warp : 0];
+  uint64_t* bar = &s_bar[warp];
+  const uint32_t row_s_bytes = 4u * L, row_y_bytes = static_cast<uint32_t>(rel_bytes) * L;
+  const int stride = gridDim.x * kTopkWarps;
+  int b = blockIdx.x * kTopkWarps + warp;
+  auto issue_row = [&](int q) {
+    mbar_arrive_expect_tx(bar, row_s_bytes + row_y_bytes);
+    tma_load_1d(stage, scores + static_cast<size_t>(q) * L, row_s_bytes, bar);
+    tma_load_1d(stage + row_s_bytes, static_cast<const unsigned char*>(rel) + static_cast<size_t>(q) * row_y_bytes,
+                row_y_bytes, bar);
+  };
+  if (staged) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      if (b < B) issue_row(b);
+    }
+    __syncwarp();
+  }
+
+  for (int iter = 0; b < B; b += stride, ++iter) {
+    const int nb = load_n(n, n_bytes, b, L);
+    const size_t base = static_cast<size_t>(b) * L;
+    const int kv = kk < nb ? kk : nb;     // ranks held by valid documents
+
+    // ---- the row: document j = q * 32 + lane -----------------------------------------------------------
+    uint32_t key[E];
+    if (staged) {
+      mbar_wait(bar, iter & 1);
+      const float* ss = reinterpret_cast<const float*>(stage);
+      const unsigned char* sy = stage + row_s_bytes;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int j = q * 32 + lane;
+        float s = 0.0f;
+        int y = 0;
+        if (j < L) {
+          s = ss[j];
+          y = load_int_clamped(sy, rel_bytes, j);
+        }
+        key[q] = j < nb ? desc_key_f32(s) : kPadKey;
+        raw_y[j] = y;
+      }
+      __syncwarp();
+      if (lane == 0 && b + stride < B) {
+        fence_proxy_async();   // the buffer was just read through the generic proxy
+        issue_row(b + stride);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int j = q * 32 + lane;
+        float s = 0.0f;
+        int y = 0;
+        if (j < L) {
+          s = scores[base + j];
+          y = rel_bytes == 8 ? clamp_i64_to_i32(reinterpret_cast<const long long*>(rel)[base + j])
+                             : reinterpret_cast<const int*>(rel)[base + j];
+        }
+        key[q] = j < nb ? desc_key_f32(s) : kPadKey;
+        raw_y[j] = y;   // grades wait in shared memory (keeps the registers for loads in flight)
+      }
+      __syncwarp();
+    }
+
+    // ---- top-kv by (key, index) ---------------------------------------------------------------------------
+    int my_doc = lane;                    // rank lane holds document my_doc (ranks >= nb: the padding itself)
+    if (kv > 0) {
+      uint32_t lmin = key[0];
+#pragma unroll
+      for (int q = 1; q < E; ++q) lmin = min(lmin, key[q]);
+      uint32_t sorted_min = lmin;
+      sort32_u32(sorted_min, lane);
+      const uint32_t T = __shfl_sync(0xffffffffu, sorted_min, kv - 1);
+      int total = 0;
+#pragma unroll
+      for (int q = 0; q < E; ++q) total += __popc(__ballot_sync(0xffffffffu, key[q] <= T));
+      if (total <= 32) {
+        int offset = 0;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const unsigned int mask = __ballot_sync(0xffffffffu, key[q] <= T);
+          if (key[q] <= T) cand[offset + __popc(mask & lt_mask)] = pack_key(key[q], q * 32 + lane);
+          offset += __popc(mask);
+        }
+        __syncwarp();
+        uint64_t c = lane < total ? cand[lane] : ~0ull;
+        sort32_u64(c, lane);
+        if (lane < kv) my_doc = static_cast<int>(c & 0xffffffffu);
+      } else {
+        // massive ties at the threshold: one exact warp argmin per rank
+        for (int p = 0; p < kv; ++p) {
+          uint64_t best = ~0ull;
+#pragma unroll
+          for (int q = 0; q < E; ++q) {
+            const uint64_t c = pack_key(key[q], q * 32 + lane);
+            best = c < best ? c : best;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+          }
+          const int j = static_cast<int>(best & 0xffffffffu);
+          if (lane == p) my_doc = j;
+#pragma unroll
+          for (int q = 0; q < E; ++q)
+            if (q * 32 + lane == j) key[q] = kPadKey;   // taken (kPadKey never beats a valid key)
+        }
+      }
+    }
+
+    // ---- dcg@kk: gain / log2(rank + 2), dcg.py:91-93 -----------------------------------------------------
+    float term = 0.0f, pad_term = 0.0f;
+    if (lane < kk) {
+      const int y = raw_y[my_doc];
+      const float g = exp_gain ? gain_of_grade(y) : static_cast<float>(y);
+      term = g * __ldg(inv_disc + lane);
+      if (lane >= nb) pad_term = term;
+    }
+    float v = warp_sum(term);
+
+    if (metric == LTR_METRIC_NDCG) {
+      // ---- ideal dcg@kk: the kv largest grades of the valid documents, then the same padding ----------
+      float iv = warp_sum(pad_term);
+      if (kv > 0) {
+        bool wide = false;
+        unsigned long long h0 = 0ull, h1 = 0ull;   // 16-bit counters: grades 0..3 | 4..7
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const bool valid = q * 32 + lane < nb;
+          const int y = raw_y[q * 32 + lane];
+          wide = wide || (valid && static_cast<unsigned int>(y) > 7u);
+          const unsigned long long one = valid ? (1ull << (16 * (y & 3))) : 0ull;
+          if (y & 4) h1 += one; else h0 += one;
+        }
+        double acc = 0.0;
+        if (!__any_sync(0xffffffffu, wide)) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+            h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+          }
+          int start = 0;
+#pragma unroll
+          for (int g = 7; g >= 1; --g) {
+            const int cnt = static_cast<int>(((g & 4) ? h1 : h0) >> (16 * (g & 3))) & 0xffff;
+            const int end = min(start + cnt, kv);
+            if (end > start) {
+              const float gain = exp_gain ? gain_of_grade(g) : static_cast<float>(g);
+              acc += static_cast<double>(gain) * (prefix[end] - prefix[start]);
+            }
+            start = end;
+          }
+        } else {
+          // arbitrary integer grades: peel off one distinct grade per round, largest first
+          uint32_t yk[E];
+#pragma unroll
+          for (int q = 0; q < E; ++q) yk[q] = q * 32 + lane < nb ? desc_key_i32(raw_y[q * 32 + lane]) : kPadKey;
+          int start = 0;
+          while (start < kv) {
+            uint32_t best = yk[0];
+#pragma unroll
+            for (int q = 1; q < E; ++q) best = min(best, yk[q]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+              const bool hit = yk[q] == best;
+              cnt += __popc(__ballot_sync(0xffffffffu, hit));
+              if (hit) yk[q] = kPadKey;
+            }
+            const int g = static_cast<int>(~best ^ 0x80000000u);
+            const int end = min(start + cnt, kv);
+            const float gain = exp_gain ? gain_of_grade(g) : static_cast<float>(g);
+            acc += static_cast<double>(gain) * (prefix[end] - prefix[start]);
+            start = end;
+          }
+        }
+        iv += static_cast<float>(acc);
+      }
+      if (iv == 0.0f) iv = 1.0f;   // dcg.py:37
+      v = v / iv;
+    }
+    if (lane == 0) out[static_cast<size_t>(b) * out_ld] = v;
+    __syncwarp();   // raw_y / cand are reused by the next query
+  }
+}
+
 }  // namespace ltr

@@ -582,3 +582,34 @@ def test_cabi_schedule_workspace_is_optional_and_does_not_change_results(B, L):
         outs.append((loss.cpu().numpy(), grad.cpu().numpy()))
     for l, g in outs[1:]:
         assert np.array_equal(l, outs[0][0]) and np.array_equal(g, outs[0][1])
+
+
+@pytest.mark.parametrize("B,L", [(12, 5), (9, 37), (33, 128), (17, 200), (9, 500), (8, 1024), (8, 202)])
+def test_cuda_topk_metrics_edge_cases(B, L, monkeypatch):
+    """dcg@k / ndcg@k for k <= 32 take the top-k selection kernel: tied scores (lowest index first,
+    incl. the massive-tie fallback), lists shorter than k, unmasked padded relevance (dcg.py:85),
+    wide and negative grades, and bit-for-bit the same ranking decisions as the full-sort kernel."""
+    from pytorchltr_b200.evaluation import dcg, ndcg
+    rng = np.random.default_rng(L)
+    s, y, n = (np.array(a) for a in make_batch(77 + L, B, L))
+    s[0] = 0.25                                  # every score tied
+    s[1] = np.round(s[1] * 2) / 2                # a handful of distinct scores
+    s[2, : L // 2] = s[2, L // 2: 2 * (L // 2)]  # exact duplicates
+    n[3] = min(3, L)                             # fewer valid documents than k
+    n[4] = 0
+    y[5] = rng.integers(-3, 40, size=L)          # grades outside 0..7
+    y[6] = rng.integers(0, 3, size=L) * 9
+    # padded relevance is deliberately NOT zeroed in rows 7..: the reference does not mask it
+    y[:7][np.arange(L)[None, :] >= n[:7, None]] = 0
+    dev = torch.device("cuda", 0)
+    st, yt, nt = (torch.as_tensor(a).to(dev) for a in (s, y, n))
+    tol = dict(rel=1e-5, abs=1e-6)
+    for exp in (True, False):
+        for k in (1, 2, 5, 10, 32):
+            got_d = dcg(st, yt, nt, k=k, exp=exp).cpu().numpy()
+            got_n = ndcg(st, yt, nt, k=k, exp=exp).cpu().numpy()
+            assert got_d == approx(oracle.dcg(s, y, n, k=k, exp=exp), **tol), (k, exp)
+            assert got_n == approx(oracle.ndcg(s, y, n, k=k, exp=exp), **tol), (k, exp)
+    # int32 inputs take the same path
+    got = ndcg(st, yt.int(), nt.int(), k=10).cpu().numpy()
+    assert got == approx(oracle.ndcg(s, y, n, k=10), **tol)
