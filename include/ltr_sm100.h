@@ -158,6 +158,10 @@ int ltr_scale_rows(const float *g, int g_stride, const float *dscores, float *ou
  * `workspace` is a device buffer of at least ltr_host_workspace_bytes(B, L) bytes.
  */
 size_t ltr_host_workspace_bytes(int B, int L);
+/* Byte offset, inside that workspace, of the DEVICE copy of dscores_out [B*L] left behind by
+ * ltr_loss_host (valid once the stream has reached it): a caller whose upstream gradient is not
+ * all ones runs ltr_scale_rows on it without copying the gradient back to the device. */
+size_t ltr_host_workspace_dscores_offset(int B, int L);
 int ltr_loss_host(int family, int mode, const float *h_scores, const int64_t *h_rel,
                   const int64_t *h_n, int B, int L, float sigma, float *h_loss_out,
                   float *h_dscores_out, void *workspace, size_t workspace_bytes, void *stream);

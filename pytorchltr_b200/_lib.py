@@ -16,7 +16,7 @@ SYMBOLS = (
     "ltr_version", "ltr_strerror", "ltr_last_cuda_error", "ltr_pairwise_additive", "ltr_lambda",
     "ltr_listnet", "ltr_rank_metrics", "ltr_rank_by_score", "ltr_scale_rows",
     "ltr_host_workspace_bytes", "ltr_loss_host", "ltr_schedule_workspace_bytes",
-    "ltr_pairwise_additive_ws", "ltr_lambda_ws",
+    "ltr_pairwise_additive_ws", "ltr_lambda_ws", "ltr_host_workspace_dscores_offset",
 )
 
 ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
@@ -69,6 +69,8 @@ def _declare(lib):
     lib.ltr_scale_rows.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.ltr_host_workspace_bytes.restype = c_size_t
     lib.ltr_host_workspace_bytes.argtypes = [c_int, c_int]
+    lib.ltr_host_workspace_dscores_offset.restype = c_size_t
+    lib.ltr_host_workspace_dscores_offset.argtypes = [c_int, c_int]
     lib.ltr_loss_host.restype = c_int
     lib.ltr_loss_host.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]

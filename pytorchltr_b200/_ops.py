@@ -61,6 +61,49 @@ def normalise(scores: torch.Tensor, relevance: Optional[torch.Tensor], n: torch.
     return s, y, nn, B, L
 
 
+def host_loss(scores: torch.Tensor, relevance: torch.Tensor, n: torch.Tensor, family: int, mode: int,
+              sigma: float, want_grad: bool, dev: torch.device):
+    """CPU caller: ONE call of the host-buffer entry point (ltr_loss_host: H2D of scores /
+    relevance / n -> ordering + fused kernel -> D2H of the loss and of d loss / d scores on the
+    current stream) and one stream synchronisation.  Returns the loss and the gradient as pinned
+    host tensors plus a device view of the gradient (kept for a backward pass whose upstream
+    gradient is not all ones)."""
+    if scores.dim() == 3:
+        scores = scores.reshape(scores.shape[0], scores.shape[1])
+    if scores.dim() != 2:
+        raise ValueError(f"scores must be (B, L) or (B, L, 1), got {tuple(scores.shape)}")
+    B, L = scores.shape
+    if L < 1:
+        raise ValueError("list size must be at least 1")
+    if L > _lib.MAX_LIST_SIZE:
+        raise ValueError(f"list size {L} exceeds LTR_MAX_LIST_SIZE={_lib.MAX_LIST_SIZE}")
+    if relevance.dim() == 3:
+        relevance = relevance.reshape(relevance.shape[0], relevance.shape[1])
+    if tuple(relevance.shape) != (B, L):
+        raise ValueError(f"relevance {tuple(relevance.shape)} does not match scores {(B, L)}")
+    if n.dim() != 1 or n.shape[0] != B:
+        raise ValueError(f"n must have shape ({B},), got {tuple(n.shape)}")
+    s = scores.detach().to(torch.float32).contiguous()
+    y = relevance.detach().to(torch.int64).contiguous()
+    nn = n.detach().to(torch.int64).contiguous()
+    loss_h = torch.empty(B, dtype=torch.float32, device="cpu", pin_memory=True)
+    grad_h = torch.empty((B, L), dtype=torch.float32, device="cpu", pin_memory=True) if want_grad else None
+    grad_d = None
+    if B > 0:
+        lib = _lib.lib()
+        ws_bytes = lib.ltr_host_workspace_bytes(B, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ltr_loss_host(family, mode, s.data_ptr(), y.data_ptr(), nn.data_ptr(), B, L, float(sigma),
+                                   loss_h.data_ptr(), _ptr(grad_h), ws.data_ptr(), ws_bytes, _stream(dev))
+            _lib.check(rc)
+            torch.cuda.current_stream(dev).synchronize()
+        if want_grad:
+            off = lib.ltr_host_workspace_dscores_offset(B, L)
+            grad_d = ws[off:off + 4 * B * L].view(torch.float32).view(B, L)
+    return loss_h, grad_h, grad_d
+
+
 def to_host(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
     """Device -> host copy for callers that passed CPU tensors: staged through pinned memory
     (torch's caching host allocator) so the copy runs at full PCIe rate, then one stream sync."""
@@ -155,16 +198,26 @@ class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scores, relevance, n, family, mode, sigma):
         dev = _device_for(scores)
-        s, y, nn, B, L = normalise(scores, relevance, n, dev)
         want_grad = bool(ctx.needs_input_grad[0])
+        ctx.scores_shape = scores.shape
+        ctx.scores_dtype = scores.dtype
+        ctx.scores_device = scores.device
+        ctx.host_grad = None
+        if not scores.is_cuda and not relevance.is_cuda and not n.is_cuda:
+            # CPU caller: host-buffer entry point, results come back as (pinned) CPU tensors
+            loss_h, grad_h, grad_d = host_loss(scores, relevance, n, family, mode, sigma, want_grad, dev)
+            if want_grad:
+                ctx.host_grad = grad_h
+                ctx.save_for_backward(grad_d if grad_d is not None else grad_h)
+            if loss_h.dtype != scores.dtype and scores.dtype.is_floating_point:
+                loss_h = loss_h.to(scores.dtype)
+            return loss_h
+        s, y, nn, B, L = normalise(scores, relevance, n, dev)
         if B == 0:
             loss = torch.empty(0, dtype=torch.float32, device=dev)
             grad = torch.empty((0, L), dtype=torch.float32, device=dev) if want_grad else None
         else:
             loss, grad, _ = launch_loss(family, mode, s, y, nn, sigma, want_grad)
-        ctx.scores_shape = scores.shape
-        ctx.scores_dtype = scores.dtype
-        ctx.scores_device = scores.device
         if want_grad:
             ctx.save_for_backward(grad)
         out = loss
@@ -178,6 +231,15 @@ class _FusedLoss(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         (saved,) = ctx.saved_tensors
+        if ctx.host_grad is not None:
+            B = ctx.host_grad.shape[0]
+            # `loss.sum().backward()` of a CPU caller: the upstream gradient is a broadcast 1.0 and
+            # the gradient is already on the host (copied back by the forward call)
+            if B == 0 or (not g.is_cuda and (B == 1 or g.stride(0) == 0) and float(g.reshape(-1)[0]) == 1.0):
+                out = ctx.host_grad
+                if out.dtype != ctx.scores_dtype:
+                    out = out.to(ctx.scores_dtype)
+                return out.reshape(ctx.scores_shape), None, None, None, None, None
         out = scale_rows(g, saved)
         if out.dtype != ctx.scores_dtype:
             out = out.to(ctx.scores_dtype)

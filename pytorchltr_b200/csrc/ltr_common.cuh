@@ -90,8 +90,8 @@ __device__ __forceinline__ uint32_t desc_key_f32(float x) {
   x = x + 0.0f;
   uint32_t u = __float_as_uint(x);
   if (x != x) u = 0x7fc00000u;
-  uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return ~asc;
+  // ascending key = u ^ (sign ? 0xffffffff : 0x80000000); descending = its complement
+  return u ^ (~static_cast<uint32_t>(static_cast<int>(u) >> 31) & 0x7fffffffu);
 }
 // Same for an int32 relevance grade (used for the ideal ranking of _max_dcg / ndcg).
 __device__ __forceinline__ uint32_t desc_key_i32(int v) {

@@ -1118,6 +1118,13 @@ size_t ltr_host_workspace_bytes(int B, int L) {
          align256(static_cast<size_t>(B) * 4) + align256(bl * 4) + align256(schedule_bytes(B));
 }
 
+size_t ltr_host_workspace_dscores_offset(int B, int L) {
+  if (B < 0 || L < 1) return 0;
+  const size_t bl = static_cast<size_t>(B) * L;
+  return align256(bl * 4) + align256(bl * 8) + align256(static_cast<size_t>(B) * 8) +
+         align256(static_cast<size_t>(B) * 4);
+}
+
 int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_rel,
                   const int64_t* h_n, int B, int L, float sigma, float* h_loss_out,
                   float* h_dscores_out, void* workspace, size_t workspace_bytes, void* stream) {

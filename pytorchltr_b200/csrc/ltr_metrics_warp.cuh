@@ -300,7 +300,6 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
   const float* __restrict__ inv_disc = tabs->inv_disc;
   const double* __restrict__ prefix = tabs->inv_disc_prefix;
   const int kk = k < L ? k : L;
-  const unsigned int lt_mask = (1u << lane) - 1u;
   const bool staged = kCanStage && tma != 0;
   unsigned char* stage = s_stage[kCanStage ? warp : 0];
   uint64_t* bar = &s_bar[warp];
@@ -333,17 +332,35 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
       mbar_wait(bar, iter & 1);
       const float* ss = reinterpret_cast<const float*>(stage);
       const unsigned char* sy = stage + row_s_bytes;
+      if (rel_bytes == 8) {
+        const int2* sy2 = reinterpret_cast<const int2*>(sy);
 #pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int j = q * 32 + lane;
-        float s = 0.0f;
-        int y = 0;
-        if (j < L) {
-          s = ss[j];
-          y = load_int_clamped(sy, rel_bytes, j);
+        for (int q = 0; q < E; ++q) {
+          const int j = q * 32 + lane;
+          float s = 0.0f;
+          int y = 0;
+          if (j < L) {
+            s = ss[j];
+            const int2 w = sy2[j];   // little endian: x = low word
+            y = w.y == (w.x >> 31) ? w.x : (w.y < 0 ? -2147483647 : 2147483647);
+          }
+          key[q] = j < nb ? desc_key_f32(s) : kPadKey;
+          raw_y[j] = y;
         }
-        key[q] = j < nb ? desc_key_f32(s) : kPadKey;
-        raw_y[j] = y;
+      } else {
+        const int* sy1 = reinterpret_cast<const int*>(sy);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int j = q * 32 + lane;
+          float s = 0.0f;
+          int y = 0;
+          if (j < L) {
+            s = ss[j];
+            y = sy1[j];
+          }
+          key[q] = j < nb ? desc_key_f32(s) : kPadKey;
+          raw_y[j] = y;
+        }
       }
       __syncwarp();
       if (lane == 0 && b + stride < B) {
@@ -376,16 +393,23 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
       uint32_t sorted_min = lmin;
       sort32_u32(sorted_min, lane);
       const uint32_t T = __shfl_sync(0xffffffffu, sorted_min, kv - 1);
-      int total = 0;
+      // candidates (key <= T): per-lane count, warp scan, each lane appends its own (any order:
+      // they are sorted next)
+      int mine = 0;
 #pragma unroll
-      for (int q = 0; q < E; ++q) total += __popc(__ballot_sync(0xffffffffu, key[q] <= T));
+      for (int q = 0; q < E; ++q) mine += key[q] <= T ? 1 : 0;
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
       if (total <= 32) {
-        int offset = 0;
+        int pos = incl - mine;
 #pragma unroll
         for (int q = 0; q < E; ++q) {
-          const unsigned int mask = __ballot_sync(0xffffffffu, key[q] <= T);
-          if (key[q] <= T) cand[offset + __popc(mask & lt_mask)] = pack_key(key[q], q * 32 + lane);
-          offset += __popc(mask);
+          if (key[q] <= T) cand[pos++] = pack_key(key[q], q * 32 + lane);
         }
         __syncwarp();
         uint64_t c = lane < total ? cand[lane] : ~0ull;
@@ -428,27 +452,34 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
       // ---- ideal dcg@kk: the kv largest grades of the valid documents, then the same padding ----------
       float iv = warp_sum(pad_term);
       if (kv > 0) {
+        // grades 0..7: eight 4-bit counters per lane (<= 8 documents at a time), widened to 16-bit
+        // fields (word f: grades f and f + 4) and summed across the warp
         bool wide = false;
-        unsigned long long h0 = 0ull, h1 = 0ull;   // 16-bit counters: grades 0..3 | 4..7
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int q = 0; q < E; ++q) {
-          const bool valid = q * 32 + lane < nb;
-          const int y = raw_y[q * 32 + lane];
-          wide = wide || (valid && static_cast<unsigned int>(y) > 7u);
-          const unsigned long long one = valid ? (1ull << (16 * (y & 3))) : 0ull;
-          if (y & 4) h1 += one; else h0 += one;
+        for (int q0 = 0; q0 < E; q0 += 8) {
+          uint32_t h = 0u;
+#pragma unroll
+          for (int q = q0; q < q0 + 8 && q < E; ++q) {
+            const int y = raw_y[q * 32 + lane];
+            const bool valid = q * 32 + lane < nb;
+            wide = wide || (valid && static_cast<unsigned int>(y) > 7u);
+            h += valid ? (1u << (4 * (y & 7))) : 0u;
+          }
+#pragma unroll
+          for (int f = 0; f < 4; ++f) w[f] += (h >> (4 * f)) & 0x000f000fu;
         }
         double acc = 0.0;
         if (!__any_sync(0xffffffffu, wide)) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            h0 += __shfl_xor_sync(0xffffffffu, h0, o);
-            h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+          for (int f = 0; f < 4; ++f) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w[f] += __shfl_xor_sync(0xffffffffu, w[f], o);
           }
           int start = 0;
 #pragma unroll
           for (int g = 7; g >= 1; --g) {
-            const int cnt = static_cast<int>(((g & 4) ? h1 : h0) >> (16 * (g & 3))) & 0xffff;
+            const int cnt = static_cast<int>((w[g & 3] >> (16 * (g >> 2))) & 0xffffu);
             const int end = min(start + cnt, kv);
             if (end > start) {
               const float gain = exp_gain ? gain_of_grade(g) : static_cast<float>(g);
