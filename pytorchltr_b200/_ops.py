@@ -236,10 +236,14 @@ class _FusedLoss(torch.autograd.Function):
             # `loss.sum().backward()` of a CPU caller: the upstream gradient is a broadcast 1.0 and
             # the gradient is already on the host (copied back by the forward call)
             if B == 0 or (not g.is_cuda and (B == 1 or g.stride(0) == 0) and float(g.reshape(-1)[0]) == 1.0):
-                out = ctx.host_grad
+                # hand over the only reference, so that autograd can adopt the tensor as `.grad`
+                # instead of cloning it
+                out, ctx.host_grad = ctx.host_grad, None
                 if out.dtype != ctx.scores_dtype:
                     out = out.to(ctx.scores_dtype)
-                return out.reshape(ctx.scores_shape), None, None, None, None, None
+                if out.shape != ctx.scores_shape:
+                    out = out.reshape(ctx.scores_shape)
+                return out, None, None, None, None, None
         out = scale_rows(g, saved)
         if out.dtype != ctx.scores_dtype:
             out = out.to(ctx.scores_dtype)

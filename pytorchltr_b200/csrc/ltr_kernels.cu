@@ -678,9 +678,21 @@ order_queries_kernel(const void* __restrict__ n, int n_bytes, int B, int L, unsi
   __shared__ unsigned int hist[LTR_MAX_LIST_SIZE + 1];
   __shared__ unsigned int wsum[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the first kOrderKeep values of every thread stay in registers for the scatter pass
+  constexpr int kOrderKeep = 8;
+  int keep[kOrderKeep];
+#pragma unroll
+  for (int r = 0; r < kOrderKeep; ++r) {
+    const int i = tid + r * kOrderThreads;
+    keep[r] = i < B ? load_n(n, n_bytes, i, L) : 0;
+  }
   for (int i = tid; i <= L; i += kOrderThreads) hist[i] = 0u;
   __syncthreads();
-  for (int i = tid; i < B; i += kOrderThreads) atomicAdd(&hist[load_n(n, n_bytes, i, L)], 1u);
+#pragma unroll
+  for (int r = 0; r < kOrderKeep; ++r)
+    if (tid + r * kOrderThreads < B) atomicAdd(&hist[keep[r]], 1u);
+  for (int i = tid + kOrderKeep * kOrderThreads; i < B; i += kOrderThreads)
+    atomicAdd(&hist[load_n(n, n_bytes, i, L)], 1u);
   __syncthreads();
   // exclusive scan in order of DECREASING n: entry e stands for n = L - e
   const int K = (L + kOrderThreads) / kOrderThreads;   // ceil((L + 1) / threads)
@@ -711,7 +723,12 @@ order_queries_kernel(const void* __restrict__ n, int n_bytes, int B, int L, unsi
     run += cnt;
   }
   __syncthreads();
-  for (int i = tid; i < B; i += kOrderThreads) {
+#pragma unroll
+  for (int r = 0; r < kOrderKeep; ++r) {
+    const int i = tid + r * kOrderThreads;
+    if (i < B) order[atomicAdd(&hist[keep[r]], 1u)] = static_cast<unsigned int>(i);
+  }
+  for (int i = tid + kOrderKeep * kOrderThreads; i < B; i += kOrderThreads) {
     const unsigned int pos = atomicAdd(&hist[load_n(n, n_bytes, i, L)], 1u);
     order[pos] = static_cast<unsigned int>(i);
   }
@@ -734,7 +751,11 @@ inline int make_schedule(const void* n, int n_bytes, int B, int L, long long slo
     const char* v = getenv("LTR_SCHEDULE");
     return v && strcmp(v, "natural") == 0;
   }();
-  if (ws && ws_bytes >= schedule_bytes(B) && B > slots && !natural &&
+  static const bool always = [] {
+    const char* v = getenv("LTR_SCHEDULE");
+    return v && strcmp(v, "always") == 0;
+  }();
+  if (ws && ws_bytes >= schedule_bytes(B) && (B > slots || always) && !natural &&
       (reinterpret_cast<uintptr_t>(ws) & 15u) == 0) {
     unsigned int* q = static_cast<unsigned int*>(ws);
     order_queries_kernel<<<1, kOrderThreads, 0, st>>>(n, n_bytes, B, L, q, q + 4);

@@ -15,8 +15,15 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 20 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pair_warp -s 5 -c 1 -o gpurun_out/${tag}_prof_c2 \
     python bench.py --steps 5 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:pair_cta -s 3 -c 1 -o gpurun_out/${tag}_prof_ns \
+ncu --set full --clock-control none --import-source on -k regex:pair_ring -s 3 -c 1 -o gpurun_out/${tag}_prof_ns \
     python bench.py --config ns --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_ns.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:topk_metrics -s 3 -c 1 -o gpurun_out/${tag}_prof_c4m \
+    python bench.py --config c4m --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_c4m.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:listnet -s 3 -c 1 -o gpurun_out/${tag}_prof_c4 \
+    python bench.py --config c4 --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_c4.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_launches_ns.csv \
+    python bench.py --config ns --steps 10 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_launch_ns.log 2>&1
+python tools/e2e_probe.py > gpurun_out/${tag}_e2e_probe.txt 2>&1
 for f in gpurun_out/${tag}_bench_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
