@@ -48,6 +48,10 @@ CONFIGS = {
                workload="LambdaNDCGLoss2 synthetic (B=65536, L=512) query-sharded"),
     "ns": dict(loss="LambdaNDCGLoss2", B=4096, L=1024,
                workload="LambdaNDCGLoss2 synthetic (B=4096, L=1024) fp32 (north-star point)"),
+    # config 4 with its 136 features: linear scorer + ListNet fused into one pass over the features
+    # (SURVEY.md 8(f) N1).  Single GPU per rank (weak scaling); 891 MB of features per batch.
+    "c4f": dict(fused="linear_listnet", loss="ListNetLoss", B=8192, L=200, F=136, skew=True,
+                workload="Linear(136,1) scorer + ListNet fused, MSLR-WEB30K-shaped (B=8192, L=200, F=136) fp32"),
     # forward-only ranking metrics (second half of config 4): 12 L + 12 algorithmic bytes / query
     "c4m": dict(metric="ndcg", k=10, B=8192, L=200, skew=True,
                 workload="ndcg@10 synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
@@ -128,9 +132,20 @@ def run_reference(args, cfg, rank, world):
     # bounded sample: a slice of the workload's batch sized for ~1 s per step
     probe_B = 64
     s, y, n = make_batch_numpy(1234, probe_B, L, cfg.get("skew", False))
+    fused_F = cfg.get("F") if cfg.get("fused") else None
+    rng = np.random.default_rng(7)
+    fused_w = rng.standard_normal(fused_F or 1).astype(np.float32) * 0.1
 
     def step(s, y, n):
+        if fused_F:
+            # scorer + ListNet + weight gradient (numpy float64 port; features drawn once per size)
+            key = len(n)
+            if key not in step.feat:
+                step.feat[key] = rng.standard_normal((key, L, fused_F), dtype=np.float32)
+            return oracle.linear_listnet(step.feat[key], fused_w, None, y, n)
         return oracle_step(oracle, family, mode, cfg, s, y, n)
+
+    step.feat = {}
 
     step(s, y, n)
     t0 = time.perf_counter()
@@ -146,8 +161,9 @@ def run_reference(args, cfg, rank, world):
         step(s, y, n)
     dt = time.perf_counter() - t0
     qps = sample_B * steps / dt
-    sample = (f"{sample_B} of the {cfg['B']} queries of one batch per step, {steps} steps; "
-              f"oracle/ltr_oracle.c (C port of the reference algorithm, OpenMP over queries)")
+    sample = (f"{sample_B} of the {cfg['B']} queries of one batch per step, {steps} steps; " +
+              ("oracle.linear_listnet (numpy float64 port of Linear + ListNet + weight gradient, BLAS threads)"
+               if fused_F else "oracle/ltr_oracle.c (C port of the reference algorithm, OpenMP over queries)"))
     line = {
         "impl": "reference", "metric": metric_name(cfg), "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
@@ -161,6 +177,224 @@ def run_reference(args, cfg, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- fused scorer + loss
+def run_fused(args, cfg, rank, local_rank, world):
+    """Config c4f: `loss = LinearListNet(F)(xs, ys, n); loss.mean().backward()` -- scores, ListNet,
+    d loss / d scores and the weight / bias gradients in one pass over the (B, L, F) features."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pytorchltr_b200 import _lib
+    from pytorchltr_b200.fused import LinearListNet
+    from pytorchltr_b200.loss import ListNetLoss
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, L, F = cfg["B"], cfg["L"], cfg["F"]
+    _, y_np, n_np = make_batch_numpy(1234 + 1000 * rank, B, L, True)
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    xs = torch.randn(B, L, F, device=dev, generator=gen)            # 891 MB: larger than L2 by itself
+    ys, ns = torch.from_numpy(y_np).to(dev), torch.from_numpy(n_np).to(dev)
+    torch.manual_seed(5)
+    model = LinearListNet(F).to(dev)
+    plain = torch.nn.Linear(F, 1).to(dev)
+    plain.load_state_dict(model.linear.state_dict())
+    plain_loss = ListNetLoss()
+    red = torch.zeros(2, device=dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        out = model(xs, ys, ns)
+        out.mean().backward()
+        return out
+
+    def unfused_step():
+        plain.zero_grad(set_to_none=True)
+        out = plain_loss(plain(xs), ys, ns)
+        out.mean().backward()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # CUDA graph of the whole step (forward + backward): the eager step is launch-bound
+    launch = "eager"
+    run = step
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run = graph.replay
+            launch = "cuda_graph"
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); falling back to eager\n")
+            torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(run, args.steps, max(args.warmup, 3))
+    sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+    unfused_ms = timed(unfused_step, min(args.steps, 20), 3) / min(args.steps, 20)
+
+    # kernel only: ltr_linear_listnet (fused kernel + the partial-gradient reduction)
+    lib = _lib.lib()
+    w = model.linear.weight.detach().reshape(-1).contiguous()
+    bias = model.linear.bias.detach().contiguous()
+    loss_buf, dsc = torch.empty(B, device=dev), torch.empty(B, L, device=dev)
+    qg = torch.empty(B, F + 1, device=dev)
+    dw, db = torch.empty(F, device=dev), torch.empty(1, device=dev)
+    ws = torch.empty(lib.ltr_linear_listnet_workspace_bytes(F), dtype=torch.uint8, device=dev)
+    gmean = torch.full((B,), 1.0 / B, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def kernel_only(nq=B):
+        _lib.check(lib.ltr_linear_listnet(xs.data_ptr(), w.data_ptr(), bias.data_ptr(), ys.data_ptr(), 8,
+                                          ns.data_ptr(), 8, nq, L, F, None, loss_buf.data_ptr(), dsc.data_ptr(),
+                                          qg.data_ptr(), None, st))
+
+    def backward_only(nq=B, g=None, stride=1):
+        g = gmean if g is None else g
+        _lib.check(lib.ltr_linear_listnet_backward(qg.data_ptr(), g.data_ptr(), stride, nq, F, dw.data_ptr(),
+                                                   db.data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    k_reps = 20
+    kernel_ms = timed(kernel_only, k_reps, 3) / k_reps
+    backward_ms = timed(backward_only, k_reps, 3) / k_reps
+    alg_bytes = B * (4 * L * F + 12 * L + 12 + 4 * (F + 1))   # + the per-query gradient row
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6548.2, "fallback: B200_PROFILING.md measured copy bandwidth"
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = (json.load(open(tpath)).get("c4f") or {}).get("dram_bytes_per_launch")
+
+    # parity spot check against the float64 oracle (not timed)
+    parity = None
+    cpu_baseline = None
+    e2e = None
+    if rank == 0:
+        import oracle
+        idx = np.arange(0, B, B // 16)
+        out = step()
+        torch.cuda.synchronize()
+        xn = xs[idx].cpu().numpy()
+        _, rl, _, _, _, _ = oracle.linear_listnet(xn, w.cpu().numpy(), bias.cpu().numpy(), y_np[idx], n_np[idx])
+        got = out.detach().cpu().double().numpy()[idx]
+        err = float(np.abs(got - rl).max() / max(1e-30, np.abs(rl).max()))
+        _, _, _, dw_ref, _, gscale = oracle.linear_listnet(xs[:256].cpu().numpy(), w.cpu().numpy(),
+                                                           bias.cpu().numpy(), y_np[:256], n_np[:256])
+        # weight gradient of the first 256 queries through the C ABI (upstream gradient of ones)
+        kernel_only(256)
+        backward_only(256, torch.ones(1, device=dev), 0)
+        torch.cuda.synchronize()
+        gerr = float((np.abs(dw.cpu().double().numpy() - dw_ref) / gscale).max())
+        parity = {"max_loss_err_rel": err, "max_dweight_err_rel_to_abs_sum": gerr, "queries_checked": 16 + 256,
+                  "ok": bool(err <= 1e-5 and gerr <= 1e-5)}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample_B = 512
+            xn = xs[:sample_B].cpu().numpy()
+            wn, bn = w.cpu().numpy(), bias.cpu().numpy()
+            oracle.linear_listnet(xn[:32], wn, bn, y_np[:32], n_np[:32])
+            t0 = time.perf_counter()
+            oracle.linear_listnet(xn, wn, bn, y_np[:sample_B], n_np[:sample_B])
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": sample_B / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                            "sample": f"{sample_B} queries of the same workload in one call ({dt:.2f} s wall), "
+                                      "oracle.linear_listnet (numpy float64, BLAS threads)"}
+    if not args.no_e2e:
+        # end to end: features, relevance and n come from pinned HOST memory every step
+        hB = B // 8
+        hx = torch.empty(hB, L, F, pin_memory=True).normal_()
+        hy, hn = torch.from_numpy(y_np[:hB]).pin_memory(), torch.from_numpy(n_np[:hB]).pin_memory()
+
+        def e2e_step():
+            model.zero_grad(set_to_none=True)
+            out = model(hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True), hn.to(dev, non_blocking=True))
+            out.mean().backward()
+            return out.cpu(), model.linear.weight.grad.cpu()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e_steps = 5
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": hB * world * e_steps / dt, "unit": "queries/s",
+               "h2d_bytes_per_step": hB * (4 * L * F + 8 * L + 8), "d2h_bytes_per_step": hB * 4 + 4 * F,
+               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "path": f"LinearListNet on {hB} queries per step from pinned host memory: H2D of features / "
+                       "relevance / n, fused kernel, D2H of the loss and the weight gradient"}
+    if rank == 0:
+        line = {
+            "metric": "loss fwd+bwd queries/sec", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "loss": "LinearListNet", "B_per_gpu": B, "L": L, "F": F,
+                       "global_batch": B * world, "parallelism": f"query-sharded dp{world}", "launch": launch,
+                       "l2_policy": "inputs larger than L2: one 891 MB feature batch per step",
+                       "n_distribution": "n ~ U[L/2, L]",
+                       "unfused_ms_per_step": unfused_ms,
+                       "unfused_path": "ListNetLoss()(torch.nn.Linear(F, 1)(xs), ys, n).mean().backward(): "
+                                       "two passes over the features (cuBLAS) + ltr_listnet"},
+            "roofline": {"bound": "hbm", "kernel": "linear_listnet_kernel (ltr_linear_listnet)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel_ms": kernel_ms, "backward_ms": backward_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+            "issue_roofline": None, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "clocks": sampler.summary("timed region"),
+            "gpu_launches": 3 * args.steps,
+            "gpu_launches_note": "per step: fused kernel (forward) + weighted column sum and its reduction "
+                                 "(backward) of libltr_sm100.so (plus torch's mean kernels)",
+            "parity_spot_check": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- clocks
@@ -608,6 +842,9 @@ def main():
     if world != args.gpus and rank == 0:
         sys.stderr.write(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun "
                          f"for N > 1; running {world} rank(s)\n")
+    if cfg.get("fused"):
+        run_fused(args, cfg, rank, local_rank, world)
+        return
     run_ours(args, cfg, rank, local_rank, world)
 
 

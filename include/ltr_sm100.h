@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LTR_VERSION 101            /* major*100 + minor */
+#define LTR_VERSION 103            /* major*100 + minor */
 #define LTR_MAX_LIST_SIZE 4096
 
 /* error codes */
@@ -149,6 +149,34 @@ int ltr_rank_by_score(const float *scores, const void *n, int n_bytes, int B, in
  */
 int ltr_scale_rows(const float *g, int g_stride, const float *dscores, float *out, int B, int L,
                    void *stream);
+
+/*
+ * Fused linear scorer + ListNet (the caller side of the loss path,
+ * examples/01-basic-usage.py:44,72: `loss_fn(torch.nn.Linear(F, 1)(features), relevance, n)`
+ * followed by `.backward()`): reads the feature tensor ONCE and returns, per launch,
+ *   scores_out  [B*L]      w . x + b                   (NULL to skip; padded rows included)
+ *   loss_out    [B]        ListNet loss per query       (same arithmetic as ltr_listnet)
+ *   dscores_out [B*L]      d loss_b / d scores[b, :]    (NULL to skip)
+ *   qgrad_out   [B*(F+1)]  per-query parameter gradient: qgrad[b, f] = sum_l dscores[b, l] *
+ *                          features[b, l, f] for f < F, qgrad[b, F] = sum_l dscores[b, l] (bias).
+ * features float32 [B*L*F] row-major, weight float32 [F], bias float32 [1] or NULL.
+ * LTR_EUNSUPPORTED unless F % 4 == 0, F <= 1024, (rel_bytes * L) % 16 == 0, 16-byte aligned
+ * features / rel, and 4 L F + rel_bytes L bytes fit in shared memory (callers then fall back to
+ * their scorer + ltr_listnet).
+ *
+ * ltr_linear_listnet_backward: the backward pass for an upstream gradient g [B] (g_stride 1) or a
+ * broadcast one (g_stride 0): dweight_out[f] = sum_b g[b] qgrad[b, f], dbias_out[0] (NULL to skip)
+ * = sum_b g[b] qgrad[b, F].  No second pass over the features.  `workspace`: device memory,
+ * >= ltr_linear_listnet_workspace_bytes(F) bytes (partial sums, reduced in a fixed order).
+ */
+size_t ltr_linear_listnet_workspace_bytes(int F);
+int ltr_linear_listnet(const float *features, const float *weight, const float *bias,
+                       const void *rel, int rel_bytes, const void *n, int n_bytes, int B, int L,
+                       int F, float *scores_out, float *loss_out, float *dscores_out,
+                       float *qgrad_out, float *loss_sum, void *stream);
+int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride, int B, int F,
+                                float *dweight_out, float *dbias_out, void *workspace,
+                                size_t workspace_bytes, void *stream);
 
 /*
  * Host-buffer form of the three loss families (the call the reference's CPU path is

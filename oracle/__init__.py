@@ -161,3 +161,37 @@ def arp(scores, relevance, n):
     rc = lib().ltr_oracle_arp(_p(s), _p(y), _p(nn), ctypes.c_int(B), ctypes.c_int(L), _p(out))
     assert rc == 0
     return out
+
+
+def linear_listnet(features, weight, bias, relevance, n):
+    """Linear scorer + ListNet + gradients in float64 (numpy); test infrastructure like the rest
+    of this package.  Scorer: ``torch.nn.Linear(F, 1)`` as used by the reference's training loop
+    (examples/01-basic-usage.py:44,72); loss: the ListNet statement of SURVEY.md 8(a) A19
+    (parity unpinned, no reference file).  Gradients are those of ``loss.sum()``.
+    -> (scores (B, L), loss (B,), dscores (B, L), dweight (F,), dbias, gscale (F,)) where
+    ``gscale[f] = sum |dscores * features[..., f]|`` is the magnitude the float32 accumulation
+    error of dweight scales with."""
+    X = np.asarray(features, dtype=np.float64)
+    w = np.asarray(weight, dtype=np.float64).reshape(-1)
+    b0 = 0.0 if bias is None else float(np.asarray(bias, dtype=np.float64).reshape(-1)[0])
+    y = np.asarray(relevance, dtype=np.float64)
+    nn = np.asarray(n, dtype=np.int64)
+    B, L, F = X.shape
+    s = X @ w + b0
+    valid = np.arange(L)[None, :] < nn[:, None]
+    loss = np.zeros(B)
+    d = np.zeros((B, L))
+    for b in range(B):
+        if nn[b] <= 0:
+            continue
+        v = valid[b]
+        sb, yb = s[b, v], y[b, v]
+        q = sb - sb.max()
+        logz = np.log(np.exp(q).sum())
+        p = np.exp(yb - yb.max())
+        p /= p.sum()
+        loss[b] = -(p * (q - logz)).sum()
+        d[b, v] = np.exp(q - logz) - p
+    dweight = np.einsum("bl,blf->f", d, X)
+    gscale = np.einsum("bl,blf->f", np.abs(d), np.abs(X))
+    return s, loss, d, dweight, d.sum(), gscale

@@ -17,6 +17,7 @@
 #include <atomic>
 
 #include "ltr_common.cuh"
+#include "ltr_linear_listnet.cuh"
 #include "ltr_metrics_warp.cuh"
 #include "ltr_pair_cta.cuh"
 #include "ltr_pair_ring.cuh"
@@ -1130,6 +1131,66 @@ int ltr_scale_rows(const float* g, int g_stride, const float* dscores, float* ou
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t ltr_linear_listnet_workspace_bytes(int F) {
+  return F < 1 ? 0 : static_cast<size_t>(kFusedBwdCtas) * (static_cast<size_t>(F) + 1) * sizeof(float);
+}
+
+int ltr_linear_listnet(const float* features, const float* weight, const float* bias, const void* rel,
+                       int rel_bytes, const void* n, int n_bytes, int B, int L, int F, float* scores_out,
+                       float* loss_out, float* dscores_out, float* qgrad_out, float* loss_sum, void* stream) {
+  int rc = check_common(features, n, n_bytes, B, L);
+  if (rc != LTR_OK) return rc;
+  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (F < 1) return LTR_EINVAL;
+  if (B > 0 && (!weight || !rel || !loss_out || !qgrad_out)) return LTR_EINVAL;
+  // the fused kernel keeps a whole L x F block in shared memory and moves it by TMA bulk copies
+  if (F % 4 != 0 || F > kFusedMaxF || (static_cast<size_t>(rel_bytes) * L) % 16 != 0 || !aligned16(features) ||
+      !aligned16(rel))
+    return LTR_EUNSUPPORTED;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  if (B == 0) return LTR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t max_smem = 227u * 1024u;
+  int nbuf = 2;
+  if (fused_smem_bytes(L, F, rel_bytes, 2) > max_smem) nbuf = 1;
+  const size_t smem = fused_smem_bytes(L, F, rel_bytes, nbuf);
+  if (smem > max_smem) return LTR_EUNSUPPORTED;
+  const int grid = di.sms < B ? di.sms : B;
+  if (nbuf == 2) {
+    LTR_CUDA(cudaFuncSetAttribute(linear_listnet_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    linear_listnet_kernel<2><<<grid, kFusedThreads, smem, st>>>(features, weight, bias, rel, rel_bytes, n, n_bytes, B,
+                                                                L, F, scores_out, loss_out, dscores_out, qgrad_out,
+                                                                loss_sum);
+  } else {
+    LTR_CUDA(cudaFuncSetAttribute(linear_listnet_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    linear_listnet_kernel<1><<<grid, kFusedThreads, smem, st>>>(features, weight, bias, rel, rel_bytes, n, n_bytes, B,
+                                                                L, F, scores_out, loss_out, dscores_out, qgrad_out,
+                                                                loss_sum);
+  }
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_linear_listnet_backward(const float* qgrad, const float* g, int g_stride, int B, int F,
+                                float* dweight_out, float* dbias_out, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (B < 0 || F < 1 || (g_stride != 0 && g_stride != 1)) return LTR_EINVAL;
+  if (!dweight_out || !workspace || (B > 0 && (!qgrad || !g))) return LTR_EINVAL;
+  if (workspace_bytes < ltr_linear_listnet_workspace_bytes(F)) return LTR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partials = static_cast<float*>(workspace);
+  const int rows = B < kFusedBwdCtas ? (B > 0 ? B : 1) : kFusedBwdCtas;
+  weighted_colsum_kernel<<<rows, 256, 0, st>>>(qgrad, g, g_stride, B, F + 1, partials);
+  LTR_CUDA(cudaGetLastError());
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partials, rows, F + 1, dweight_out, dbias_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
 
 size_t ltr_host_workspace_bytes(int B, int L) {
   if (B < 0 || L < 1) return 0;

@@ -613,3 +613,72 @@ def test_cuda_topk_metrics_edge_cases(B, L, monkeypatch):
     # int32 inputs take the same path
     got = ndcg(st, yt.int(), nt.int(), k=10).cpu().numpy()
     assert got == approx(oracle.ndcg(s, y, n, k=10), **tol)
+
+
+# ------------------------------------------------------------------ fused linear scorer + ListNet (N1)
+def _fused_batch(seed, B, L, F):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(B, L, F, generator=g, dtype=torch.float32)
+    w = torch.randn(F, generator=g, dtype=torch.float32) * 0.3
+    b = torch.randn(1, generator=g, dtype=torch.float32)
+    n = torch.randint(L // 2, L + 1, (B,), generator=g, dtype=torch.int64)
+    y = torch.randint(0, 5, (B, L), generator=g, dtype=torch.int64)
+    return X, w, b, y, n
+
+
+@pytest.mark.parametrize("B,L,F", [(5, 8, 4), (37, 200, 136), (300, 40, 64), (3, 100, 256), (4, 50, 12),
+                                   (6, 30, 10), (2, 300, 136)])
+def test_cuda_fused_linear_listnet_vs_oracle(B, L, F):
+    """ltr_linear_listnet (one pass over the features) against the float64 oracle: loss and dscores
+    within 1e-5 (relative to the row maximum), dweight within 1e-5 of sum |dscores * x| (the scale
+    its float32 accumulation error grows with).  (6, 30, 10) and (2, 300, 136) do not fit the fused
+    kernel (F % 4 != 0; block larger than shared memory) and take the scorer + ltr_listnet path."""
+    from pytorchltr_b200.fused import linear_listnet
+    X, w, b, y, n = _fused_batch(B * 1000 + L + F, B, L, F)
+    n[0] = 0
+    if B > 1:
+        n[1] = 1
+    dev = torch.device("cuda", 0)
+    wd = w.to(dev).requires_grad_(True)
+    bd = b.to(dev).requires_grad_(True)
+    loss = linear_listnet(X.to(dev), wd, bd, y.to(dev), n.to(dev))
+    loss.sum().backward()
+    s_ref, l_ref, d_ref, dw_ref, db_ref, gscale = oracle.linear_listnet(X.numpy(), w.numpy(), b.numpy(),
+                                                                        y.numpy(), n.numpy())
+    got = loss.detach().cpu().double().numpy()
+    assert np.all(np.abs(got - l_ref) <= 1e-5 * np.abs(l_ref) + 2e-6), np.abs(got - l_ref).max()
+    gw = wd.grad.cpu().double().numpy()
+    assert np.all(np.abs(gw - dw_ref) <= 1e-5 * gscale + 1e-6), (np.abs(gw - dw_ref) / (gscale + 1e-30)).max()
+    assert abs(float(bd.grad.cpu()) - db_ref) <= 1e-5 * np.abs(d_ref).sum() + 1e-6
+    # .mean() scales the same gradients; a per-query upstream gradient takes the second pass
+    wd.grad = None
+    bd.grad = None
+    wts = torch.rand(B, generator=torch.Generator().manual_seed(3)) + 0.5
+    (linear_listnet(X.to(dev), wd, bd, y.to(dev), n.to(dev)) * wts.to(dev)).sum().backward()
+    dw_w = np.einsum("bl,blf->f", d_ref * wts.double().numpy()[:, None], X.double().numpy())
+    gw = wd.grad.cpu().double().numpy()
+    assert np.all(np.abs(gw - dw_w) <= 2e-5 * gscale * 1.5 + 1e-6)
+
+
+def test_cuda_fused_linear_listnet_module_matches_unfused_modules():
+    """LinearListNet(F) == ListNetLoss()(Linear(F, 1)(xs), ys, n) with the same parameters: loss,
+    weight and bias gradients (float32 on both sides, so the tolerance is the accumulation order)."""
+    from pytorchltr_b200.fused import LinearListNet
+    from pytorchltr_b200.loss import ListNetLoss
+    B, L, F = 64, 200, 136
+    X, w, b, y, n = _fused_batch(7, B, L, F)
+    dev = torch.device("cuda", 0)
+    fused = LinearListNet(F).to(dev)
+    with torch.no_grad():
+        fused.linear.weight.copy_(w.reshape(1, F))
+        fused.linear.bias.copy_(b)
+    plain = torch.nn.Linear(F, 1).to(dev)
+    plain.load_state_dict(fused.linear.state_dict())
+    Xd, yd, nd = X.to(dev), y.to(dev), n.to(dev)
+    lf = fused(Xd, yd, nd)
+    lf.mean().backward()
+    lp = ListNetLoss()(plain(Xd), yd, nd)
+    lp.mean().backward()
+    assert torch.allclose(lf, lp, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(fused.linear.weight.grad, plain.weight.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(fused.linear.bias.grad, plain.bias.grad, rtol=1e-4, atol=1e-6)
