@@ -9,7 +9,7 @@
 //   one persistent CTA per SM; the L x F feature block of a query (109 KB at (200, 136)) and its
 //   relevance row are staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier), double
 //   buffered so that the next query's block streams in while the current one is processed;
-//     scores   s_l = w . x_l + b        one thread per row, 128-bit loads, rotated start (conflict free)
+//     scores   s_l = w . x_l + b        two threads per row, 128-bit loads (conflict free at F = 136)
 //     ListNet  loss, d_l = softmax(s)_l - softmax(rel)_l over the valid documents (ltr_listnet)
 //     weight gradient  += sum_l d_l x_l  out of the SAME shared-memory block: 4 features per
 //                      thread (128-bit loads), the rows dealt to 512 / (F / 4) thread slices,
@@ -29,7 +29,7 @@ namespace ltr {
 constexpr int kFusedThreads = 512;
 constexpr int kFusedWarps = kFusedThreads / 32;
 constexpr int kFusedMaxF = 1024;         // F / 4 feature groups must not exceed the CTA
-constexpr int kFusedBwdCtas = 64;        // rows of the backward pass's partial-sum workspace
+constexpr int kFusedBwdCtas = 296;       // rows of the backward pass's partial-sum workspace
 
 __host__ __device__ inline size_t fused_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
 __host__ __device__ inline size_t fused_stage_bytes(int L, int F, int rel_bytes) {
@@ -45,36 +45,46 @@ __host__ __device__ inline size_t fused_front_bytes(int L, int F, int rel_bytes,
 }
 __host__ __device__ inline size_t fused_smem_bytes(int L, int F, int rel_bytes, int nbuf) {
   return fused_front_bytes(L, F, rel_bytes, nbuf) + fused_part_bytes(F) + fused_align16(4u * F) +
-         2u * fused_align16(4u * L) + 4u * 64 + 16u;
+         2u * fused_align16(4u * L) + 4u * 128 + 16u;
 }
 
-// three sums at once over the CTA; `red` holds 64 floats
-__device__ __forceinline__ void cta_sum3(float& a, float& b, float& c, float* red) {
-  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) { red[warp] = a; red[16 + warp] = b; red[32 + warp] = c; }
-  __syncthreads();
-  if (warp == 0) {
-    float x = lane < kFusedWarps ? red[lane] : 0.0f;
-    float y = lane < kFusedWarps ? red[16 + lane] : 0.0f;
-    float z = lane < kFusedWarps ? red[32 + lane] : 0.0f;
-    x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
-    if (lane == 0) { red[48] = x; red[49] = y; red[50] = z; }
-  }
-  __syncthreads();
-  a = red[48]; b = red[49]; c = red[50];
-}
+// CTA-wide reductions with ONE barrier each: every warp publishes its partial results, and after
+// the barrier every warp folds the kFusedWarps partials itself (3 loads + a 16-lane butterfly).
+// The two functions use disjoint halves of `red` (128 floats) and alternate, so neither needs a
+// barrier before overwriting its slots: the other function's barrier lies in between.
 __device__ __forceinline__ void cta_max2(float& a, float& b, float* red) {
   a = warp_max(a); b = warp_max(b);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
   if (lane == 0) { red[warp] = a; red[16 + warp] = b; }
   __syncthreads();
-  float x = red[0], y = red[16];
+  float x = lane < kFusedWarps ? red[lane] : -INFINITY;
+  float y = lane < kFusedWarps ? red[16 + lane] : -INFINITY;
 #pragma unroll
-  for (int w = 1; w < kFusedWarps; ++w) { x = fmaxf(x, red[w]); y = fmaxf(y, red[16 + w]); }
-  a = x; b = y;
+  for (int o = 8; o > 0; o >>= 1) {
+    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, o));
+  }
+  a = __shfl_sync(0xffffffffu, x, 0);
+  b = __shfl_sync(0xffffffffu, y, 0);
+}
+__device__ __forceinline__ void cta_sum3(float& a, float& b, float& c, float* red) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* r = red + 64;
+  if (lane == 0) { r[warp] = a; r[16 + warp] = b; r[32 + warp] = c; }
+  __syncthreads();
+  float x = lane < kFusedWarps ? r[lane] : 0.0f;
+  float y = lane < kFusedWarps ? r[16 + lane] : 0.0f;
+  float z = lane < kFusedWarps ? r[32 + lane] : 0.0f;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+  }
+  a = __shfl_sync(0xffffffffu, x, 0);
+  b = __shfl_sync(0xffffffffu, y, 0);
+  c = __shfl_sync(0xffffffffu, z, 0);
 }
 
 template <int NBUF>
@@ -93,7 +103,7 @@ linear_listnet_kernel(const float* __restrict__ feat, const float* __restrict__ 
   float* w_s = reinterpret_cast<float*>(p);            p += fused_align16(4u * F);
   float* sc = reinterpret_cast<float*>(p);             p += fused_align16(4u * L);
   float* dd = reinterpret_cast<float*>(p);             p += fused_align16(4u * L);
-  float* red = reinterpret_cast<float*>(p);            p += 4u * 64;
+  float* red = reinterpret_cast<float*>(p);            p += 4u * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p);
 
   const int tid = threadIdx.x;
@@ -146,41 +156,49 @@ linear_listnet_kernel(const float* __restrict__ feat, const float* __restrict__ 
     const unsigned char* Ys = smem_raw + buf * stage_bytes + x_bytes;
     mbar_wait(bars + buf, (it / NBUF) & 1);
 
-    // ---- scores: one thread per row, 128-bit loads.  Rows are F floats apart, i.e. 8 l mod 32 banks
-    // for F = 136: the feature groups are walked from a start rotated by (l >> 2) & 1 so that the 8
-    // rows of a quarter warp hit 8 different 4-bank groups -------------------------------------------
+    // ---- scores: two threads per row (feature groups split in halves), 128-bit loads.  Rows are F
+    // floats apart (8 l mod 32 banks for F = 136) and the second half starts (ngroups + 1) / 2 groups
+    // further (4 banks further for F = 136): the 4 rows x 2 halves of a quarter warp hit 8 different
+    // 4-bank groups -----------------------------------------------------------------------------------
     const int rows = scores_out ? L : nb;
     {
       const float4* w4 = reinterpret_cast<const float4*>(w_s);
-      for (int l = tid; l < rows; l += kFusedThreads) {
-        const float4* xr = reinterpret_cast<const float4*>(Xs + static_cast<size_t>(l) * F);
-        int gg = (l >> 2) & 1;
-        gg = gg < ngroups ? gg : 0;
+      const int half = tid & 1;
+      const int gsplit = (ngroups + 1) >> 1;
+      const int g0 = half ? gsplit : 0, g1 = half ? ngroups : gsplit;
+      const int rows2 = (rows + 1) & ~1;   // both lanes of a pair run the loop (shuffle below)
+      for (int l = tid >> 1; l < rows2; l += kFusedThreads >> 1) {
+        const int lr = l < rows ? l : rows - 1;
+        const float4* xr = reinterpret_cast<const float4*>(Xs + static_cast<size_t>(lr) * F);
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll 4
-        for (int g = 0; g < ngroups; ++g) {
-          const float4 x = xr[gg], w = w4[gg];
+        for (int g = g0; g < g1; ++g) {
+          const float4 x = xr[g], w = w4[g];
           a0 = fmaf(x.x, w.x, a0); a1 = fmaf(x.y, w.y, a1);
           a2 = fmaf(x.z, w.z, a2); a3 = fmaf(x.w, w.w, a3);
-          gg = gg + 1 == ngroups ? 0 : gg + 1;
         }
-        sc[l] = ((a0 + a1) + (a2 + a3)) + b0;
+        float sum = (a0 + a1) + (a2 + a3);
+        sum += __shfl_xor_sync(0x3u << (threadIdx.x & 30), sum, 1);   // the pair only: other lanes may have left
+        if (half == 0 && l < rows) sc[l] = sum + b0;
       }
     }
     __syncthreads();
 
-    // ---- ListNet over the valid documents (same arithmetic as listnet_reg_kernel) -----------------
+    // ---- ListNet over the valid documents (same arithmetic as listnet_reg_kernel); the grades wait
+    // as floats in dd[], which the last pass overwrites with d loss / d score ------------------------
     float ms = -INFINITY, my = -INFINITY;
     for (int l = tid; l < nb; l += kFusedThreads) {
+      const float y = static_cast<float>(load_int_clamped(Ys, rel_bytes, l));
+      dd[l] = y;
       ms = fmaxf(ms, sc[l]);
-      my = fmaxf(my, static_cast<float>(load_int_clamped(Ys, rel_bytes, l)));
+      my = fmaxf(my, y);
     }
     cta_max2(ms, my, red);
     float zs = 0.0f, zy = 0.0f, a = 0.0f;
     for (int l = tid; l < nb; l += kFusedThreads) {
       const float ds = sc[l] - ms;
       const float es = ex2_approx(ds * kLog2e);
-      const float ey = ex2_approx((static_cast<float>(load_int_clamped(Ys, rel_bytes, l)) - my) * kLog2e);
+      const float ey = ex2_approx((dd[l] - my) * kLog2e);
       zs += es; zy += ey;
       a = fmaf(ey, ds, a);
     }
@@ -193,7 +211,7 @@ linear_listnet_kernel(const float* __restrict__ feat, const float* __restrict__ 
       const float s = l < rows ? sc[l] : 0.0f;
       if (l < nb) {
         const float es = ex2_approx((s - ms) * kLog2e);
-        const float ey = ex2_approx((static_cast<float>(load_int_clamped(Ys, rel_bytes, l)) - my) * kLog2e);
+        const float ey = ex2_approx((dd[l] - my) * kLog2e);
         d = es * izs - ey * izy;
       }
       dd[l] = d;
@@ -247,6 +265,7 @@ weighted_colsum_kernel(const float* __restrict__ qgrad, const float* __restrict_
   const int b0 = blockIdx.x * per, b1 = min(B, b0 + per);
   for (int f = threadIdx.x; f < cols; f += blockDim.x) {
     float s = 0.0f;
+#pragma unroll 8
     for (int b = b0; b < b1; ++b) s = fmaf(g[static_cast<size_t>(b) * g_stride], qgrad[static_cast<size_t>(b) * cols + f], s);
     partials[static_cast<size_t>(blockIdx.x) * cols + f] = s;
   }
