@@ -44,6 +44,10 @@ CONFIGS = {
                workload="PairwiseDCGHingeLoss synthetic (B=1024, L=1024) fp32"),
     "c4": dict(loss="ListNetLoss", B=8192, L=200, skew=True,
                workload="ListNet synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
+    # config 4 at eight times the batch: shows the ListNet kernel's bandwidth once the launch ramp
+    # (a few microseconds) no longer dominates a 7 us kernel
+    "c4x": dict(loss="ListNetLoss", B=65536, L=200, skew=True,
+                workload="ListNet synthetic MSLR-WEB30K-shaped (B=65536, L=200) fp32"),
     "c5": dict(loss="LambdaNDCGLoss2", B=65536, L=512, strong=True,
                workload="LambdaNDCGLoss2 synthetic (B=65536, L=512) query-sharded"),
     "ns": dict(loss="LambdaNDCGLoss2", B=4096, L=1024,

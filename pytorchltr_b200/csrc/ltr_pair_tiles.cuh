@@ -182,22 +182,42 @@ __device__ __forceinline__ void load_window(const float4* __restrict__ w4, float
   dwin[4] = w1.x; dwin[5] = w1.y; dwin[6] = w1.z; dwin[7] = w1.w;
 }
 
+// R consecutive floats of chunk `chunk`; chunks are S floats apart (S = R: contiguous ranks,
+// S = 4: every chunk padded to 4 slots, which makes the access one 128-bit load for every R)
+template <int R, int S>
+__device__ __forceinline__ void load_chunk_s(const float* __restrict__ p, int chunk, float (&v)[R]) {
+  if constexpr (S == 4 && R < 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + chunk * 4);
+    const float u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = u[r];
+  } else {
+    load_chunk<R>(p, chunk * S, v);
+  }
+}
+
 // All-pairs pass over one "ring" of C <= 32 chunks of R ranks held by one warp (C*R >= n).
-//   it    : rank-ordered factors of this block in shared memory, padded to C*R entries
-//   gcol  : warp-private column-gradient accumulators, chunk c at gcol[4c .. 4c+R), zero on entry
+//   it    : rank-ordered factors of this block in shared memory, chunk c at [S c, S c + R)
+//   gcol  : warp-private column-gradient accumulators, chunk c at gcol[4c .. 4c+R), zero on entry;
+//           with S == 4 (the warp-per-query kernel) it has 64 chunks: lanes without a chunk dump
+//           their (all-zero) column sums into chunk 32 + lane
 //   wtab  : window table for this R (TW_DELTA only)
 // Returns per-lane partial loss; racc[r] holds -sum lambda' of the lane's rows.
-template <int TW, bool FACTORED, int R>
+// FACTORED with S == 4 takes a fast path: a lane without rows carries a = 0 and the padding gain,
+// so its pairs contribute exact zeros and nothing has to be predicated except the address of its
+// column update; only the doubled last step of an even ring goes through the guarded code.
+template <int TW, bool FACTORED, int R, int S = R>
 __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict__ gcol,
                                            const float* __restrict__ wtab, int C, int n, int lane,
                                            float (&racc)[R]) {
+  constexpr bool kFast = FACTORED && S == 4;
   const bool active = lane < C;
   const int me = active ? lane : 0;
   const float* colx = FACTORED ? it.b : it.a;
   float ra[R], re[R], rg[R], rv[R];
-  load_chunk<R>(it.a, me * R, ra);
-  load_chunk<R>(it.g, me * R, rg);
-  if constexpr (FACTORED) load_chunk<R>(it.e, me * R, re);
+  load_chunk_s<R, S>(it.a, me, ra);
+  load_chunk_s<R, S>(it.g, me, rg);
+  if constexpr (FACTORED) load_chunk_s<R, S>(it.e, me, re);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     rv[r] = 1.0f;
@@ -218,9 +238,9 @@ __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict_
     float dwin[8];
     if constexpr (TW == TW_DELTA) load_window(reinterpret_cast<const float4*>(wtab) + kMaxChunks * 2, dwin);
     float cx[R], ce[R], cg[R];
-    load_chunk<R>(colx, me * R, cx);
-    load_chunk<R>(it.g, me * R, cg);
-    if constexpr (FACTORED) load_chunk<R>(it.e, me * R, ce);
+    load_chunk_s<R, S>(colx, me, cx);
+    load_chunk_s<R, S>(it.g, me, cg);
+    if constexpr (FACTORED) load_chunk_s<R, S>(it.e, me, ce);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -235,18 +255,47 @@ __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict_
 
   const int steps = C >> 1;
   // even ring: the last step pairs chunk l with l + C/2 from both ends; only the lower half commits
-  const bool dup_last = ((C & 1) == 0) && lane >= steps;
+  const bool even = (C & 1) == 0;
+  const bool dup_last = even && lane >= steps;
   int pc = me;
-  for (int m = 1; m <= steps; ++m) {
+  int m = 1;
+  if constexpr (kFast) {
+    const int nfast = even ? steps - 1 : steps;
+    for (; m <= nfast; ++m) {
+      pc = pc + 1 == C ? 0 : pc + 1;
+      float dwin[8];
+      if constexpr (TW == TW_DELTA)
+        load_window(reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2, dwin);
+      float4* g4 = reinterpret_cast<float4*>(gcol) + (active ? pc : 32 + lane);
+      const float4 gold = *g4;
+      float cx[R], ce[R], cg[R];
+      load_chunk_s<R, S>(colx, pc, cx);
+      load_chunk_s<R, S>(it.g, pc, cg);
+      load_chunk_s<R, S>(it.e, pc, ce);
+      float tc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int c = 0; c < R; ++c) {
+          float dw = rv[r];
+          if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
+          pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], ce[c], cg[c], dw, lacc, racc[r], tc[c]);
+        }
+      }
+      *g4 = make_float4(gold.x + tc[0], gold.y + tc[1], gold.z + tc[2], gold.w + tc[3]);
+      __syncwarp();
+    }
+  }
+  for (; m <= steps; ++m) {
     pc = pc + 1 == C ? 0 : pc + 1;
     const bool commit = active && !(dup_last && m == steps);
     float dwin[8];
     if constexpr (TW == TW_DELTA)
       load_window(reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2, dwin);
     float cx[R], ce[R], cg[R];
-    load_chunk<R>(colx, pc * R, cx);
-    load_chunk<R>(it.g, pc * R, cg);
-    if constexpr (FACTORED) load_chunk<R>(it.e, pc * R, ce);
+    load_chunk_s<R, S>(colx, pc, cx);
+    load_chunk_s<R, S>(it.g, pc, cg);
+    if constexpr (FACTORED) load_chunk_s<R, S>(it.e, pc, ce);
     float tl = 0.0f, tr[R], tc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { tr[r] = 0.0f; tc[r] = 0.0f; }

@@ -101,7 +101,9 @@ struct __align__(16) WarpScratch {
   __align__(16) float fb[kWarpL];
   __align__(16) float fe[kWarpL];
   __align__(16) float fg[kWarpL];
-  __align__(16) float gcol[kWarpL];        // column gradients: chunk c owns gcol[4c .. 4c+3]
+  __align__(16) float gcol[2 * kWarpL];    // column gradients: chunk c owns gcol[4c .. 4c+3]; the upper half is
+                                           // the dump of lanes without a chunk (ring_pass) and, before
+                                           // the pair phase, the rank -> document map
   __align__(16) float raw_s[kWarpL];       // scores, document order; reused: rank-order gradient
   __align__(16) int raw_y[kWarpL];         // relevance, document order; reused: document-order gradient
 };
@@ -146,7 +148,7 @@ __device__ __forceinline__ float ring_dispatch(WarpScratch& ws, const PairTables
   const int C = (n + R - 1) / R;
   float racc[R];
   const PairSoA it = {ws.fa, ws.fb, ws.fe, ws.fg};
-  const float l = ring_pass<TW, FACTORED, R>(it, ws.gcol, tb.wtab[R - 1], C, n, lane, racc);
+  const float l = ring_pass<TW, FACTORED, R, 4>(it, ws.gcol, tb.wtab[R - 1], C, n, lane, racc);
   // rank-order gradient (unscaled): column part + row part
   float* glin = ws.raw_s;
   if (lane < C) {
@@ -240,9 +242,8 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     // against the exact (32-bit key, index) order; if two scores are closer than 128 ulps and
     // came out in the wrong order, the exact 64-bit network is run instead.
     int doc[kWarpE];
-    float ss[kWarpE];
 #pragma unroll
-    for (int r = 0; r < kWarpE; ++r) { doc[r] = lane * kWarpE + r; ss[r] = sv[r]; }
+    for (int r = 0; r < kWarpE; ++r) doc[r] = lane * kWarpE + r;
     const bool rank_weighted = TW == TW_DELTA || (TW == TW_TWO && variant != 0);   // NDCG losses
     if (rank_weighted || ranking_out != nullptr) {
       uint32_t ekey[kWarpE];   // exact keys (document order for now)
@@ -256,10 +257,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       warp_bitonic_sort32<kWarpE>(pk, lane);
       __syncwarp();
 #pragma unroll
-      for (int r = 0; r < kWarpE; ++r) {
-        doc[r] = static_cast<int>(pk[r] & 127u);
-        ss[r] = ws.raw_s[doc[r]];
-      }
+      for (int r = 0; r < kWarpE; ++r) doc[r] = static_cast<int>(pk[r] & 127u);
       // The packed order is exact unless two neighbouring valid keys share their 25 key bits.
       const uint32_t pk_next = __shfl_down_sync(0xffffffffu, pk[0], 1);
       bool ambiguous = false;
@@ -275,7 +273,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
 #pragma unroll
         for (int r = 0; r < kWarpE; ++r) {
           const int p = lane * kWarpE + r;
-          xk[r] = pack_key(p < nb ? desc_key_f32(ss[r]) : kPadKey, doc[r]);
+          xk[r] = pack_key(p < nb ? desc_key_f32(ws.raw_s[doc[r]]) : kPadKey, doc[r]);
         }
         const uint64_t next0 = __shfl_down_sync(0xffffffffu, xk[0], 1);
         const bool bad = (xk[0] > xk[1]) || (xk[1] > xk[2]) || (xk[2] > xk[3]) || (lane < 31 && xk[3] > next0);
@@ -284,10 +282,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
           for (int r = 0; r < kWarpE; ++r) xk[r] = pack_key(ekey[r], lane * kWarpE + r);
           warp_bitonic_sort64<kWarpE>(xk, lane);
 #pragma unroll
-          for (int r = 0; r < kWarpE; ++r) {
-            doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
-            ss[r] = ws.raw_s[doc[r]];
-          }
+          for (int r = 0; r < kWarpE; ++r) doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
         }
       }
     }
@@ -367,50 +362,59 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
     const float inv_max_dcg = 1.0f / max_dcg;
 
-    // ---- rank-ordered relevance, score range ---------------------------------------------------
-    int ys[kWarpE];
+    // ---- score range; rank -> document map for the chunk owners -------------------------------------
     float smax = -INFINITY, smin = INFINITY;
+    int* rank2doc = reinterpret_cast<int*>(ws.gcol + kWarpL);
 #pragma unroll
     for (int r = 0; r < kWarpE; ++r) {
       const int p = lane * kWarpE + r;
-      ys[r] = ws.raw_y[doc[r]];
-      if (p < nb) { smax = fmaxf(smax, ss[r]); smin = fminf(smin, ss[r]); }
+      if (p < nb) { smax = fmaxf(smax, sv[r]); smin = fminf(smin, sv[r]); }   // document order: same extremes
       if (ranking_out && p < L) ranking_out[base + p] = doc[r];
     }
-    // sorted: the extremes sit at ranks 0 and nb - 1, but a reduction is as cheap as finding them
+    *reinterpret_cast<int4*>(rank2doc + lane * kWarpE) = make_int4(doc[0], doc[1], doc[2], doc[3]);
     smax = warp_max(smax);
     smin = -warp_max(-smin);
     const float mid = 0.5f * (smax + smin);
     // NaN / inf scores fail this test and take the stable form
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
-    __syncwarp();   // raw_s / raw_y fully consumed: they are reused below
+    // chunk size of the ring: R consecutive ranks per lane, the densest chunking that fits 32 lanes
+    // (the stable sigmoid form always takes R = 4)
+    const int Rq = (TW != TW_HINGE && !factored) ? 4 : max(1, (nb + 31) >> 5);
+    __syncwarp();
 
-    // ---- per-document factors -> shared memory (rank order) ------------------------------------
+    // ---- per-document factors -> shared memory: lane c writes chunk c = ranks [R c, R c + R) into the
+    // 4 slots [4 c, 4 c + 4) (unused slots and ranks >= n carry the padding values) -------------------
+    float diag = 0.0f;   // ARP1 / NDCG1 also count the pairs (i, i): w_i * log2(1 + e^0) = w_i
     {
       float fa[kWarpE], fb[kWarpE], fe[kWarpE], fg[kWarpE];
 #pragma unroll
-      for (int r = 0; r < kWarpE; ++r) {
-        const int p = lane * kWarpE + r;
-        fa[r] = factored ? 0.0f : -1.0e30f;   // padding
-        fb[r] = 0.0f; fe[r] = 0.0f; fg[r] = TW == TW_HINGE ? -1.0e30f : 0.0f;
-        if (p < nb) {
-          if constexpr (TW == TW_DELTA) fg[r] = gain_of_grade(ys[r]) * inv_max_dcg;
-          else if (TW == TW_TWO && variant != 0) fg[r] = gain_of_grade(ys[r]) * inv_max_dcg / tb.disc[p];
-          else fg[r] = static_cast<float>(ys[r]);
+      for (int j = 0; j < kWarpE; ++j) {
+        const int p = lane * Rq + j;
+        fa[j] = factored ? 0.0f : -1.0e30f;   // padding
+        fb[j] = 0.0f; fe[j] = 0.0f; fg[j] = TW == TW_HINGE ? -1.0e30f : 0.0f;
+        if (j < Rq && p < nb) {
+          const int d = rank2doc[p];
+          const float sd = ws.raw_s[d];
+          const int yd = ws.raw_y[d];
+          if constexpr (TW == TW_DELTA) fg[j] = gain_of_grade(yd) * inv_max_dcg;
+          else if (TW == TW_TWO && variant != 0) fg[j] = gain_of_grade(yd) * inv_max_dcg / tb.disc[p];
+          else fg[j] = static_cast<float>(yd);
+          if constexpr (TW == TW_TWO) diag += fg[j];
           if constexpr (TW == TW_HINGE) {
-            fa[r] = ss[r];                       // raw score: the hinge works on s_i - s_j itself
+            fa[j] = sd;                          // raw score: the hinge works on s_i - s_j itself
           } else if (factored) {
-            const float c = ss[r] - mid;
+            const float c = sd - mid;
             const float eh = c * k_hi;
             const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
-            fe[r] = eh;
-            fa[r] = ex2_approx(-eh) * (1.0f - el);
-            fb[r] = ex2_approx(eh) * (1.0f + el);
+            fe[j] = eh;
+            fa[j] = ex2_approx(-eh) * (1.0f - el);
+            fb[j] = ex2_approx(eh) * (1.0f + el);
           } else {
-            fa[r] = sigma * ss[r];
+            fa[j] = sigma * sd;
           }
         }
       }
+      __syncwarp();   // raw_s / raw_y / rank2doc fully consumed: they are reused below
       const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       reinterpret_cast<float4*>(ws.fa)[lane] = make_float4(fa[0], fa[1], fa[2], fa[3]);
       reinterpret_cast<float4*>(ws.fb)[lane] = make_float4(fb[0], fb[1], fb[2], fb[3]);
@@ -423,23 +427,16 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
 
     // ---- all pairs, once ----------------------------------------------------------------------------
     float lacc = 0.0f;
-    float diag = 0.0f;   // ARP1 / NDCG1 also count the pairs (i, i): w_i * log2(1 + e^0) = w_i
-    if constexpr (TW == TW_TWO) {
-      const float4 w4 = reinterpret_cast<const float4*>(ws.fg)[lane];
-      diag = (w4.x + w4.y) + (w4.z + w4.w);   // padding carries weight 0
-    }
     if (nb > 1) {
       if (factored) {
-        const int R = (nb + 31) >> 5;
-        if (R == 1) lacc = ring_dispatch<TW, true, 1>(ws, tb, nb, lane);
-        else if (R == 2) lacc = ring_dispatch<TW, true, 2>(ws, tb, nb, lane);
-        else if (R == 3) lacc = ring_dispatch<TW, true, 3>(ws, tb, nb, lane);
+        if (Rq == 1) lacc = ring_dispatch<TW, true, 1>(ws, tb, nb, lane);
+        else if (Rq == 2) lacc = ring_dispatch<TW, true, 2>(ws, tb, nb, lane);
+        else if (Rq == 3) lacc = ring_dispatch<TW, true, 3>(ws, tb, nb, lane);
         else lacc = ring_dispatch<TW, true, 4>(ws, tb, nb, lane);
       } else if constexpr (TW == TW_HINGE) {
-        const int R = (nb + 31) >> 5;
-        if (R == 1) lacc = ring_dispatch<TW, false, 1>(ws, tb, nb, lane);
-        else if (R == 2) lacc = ring_dispatch<TW, false, 2>(ws, tb, nb, lane);
-        else if (R == 3) lacc = ring_dispatch<TW, false, 3>(ws, tb, nb, lane);
+        if (Rq == 1) lacc = ring_dispatch<TW, false, 1>(ws, tb, nb, lane);
+        else if (Rq == 2) lacc = ring_dispatch<TW, false, 2>(ws, tb, nb, lane);
+        else if (Rq == 3) lacc = ring_dispatch<TW, false, 3>(ws, tb, nb, lane);
         else lacc = ring_dispatch<TW, false, 4>(ws, tb, nb, lane);
       } else {
         lacc = ring_dispatch<TW, false, 4>(ws, tb, nb, lane);
