@@ -7,8 +7,8 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2
 tail -3 gpurun_out/${tag}_pytest.log
 python bench.py --steps 2000 --warmup 200 > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err
 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/${tag}_bench_c2_reference.json 2>&1
-for c in ns c3 c4 c4m c5; do
-  steps=300; [ $c = c5 ] && steps=30
+for c in ns c3 c4 c4x c4m c4f c5; do
+  steps=300; [ $c = c5 ] && steps=30; [ $c = c4f ] && steps=30
   python bench.py --config $c --steps $steps --warmup 20 --no-e2e > gpurun_out/${tag}_bench_$c.json 2> gpurun_out/${tag}_bench_$c.err
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
@@ -23,7 +23,10 @@ ncu --set full --clock-control none --import-source on -k regex:listnet -s 3 -c 
     python bench.py --config c4 --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_c4.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_launches_ns.csv \
     python bench.py --config ns --steps 10 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_launch_ns.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:linear_listnet_kernel -s 2 -c 1 -o gpurun_out/${tag}_prof_c4f \
+    python bench.py --config c4f --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_c4f.log 2>&1
 python tools/e2e_probe.py > gpurun_out/${tag}_e2e_probe.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.txt 2>&1; tail -1 gpurun_out/${tag}_smoke.txt
 for f in gpurun_out/${tag}_bench_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
