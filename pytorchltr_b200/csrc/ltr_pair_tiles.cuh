@@ -67,12 +67,14 @@ __device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx
     // s_loser) in float32 with the reference's two roundings (negating a float32 difference is
     // exact), inactive when it is < 0; the kink loss == 0 stays active (gradient -1 / +1).
     // Padding is (score -1e30, relevance -1e30): it always loses with loss < 0.
+    // Branch-free (10 FP32 ops): w = sign(gd) by clamping the integer-valued grade difference,
+    // l = fma(-w, d, 1) = fl(1 - (+-d)) (w d is exact, so this is the reference's rounding),
+    // cnt = l >= 0 ? w : 0 (0 for equal grades), loss += |cnt| l.
     const float d = ra - cx;
-    const float sd = gd > 0.0f ? d : -d;
-    const float l = 1.0f - sd;
-    const bool act = (gd != 0.0f) && !(l < 0.0f);
-    lacc += act ? l : 0.0f;
-    const float cnt = act ? (gd > 0.0f ? 1.0f : -1.0f) : 0.0f;   // +1: the row wins
+    const float w = fminf(fmaxf(gd, -1.0f), 1.0f);
+    const float l = fmaf(-w, d, 1.0f);
+    const float cnt = !(l < 0.0f) ? w : 0.0f;     // +1: the row wins and the pair is active
+    lacc = fmaf(fabsf(cnt), l, lacc);
     racc -= cnt;
     cacc += cnt;
     return;
