@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LTR_VERSION 103            /* major*100 + minor */
+#define LTR_VERSION 104            /* major*100 + minor */
 #define LTR_MAX_LIST_SIZE 4096
 
 /* error codes */
@@ -177,6 +177,23 @@ int ltr_linear_listnet(const float *features, const float *weight, const float *
 int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride, int B, int F,
                                 float *dweight_out, float *dbias_out, void *workspace,
                                 size_t workspace_bytes, void *stream);
+
+/*
+ * Ragged -> padded batch on the device.  Replaces the Python loop of
+ * SVMRankDataset.collate_fn()._collate_fn with the default ListSampler
+ * (datasets/svmrank/svmrank.py:135-205, datasets/list_sampler.py:5-19) for a dataset held in device
+ * memory as features float32 [N*F], relevance int64 [N], offsets int64 [Q+1] (query q owns the
+ * documents offsets[q] .. offsets[q+1]); qidx int64 [B] are the queries of the batch.
+ *   feat_out [B*L*F] the first min(count, L) documents of every query, zero padded
+ *   rel_out  [B*L]   int64, zero padded (svmrank.py:149-150)
+ *   n_out    [B]     int64 min(count, L)                       (svmrank.py:194)
+ *   count_out [B]    int64 untruncated list sizes, NULL to skip
+ * L is the batch's list_size: max over the batch of min(count, max_list_size), computed by the
+ * caller (it sizes the outputs).
+ */
+int ltr_collate(const float *features, const int64_t *relevance, const int64_t *offsets,
+                const int64_t *qidx, int B, int L, int F, float *feat_out, int64_t *rel_out,
+                int64_t *n_out, int64_t *count_out, void *stream);
 
 /*
  * Host-buffer form of the three loss families (the call the reference's CPU path is

@@ -195,3 +195,25 @@ def linear_listnet(features, weight, bias, relevance, n):
     dweight = np.einsum("bl,blf->f", d, X)
     gscale = np.einsum("bl,blf->f", np.abs(d), np.abs(X))
     return s, loss, d, dweight, d.sum(), gscale
+
+
+def collate(items, indices, max_list_size=None):
+    """CPU restatement of SVMRankDataset.collate_fn(ListSampler(max_list_size)) for dense items
+    (datasets/svmrank/svmrank.py:135-205, datasets/list_sampler.py:5-19): test infrastructure.
+    `items[i]` = (features (n_i, F), relevance (n_i,), qid).  -> (features (B, L, F) f32, relevance
+    (B, L) i64, n (B,) i64, qid (B,) i64)."""
+    batch = [items[i] for i in indices]
+    sizes = [b[1].shape[0] if max_list_size is None else min(max_list_size, b[1].shape[0]) for b in batch]
+    L = max(sizes)                                                     # svmrank.py:142-143
+    F = batch[0][0].shape[1]
+    feats = np.zeros((len(batch), L, F), dtype=np.float32)             # :149-150
+    rel = np.zeros((len(batch), L), dtype=np.int64)
+    n = np.zeros(len(batch), dtype=np.int64)
+    qid = np.zeros(len(batch), dtype=np.int64)
+    for b, (x, y, q) in enumerate(batch):
+        k = min(x.shape[0], L)                                         # ListSampler: arange(list_size), :161,176
+        feats[b, :k] = x[:k]
+        rel[b, :k] = y[:k]
+        n[b] = k                                                       # min(sample.n, list_size), :194
+        qid[b] = q
+    return feats, rel, n, qid

@@ -16,6 +16,7 @@
 
 #include <atomic>
 
+#include "ltr_collate.cuh"
 #include "ltr_common.cuh"
 #include "ltr_linear_listnet.cuh"
 #include "ltr_metrics_warp.cuh"
@@ -1131,6 +1132,27 @@ int ltr_scale_rows(const float* g, int g_stride, const float* dscores, float* ou
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+int ltr_collate(const float* features, const int64_t* relevance, const int64_t* offsets, const int64_t* qidx,
+                int B, int L, int F, float* feat_out, int64_t* rel_out, int64_t* n_out, int64_t* count_out,
+                void* stream) {
+  if (B < 0 || L < 1 || F < 1) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!features || !relevance || !offsets || !qidx || !feat_out || !rel_out || !n_out) return LTR_EINVAL;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const size_t row_floats = static_cast<size_t>(L) * F;
+  const long long slabs = static_cast<long long>((row_floats + kCollateSlab - 1) / kCollateSlab);
+  const long long grid = slabs * B;
+  if (grid > 2147483647LL) return LTR_EUNSUPPORTED;
+  const int vec_ok = (F % 4 == 0) && aligned16(features) && aligned16(feat_out);
+  collate_kernel<<<static_cast<unsigned int>(grid), kCollateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      features, relevance, offsets, qidx, B, L, F, static_cast<int>(slabs), vec_ok, feat_out, rel_out, n_out,
+      count_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
 
 size_t ltr_linear_listnet_workspace_bytes(int F) {
   return F < 1 ? 0 : static_cast<size_t>(kFusedBwdCtas) * (static_cast<size_t>(F) + 1) * sizeof(float);
