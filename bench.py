@@ -743,6 +743,12 @@ def run_ours(args, cfg, rank, local_rank, world):
                  "frac": ach_pairs / peak_pairs, "pairs_per_launch": mean_pairs,
                  "note": "binding roofline of the O(L^2) losses (SURVEY.md F4); peak derived from "
                          "SM count x max SM clock x pipe width"}
+        if "Hinge" in cfg["loss"] and 128 < L <= 1024 and os.environ.get("LTR_HINGE") != "pairs" \
+                and os.environ.get("LTR_KERNEL") not in ("tiles", "generic"):
+            # the hinge losses no longer enumerate pairs at these sizes (sort + scans, O(n log n)):
+            # "achieved" is the pair rate an O(L^2) kernel would need to match it, not an issue rate
+            issue.update({"bound": "latency (O(n log n) sort + scans; pairs are not enumerated)",
+                          "frac": None, "equivalent_pair_rate_vs_fp32_issue_peak": ach_pairs / peak_pairs})
 
     # ---- e2e: public API, pinned host tensors in, host loss + gradient out -------------------
     e2e = None

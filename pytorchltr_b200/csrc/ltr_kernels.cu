@@ -18,6 +18,7 @@
 
 #include "ltr_collate.cuh"
 #include "ltr_common.cuh"
+#include "ltr_hinge_sorted.cuh"
 #include "ltr_linear_listnet.cuh"
 #include "ltr_metrics_warp.cuh"
 #include "ltr_pair_cta.cuh"
@@ -860,6 +861,27 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
   return LTR_OK;
 }
 
+// PairwiseHingeLoss / PairwiseDCGHingeLoss for 128 < L <= 1024: O(n log n) by sorting
+// (ltr_hinge_sorted.cuh).  LTR_HINGE=pairs keeps the O(n^2) pair kernels (A-B timing, cross-check).
+inline bool hinge_by_pairs() {
+  const char* v = getenv("LTR_HINGE");
+  return v && strcmp(v, "pairs") == 0;
+}
+
+int launch_hinge_sorted(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes, int B,
+                        int L, int dcg_mod, float* loss_out, float* grad_out, float* loss_sum, cudaStream_t st,
+                        const DeviceInfo& di) {
+  const int P = next_pow2(L);
+  const size_t smem = hinge_smem_bytes(L, P);
+  int grid = 0;
+  int rc = persistent_grid(hinge_sorted_kernel, kHingeThreads, smem, B, di, &grid);
+  if (rc != LTR_OK) return rc;
+  hinge_sorted_kernel<<<grid, kHingeThreads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, dcg_mod,
+                                                         loss_out, grad_out, loss_sum);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,
                   int n_bytes, int B, int L, float sigma, float* loss_out, float* grad_out,
                   int64_t* ranking_out, float* loss_sum, void* ws, size_t ws_bytes, void* stream) {
@@ -876,6 +898,10 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
     // every unordered pair once: one warp per query for short lists, one CTA per query on a
     // query-wide chunk ring up to 1024 documents, 128 x 128 rank tiles beyond
     const bool ring = L <= kRingMaxL && !force_tiles();
+    if ((pm == PM_HINGE || pm == PM_DCG_HINGE) && L > kWarpL && L <= kHingeMaxL && !ranking_out &&
+        !force_tiles() && !hinge_by_pairs())
+      return launch_hinge_sorted(scores, rel, rel_bytes, n, n_bytes, B, L, pm == PM_DCG_HINGE ? 1 : 0, loss_out,
+                                 grad_out, loss_sum, st, di);
 #define LTR_TILED(TWMODE, DCG)                                                                          \
   return L <= kWarpL                                                                                    \
              ? launch_pair_warp<TWMODE>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, DCG, loss_out,  \

@@ -682,3 +682,36 @@ def test_cuda_fused_linear_listnet_module_matches_unfused_modules():
     assert torch.allclose(lf, lp, rtol=1e-5, atol=1e-5)
     assert torch.allclose(fused.linear.weight.grad, plain.weight.grad, rtol=1e-4, atol=1e-6)
     assert torch.allclose(fused.linear.bias.grad, plain.bias.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["hinge", "dcg_hinge"])
+@pytest.mark.parametrize("B,L", [(6, 200), (3, 1000), (40, 130)])
+def test_cuda_sorted_hinge_matches_pair_kernels_and_oracle(mode, B, L, monkeypatch):
+    """Lists longer than 128 take the O(n log n) sorted hinge kernel.  Scores on a 1/4 grid put many
+    pairs exactly on the kink (s_i - s_j == 1: active, gradient -1 / +1) and create ties; the integer
+    valued gradients must equal the float32 restatement of the reference bit for bit, and the O(n^2)
+    pair kernels (LTR_HINGE=pairs) must agree."""
+    rng = np.random.default_rng(B * L)
+    s, y, n = (np.array(a) for a in make_batch(31 + L, B, L))
+    s[0] = np.round(s[0] * 4) / 4
+    s[1] = np.round(s[1] * 2) / 2
+    if B > 2:
+        s[2] = 0.5                      # every score tied
+    n[0] = L
+    y[np.arange(L)[None, :] >= n[:, None]] = 0
+    if B > 4:
+        y[4, : n[4]] = rng.integers(-5, 60, size=n[4])   # grades outside 0..31: in-kernel O(n^2) fallback
+    wts = rng.uniform(0.5, 2.0, size=B).astype(np.float32)
+    loss, grad = _run_cuda(mode, s, y, n, weights=wts)
+    ref_loss, ref_grad = oracle.pairwise_additive(mode, s, y, n, f32=True)
+    _assert_parity(loss, grad, ref_loss, ref_grad * wts[:, None].astype(np.float64))
+    if mode == "hinge":
+        assert np.array_equal(grad, ref_grad * wts[:, None].astype(np.float64).astype(np.float32)) or \
+            np.array_equal(grad.astype(np.float32), (ref_grad.astype(np.float32) * wts[:, None]))
+    monkeypatch.setenv("LTR_HINGE", "pairs")
+    loss2, grad2 = _run_cuda(mode, s, y, n, weights=wts)
+    assert np.allclose(loss, loss2, rtol=1e-5, atol=1e-6)
+    if mode == "hinge":
+        assert np.array_equal(grad, grad2)
+    else:
+        assert np.allclose(grad, grad2, rtol=1e-5, atol=1e-9)
