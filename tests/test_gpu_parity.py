@@ -715,3 +715,36 @@ def test_cuda_sorted_hinge_matches_pair_kernels_and_oracle(mode, B, L, monkeypat
         assert np.array_equal(grad, grad2)
     else:
         assert np.allclose(grad, grad2, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["ndcg2", "hinge", "logistic", "arp1"])
+@pytest.mark.parametrize("L", [130, 203, 512])
+def test_cuda_long_lists_int32_cpu_tensors_and_unaligned_rows(mode, L):
+    """Lists longer than 128 (ring / sorted-hinge kernels): int32 relevance and n (4-byte TMA rows),
+    list sizes that are not a multiple of 4 (plain-load path instead of TMA), CPU tensors through
+    ltr_loss_host, and a non-contiguous scores view (made contiguous by the wrapper)."""
+    B = 5
+    s, y, n = make_batch(1700 + L, B, L)
+    n[0] = 3
+    y[np.arange(L)[None, :] >= n[:, None]] = 0
+    ref_loss, ref_grad = _oracle_loss(mode, s, y, n)
+    dev = torch.device("cuda", 0)
+    # int32 inputs
+    st = torch.as_tensor(s).to(dev).requires_grad_(True)
+    out = _loss_module(mode)(st, torch.as_tensor(y).to(dev).int(), torch.as_tensor(n).to(dev).int())
+    out.sum().backward()
+    _assert_parity(out.detach().cpu().double().numpy(), st.grad.cpu().double().numpy(), ref_loss, ref_grad)
+    # CPU tensors (host-buffer entry point), (B, L, 1) scores like a model output
+    sc = torch.as_tensor(s).clone().reshape(B, L, 1).requires_grad_(True)
+    out = _loss_module(mode)(sc, torch.as_tensor(y), torch.as_tensor(n))
+    assert out.device.type == "cpu"
+    out.mean().backward()
+    assert sc.grad.shape == (B, L, 1) and sc.grad.device.type == "cpu"
+    _assert_parity(out.detach().double().numpy(), sc.grad.reshape(B, L).double().numpy() * B, ref_loss, ref_grad)
+    # a strided view: every second column of a wider tensor
+    wide = torch.zeros(B, 2 * L, device=dev)
+    wide[:, ::2] = torch.as_tensor(s).to(dev)
+    sv = wide[:, ::2].detach().requires_grad_(True)
+    out = _loss_module(mode)(sv, torch.as_tensor(y).to(dev), torch.as_tensor(n).to(dev))
+    out.sum().backward()
+    _assert_parity(out.detach().cpu().double().numpy(), sv.grad.cpu().double().numpy(), ref_loss, ref_grad)
