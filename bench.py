@@ -743,7 +743,7 @@ def run_ours(args, cfg, rank, local_rank, world):
                  "frac": ach_pairs / peak_pairs, "pairs_per_launch": mean_pairs,
                  "note": "binding roofline of the O(L^2) losses (SURVEY.md F4); peak derived from "
                          "SM count x max SM clock x pipe width"}
-        if "Hinge" in cfg["loss"] and 128 < L <= 1024 and os.environ.get("LTR_HINGE") != "pairs" \
+        if "Hinge" in cfg["loss"] and 128 < L <= 4096 and os.environ.get("LTR_HINGE") != "pairs" \
                 and os.environ.get("LTR_KERNEL") not in ("tiles", "generic"):
             # the hinge losses no longer enumerate pairs at these sizes (sort + scans, O(n log n)):
             # "achieved" is the pair rate an O(L^2) kernel would need to match it, not an issue rate

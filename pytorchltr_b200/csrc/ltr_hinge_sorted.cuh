@@ -1,5 +1,6 @@
 // ltr_hinge_sorted.cuh -- PairwiseHingeLoss / PairwiseDCGHingeLoss (loss/pairwise_additive.py:93-133)
-// in O(n log n + n G) per query instead of O(n^2), for list sizes 129 .. 1024.
+// in O(n log n + n G) per query instead of O(n^2), for list sizes 129 .. 4096 (256 threads per
+// query up to 1024 documents, 1024 threads beyond).
 //
 // The hinge pair term is piecewise linear: with d = fl(s_i - s_j) the pair (i wins on relevance) is
 // active iff !(fl(1 - d) < 0), i.e. iff d <= 1 (1 - d is exact around 1), and then contributes
@@ -22,9 +23,8 @@
 
 namespace ltr {
 
-constexpr int kHingeThreads = 256;
-constexpr int kHingeMaxL = 1024;
-constexpr int kHingePer = kHingeMaxL / kHingeThreads;   // documents per thread
+constexpr int kHingePer = 4;          // documents per thread: L <= 4 * THREADS
+constexpr int kHingeMaxWarps = 32;
 
 struct HingeSmem {
   uint64_t* keys;     // [P]
@@ -35,15 +35,16 @@ struct HingeSmem {
   uint16_t* doc;      // [Lp]
   uint16_t* A;        // [Lp + 1]
   double* S;          // [Lp + 1]
-  double* wsum_d;     // [8]
-  int* wsum_i;        // [8]
+  double* wsum_d;     // [32]
+  int* wsum_i;        // [32]
   int* hist;          // [40]
-  double* red_d;      // [16]
+  double* red_d;      // [32]
 };
 
 __host__ __device__ inline size_t hinge_smem_bytes(int L, int P) {
   const size_t Lp = (static_cast<size_t>(L) + 127) / 128 * 128;
-  return 8u * P + 4u * Lp * 2 + 4u * Lp * 2 + 2u * Lp + 2u * (Lp + 8) + 8u * (Lp + 2) + 8u * 8 + 4u * 8 + 4u * 40 + 8u * 16;
+  return 8u * P + 4u * Lp * 2 + 4u * Lp * 2 + 2u * Lp + 2u * (Lp + 8) + 8u * (Lp + 2) + 8u * kHingeMaxWarps +
+         4u * kHingeMaxWarps + 4u * 40 + 8u * kHingeMaxWarps;
 }
 
 __device__ __forceinline__ HingeSmem hinge_carve(unsigned char* base, int L, int P) {
@@ -51,13 +52,13 @@ __device__ __forceinline__ HingeSmem hinge_carve(unsigned char* base, int L, int
   HingeSmem m;
   m.keys = reinterpret_cast<uint64_t*>(base);      base += 8u * P;
   m.S = reinterpret_cast<double*>(base);           base += 8u * (Lp + 2);
-  m.wsum_d = reinterpret_cast<double*>(base);      base += 8u * 8;
-  m.red_d = reinterpret_cast<double*>(base);       base += 8u * 16;
+  m.wsum_d = reinterpret_cast<double*>(base);      base += 8u * kHingeMaxWarps;
+  m.red_d = reinterpret_cast<double*>(base);       base += 8u * kHingeMaxWarps;
   m.raw_s = reinterpret_cast<float*>(base);        base += 4u * Lp;
   m.raw_y = reinterpret_cast<int*>(base);          base += 4u * Lp;
   m.ss = reinterpret_cast<float*>(base);           base += 4u * Lp;
   m.cls = reinterpret_cast<int*>(base);            base += 4u * Lp;
-  m.wsum_i = reinterpret_cast<int*>(base);         base += 4u * 8;
+  m.wsum_i = reinterpret_cast<int*>(base);         base += 4u * kHingeMaxWarps;
   m.hist = reinterpret_cast<int*>(base);           base += 4u * 40;
   m.doc = reinterpret_cast<uint16_t*>(base);       base += 2u * Lp;
   m.A = reinterpret_cast<uint16_t*>(base);
@@ -67,6 +68,7 @@ __device__ __forceinline__ HingeSmem hinge_carve(unsigned char* base, int L, int
 // ascending score key: complement of the descending key (ltr_common.cuh)
 __device__ __forceinline__ uint32_t asc_key_f32(float x) { return ~desc_key_f32(x); }
 
+template <int kHingeThreads>
 __global__ void __launch_bounds__(kHingeThreads)
 hinge_sorted_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                     const void* __restrict__ n, int n_bytes, int B, int L, int P, int variant,

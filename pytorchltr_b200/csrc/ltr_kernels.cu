@@ -861,25 +861,38 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
   return LTR_OK;
 }
 
-// PairwiseHingeLoss / PairwiseDCGHingeLoss for 128 < L <= 1024: O(n log n) by sorting
+// PairwiseHingeLoss / PairwiseDCGHingeLoss for L > 128: O(n log n) by sorting
 // (ltr_hinge_sorted.cuh).  LTR_HINGE=pairs keeps the O(n^2) pair kernels (A-B timing, cross-check).
 inline bool hinge_by_pairs() {
   const char* v = getenv("LTR_HINGE");
   return v && strcmp(v, "pairs") == 0;
 }
 
-int launch_hinge_sorted(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes, int B,
-                        int L, int dcg_mod, float* loss_out, float* grad_out, float* loss_sum, cudaStream_t st,
-                        const DeviceInfo& di) {
+constexpr int kHingeMaxL = 4096;
+
+template <int THREADS>
+int launch_hinge_sorted_t(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes, int B,
+                          int L, int dcg_mod, float* loss_out, float* grad_out, float* loss_sum, cudaStream_t st,
+                          const DeviceInfo& di) {
   const int P = next_pow2(L);
   const size_t smem = hinge_smem_bytes(L, P);
   int grid = 0;
-  int rc = persistent_grid(hinge_sorted_kernel, kHingeThreads, smem, B, di, &grid);
+  int rc = persistent_grid(hinge_sorted_kernel<THREADS>, THREADS, smem, B, di, &grid);
   if (rc != LTR_OK) return rc;
-  hinge_sorted_kernel<<<grid, kHingeThreads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, dcg_mod,
-                                                         loss_out, grad_out, loss_sum);
+  hinge_sorted_kernel<THREADS><<<grid, THREADS, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, dcg_mod,
+                                                            loss_out, grad_out, loss_sum);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
+}
+
+int launch_hinge_sorted(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes, int B,
+                        int L, int dcg_mod, float* loss_out, float* grad_out, float* loss_sum, cudaStream_t st,
+                        const DeviceInfo& di) {
+  if (L <= 1024)
+    return launch_hinge_sorted_t<256>(scores, rel, rel_bytes, n, n_bytes, B, L, dcg_mod, loss_out, grad_out,
+                                      loss_sum, st, di);
+  return launch_hinge_sorted_t<1024>(scores, rel, rel_bytes, n, n_bytes, B, L, dcg_mod, loss_out, grad_out, loss_sum,
+                                     st, di);
 }
 
 int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, const void* n,

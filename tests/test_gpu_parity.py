@@ -685,7 +685,7 @@ def test_cuda_fused_linear_listnet_module_matches_unfused_modules():
 
 
 @pytest.mark.parametrize("mode", ["hinge", "dcg_hinge"])
-@pytest.mark.parametrize("B,L", [(6, 200), (3, 1000), (40, 130)])
+@pytest.mark.parametrize("B,L", [(6, 200), (3, 1000), (40, 130), (3, 1500), (2, 4096)])
 def test_cuda_sorted_hinge_matches_pair_kernels_and_oracle(mode, B, L, monkeypatch):
     """Lists longer than 128 take the O(n log n) sorted hinge kernel.  Scores on a 1/4 grid put many
     pairs exactly on the kink (s_i - s_j == 1: active, gradient -1 / +1) and create ties; the integer
