@@ -25,8 +25,19 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
     python bench.py --config ns --steps 10 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_launch_ns.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:linear_listnet_kernel -s 2 -c 1 -o gpurun_out/${tag}_prof_c4f \
     python bench.py --config c4f --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_c4f.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:hinge_sorted -s 3 -c 1 -o gpurun_out/${tag}_prof_c3 \
+    python bench.py --config c3 --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_full_c3.log 2>&1
+python tools/collate_probe.py > gpurun_out/${tag}_collate_probe.txt 2>&1
 python tools/e2e_probe.py > gpurun_out/${tag}_e2e_probe.txt 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.txt 2>&1; tail -1 gpurun_out/${tag}_smoke.txt
+# summarise the captures on the box and drop the reports (gpurun copies back at most 64 MiB)
+for c in c2 ns c4m c4 c4f c3; do
+  rep=gpurun_out/${tag}_prof_$c.ncu-rep
+  [ -f $rep ] || continue
+  python profiles/summarize_ncu.py $rep > gpurun_out/${tag}_ncu_full_$c.txt 2>/dev/null
+  python tools/ncu_lines.py $rep 40 > gpurun_out/${tag}_ncu_source_hotlines_$c.txt 2>/dev/null
+  rm -f $rep
+done
 for f in gpurun_out/${tag}_bench_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
