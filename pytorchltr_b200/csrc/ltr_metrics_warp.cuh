@@ -328,6 +328,21 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 
     // ---- the row: document j = q * 32 + lane -----------------------------------------------------------
     uint32_t key[E];
+    // grade counters for the ideal DCG, filled while the row is unpacked: eight 4-bit counters per
+    // lane (<= 8 documents at a time), widened to 16-bit fields (word f: grades f and f + 4)
+    bool wide = false;
+    uint32_t hacc = 0u;
+    uint32_t wcnt[4] = {0u, 0u, 0u, 0u};
+    auto count_grade = [&](int q, int j, int y) {
+      const bool valid = j < nb;
+      wide = wide || (valid && static_cast<unsigned int>(y) > 7u);
+      hacc += valid ? (1u << (4 * (y & 7))) : 0u;
+      if ((q & 7) == 7 || q == E - 1) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) wcnt[f] += (hacc >> (4 * f)) & 0x000f000fu;
+        hacc = 0u;
+      }
+    };
     if (staged) {
       mbar_wait(bar, iter & 1);
       const float* ss = reinterpret_cast<const float*>(stage);
@@ -346,6 +361,7 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
           }
           key[q] = j < nb ? desc_key_f32(s) : kPadKey;
           raw_y[j] = y;
+          count_grade(q, j, y);
         }
       } else {
         const int* sy1 = reinterpret_cast<const int*>(sy);
@@ -360,6 +376,7 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
           }
           key[q] = j < nb ? desc_key_f32(s) : kPadKey;
           raw_y[j] = y;
+          count_grade(q, j, y);
         }
       }
       __syncwarp();
@@ -380,6 +397,7 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
         }
         key[q] = j < nb ? desc_key_f32(s) : kPadKey;
         raw_y[j] = y;   // grades wait in shared memory (keeps the registers for loads in flight)
+        count_grade(q, j, y);
       }
       __syncwarp();
     }
@@ -452,34 +470,17 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
       // ---- ideal dcg@kk: the kv largest grades of the valid documents, then the same padding ----------
       float iv = warp_sum(pad_term);
       if (kv > 0) {
-        // grades 0..7: eight 4-bit counters per lane (<= 8 documents at a time), widened to 16-bit
-        // fields (word f: grades f and f + 4) and summed across the warp
-        bool wide = false;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int q0 = 0; q0 < E; q0 += 8) {
-          uint32_t h = 0u;
-#pragma unroll
-          for (int q = q0; q < q0 + 8 && q < E; ++q) {
-            const int y = raw_y[q * 32 + lane];
-            const bool valid = q * 32 + lane < nb;
-            wide = wide || (valid && static_cast<unsigned int>(y) > 7u);
-            h += valid ? (1u << (4 * (y & 7))) : 0u;
-          }
-#pragma unroll
-          for (int f = 0; f < 4; ++f) w[f] += (h >> (4 * f)) & 0x000f000fu;
-        }
         double acc = 0.0;
         if (!__any_sync(0xffffffffu, wide)) {
 #pragma unroll
           for (int f = 0; f < 4; ++f) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) w[f] += __shfl_xor_sync(0xffffffffu, w[f], o);
+            for (int o = 16; o > 0; o >>= 1) wcnt[f] += __shfl_xor_sync(0xffffffffu, wcnt[f], o);
           }
           int start = 0;
 #pragma unroll
           for (int g = 7; g >= 1; --g) {
-            const int cnt = static_cast<int>((w[g & 3] >> (16 * (g >> 2))) & 0xffffu);
+            const int cnt = static_cast<int>((wcnt[g & 3] >> (16 * (g >> 2))) & 0xffffu);
             const int end = min(start + cnt, kv);
             if (end > start) {
               const float gain = exp_gain ? gain_of_grade(g) : static_cast<float>(g);
