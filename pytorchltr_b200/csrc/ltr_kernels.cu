@@ -1079,11 +1079,19 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
     topk_metrics_warp_kernel<E><<<grid, kTopkWarps * 32, 0, st>>>(metric, scores, rel, rel_bytes, n, n_bytes, B, \
                                                                   L, k, exp_gain, tma, out, out_ld, tabs);  \
   } while (0)
+    // E = documents per lane: the smallest instantiated size that covers L (the kernel walks the
+    // row in strides of 32, so E need not be a power of two)
     if (L <= 32) LTR_TOPK_LAUNCH(1);
     else if (L <= 64) LTR_TOPK_LAUNCH(2);
+    else if (L <= 96) LTR_TOPK_LAUNCH(3);
     else if (L <= 128) LTR_TOPK_LAUNCH(4);
+    else if (L <= 160) LTR_TOPK_LAUNCH(5);
+    else if (L <= 192) LTR_TOPK_LAUNCH(6);
+    else if (L <= 224) LTR_TOPK_LAUNCH(7);
     else if (L <= 256) LTR_TOPK_LAUNCH(8);
+    else if (L <= 384) LTR_TOPK_LAUNCH(12);
     else if (L <= 512) LTR_TOPK_LAUNCH(16);
+    else if (L <= 768) LTR_TOPK_LAUNCH(24);
     else LTR_TOPK_LAUNCH(32);
 #undef LTR_TOPK_LAUNCH
     LTR_CUDA(cudaGetLastError());

@@ -584,7 +584,8 @@ def test_cabi_schedule_workspace_is_optional_and_does_not_change_results(B, L):
         assert np.array_equal(l, outs[0][0]) and np.array_equal(g, outs[0][1])
 
 
-@pytest.mark.parametrize("B,L", [(12, 5), (9, 37), (33, 128), (17, 200), (9, 500), (8, 1024), (8, 202)])
+@pytest.mark.parametrize("B,L", [(12, 5), (9, 37), (33, 128), (17, 200), (9, 500), (8, 1024), (8, 202), (8, 96),
+                                 (8, 150), (8, 190), (8, 250), (8, 300), (8, 700)])
 def test_cuda_topk_metrics_edge_cases(B, L, monkeypatch):
     """dcg@k / ndcg@k for k <= 32 take the top-k selection kernel: tied scores (lowest index first,
     incl. the massive-tie fallback), lists shorter than k, unmasked padded relevance (dcg.py:85),
