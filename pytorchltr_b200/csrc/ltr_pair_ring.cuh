@@ -275,7 +275,19 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
   const int C = (nb + R - 1) / R;
   const int G = (C + 31) >> 5;
   const int M = C >> 1;                 // ring steps 1 .. M; step 0 is the triangle inside a chunk
-  const int U = G * (M + 1);
+  // The last row group only has cl_n = C - 32 (G - 1) chunks.  When they fill at most half the warp,
+  // f lanes share every chunk ("replicas") and split its M + 1 steps into f runs of T: replica s of
+  // chunk c takes the steps s T .. s T + T - 1, so the group costs T instead of M + 1 steps.  All
+  // lanes of one iteration still touch different column chunks as long as T >= cl_n (two lanes meet
+  // the same column iff their chunk offsets differ by a multiple of T) and (f - 1) T + cl_n <= C (no
+  // collision around the ring): f is halved until both hold.
+  const int cl_n = C - ((G - 1) << 5);
+  int f = 1;
+  while (cl_n * f * 2 <= 32) f <<= 1;
+  int T = (M + f) / f;                  // ceil((M + 1) / f)
+  while (f > 1 && (T < cl_n || (f - 1) * T + cl_n > C)) { f >>= 1; T = (M + f) / f; }
+  const int U_full = (G - 1) * (M + 1);
+  const int U = U_full + T;             // f == 1: T == M + 1
   int u = static_cast<int>((static_cast<long long>(U) * warp) / kRingWarps);
   const int u_end = static_cast<int>((static_cast<long long>(U) * (warp + 1)) / kRingWarps);
   const bool even = (C & 1) == 0;
@@ -284,13 +296,19 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
 
   while (u < u_end) {
     // ---- a run of steps [m0, m1) of row group g ------------------------------------------------------
-    const int g = u / (M + 1);
+    const bool last = u >= U_full;
+    const int g = last ? G - 1 : u / (M + 1);
     int m0 = u - g * (M + 1);
-    const int m1 = min(M + 1, m0 + (u_end - u));
+    const int steps_g = (last && f > 1) ? T : M + 1;
+    const int m1 = min(steps_g, m0 + (u_end - u));
     u += m1 - m0;
-    const int c = (g << 5) + lane;
-    const bool active = c < C;
-    const bool full = ((g << 5) + 31) < C;            // warp-uniform
+    const bool replicated = last && f > 1;             // warp-uniform
+    // lane -> (chunk, replica); replica 0 of every chunk everywhere else
+    const int sub = replicated ? lane / cl_n : 0;
+    const int cl = replicated ? lane - sub * cl_n : lane;
+    const int c = (g << 5) + cl;
+    const bool active = replicated ? sub < f : c < C;
+    const bool full = !replicated && ((g << 5) + 31) < C;   // warp-uniform
     const int me = active ? c : 0;                    // an idle lane mirrors chunk 0 and never commits
     float ra[R], re[R], rg[R], rv[R], racc[R];
     load_chunk<R>(it.a, me * R, ra);
@@ -310,7 +328,7 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
       racc[r] = 0.0f;
     }
     if (m0 == 0) {
-      // ---- triangle inside the chunk (rank distance k - r > 0) ---------------------------------------
+      // ---- triangle inside the chunk (rank distance k - r > 0); replica 0 only ----------------------------
       float dwin[8];
       if constexpr (TW == TW_DELTA) {
         const float4 w1 = *reinterpret_cast<const float4*>(symc);
@@ -321,36 +339,62 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
       load_chunk<R>(colx, me * R, cx);
       load_chunk<R>(it.g, me * R, cg);
       if constexpr (FACTORED) load_chunk<R>(it.e, me * R, ce);
-      float tl = 0.0f;
+      float tl = 0.0f, tr[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) tr[r] = 0.0f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int k = r + 1; k < R; ++k) {
           float dw = rv[r];
           if constexpr (TW == TW_DELTA) dw = dwin[k - r + R - 1];
-          pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[k], FACTORED ? ce[k] : 0.0f, cg[k], dw, tl, racc[r],
-                                  racc[k]);
+          pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[k], FACTORED ? ce[k] : 0.0f, cg[k], dw, tl, tr[r],
+                                  tr[k]);
         }
       }
-      lacc += active ? tl : 0.0f;
-      m0 = 1;
+      if (active && sub == 0) {
+        lacc += tl;
+#pragma unroll
+        for (int r = 0; r < R; ++r) racc[r] += tr[r];
+      }
+      if (!replicated) m0 = 1;
     }
-    // even ring: the last step meets chunk c + C/2 from both ends; only the unwrapped end commits
-    const int m_plain = (even && m1 == M + 1) ? M : m1;
-    const int m_fast = full ? m_plain : m0;
-    for (int m = m0; m < m_fast; ++m)
-      ring_step<TW, FACTORED, true>(it, colx, gw, symc, c, true, m, C, false, ra, re, rg, rv, racc, lacc);
-    for (int m = max(m0, m_fast); m < m1; ++m)
-      ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, active, m, C, even && m == M, ra, re, rg, rv, racc,
-                                     lacc);
-    // ---- flush the rows ------------------------------------------------------------------------------------
-    if (active) {
-      float4* g4 = reinterpret_cast<float4*>(gw) + c;
-      float4 t = *g4;
-      t.x += racc[0]; t.y += racc[1]; t.z += racc[2]; t.w += racc[3];
-      *g4 = t;
+    if (!replicated) {
+      // even ring: the last step meets chunk c + C/2 from both ends; only the unwrapped end commits
+      const int m_plain = (even && m1 == M + 1) ? M : m1;
+      const int m_fast = full ? m_plain : m0;
+      for (int m = m0; m < m_fast; ++m)
+        ring_step<TW, FACTORED, true>(it, colx, gw, symc, c, true, m, C, false, ra, re, rg, rv, racc, lacc);
+      for (int m = max(m0, m_fast); m < m1; ++m)
+        ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, active, m, C, even && m == M, ra, re, rg, rv, racc,
+                                       lacc);
+      // ---- flush the rows ----------------------------------------------------------------------------------
+      if (active) {
+        float4* g4 = reinterpret_cast<float4*>(gw) + c;
+        float4 t = *g4;
+        t.x += racc[0]; t.y += racc[1]; t.z += racc[2]; t.w += racc[3];
+        *g4 = t;
+      }
+      __syncwarp();
+    } else {
+      // replica `sub` of chunk c: iteration t is its ring step sub * T + t (step 0 is the triangle above)
+      for (int t = m0; t < m1; ++t) {
+        const int m = sub * T + t;
+        const bool on = active && m >= 1 && m <= M;
+        ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, on, on ? m : 1, C, even && m == M, ra, re, rg, rv,
+                                       racc, lacc);
+      }
+      // the f replicas of a chunk add their row sums one after the other
+      for (int s = 0; s < f; ++s) {
+        if (active && sub == s) {
+          float4* g4 = reinterpret_cast<float4*>(gw) + c;
+          float4 tt = *g4;
+          tt.x += racc[0]; tt.y += racc[1]; tt.z += racc[2]; tt.w += racc[3];
+          *g4 = tt;
+        }
+        __syncwarp();
+      }
     }
-    __syncwarp();
   }
   return lacc;
 }
