@@ -91,3 +91,24 @@ def test_work_split_is_even():
         sched = schedule(C)
         steps = [len({it for w, it, *_ in sched if w == warp}) for warp in range(WARPS)]
         assert max(steps) - min(steps) <= 2, (C, steps)
+
+
+@pytest.mark.parametrize("C", list(range(2, 33)))
+def test_single_warp_ring_every_chunk_pair_once(C):
+    """ring_pass (csrc/ltr_pair_tiles.cuh): one warp, lane l owns chunk l, step m meets chunk
+    (l + m) mod C for m = 1 .. C // 2; on an even ring the last step is met from both ends and only
+    the lanes below C / 2 commit."""
+    steps = C // 2
+    even = C % 2 == 0
+    pairs = {}
+    for m in range(1, steps + 1):
+        cols = []
+        for lane in range(C):
+            pc = (lane + m) % C
+            if even and m == steps and lane >= steps:
+                continue
+            cols.append(pc)
+            key = (min(lane, pc), max(lane, pc))
+            pairs[key] = pairs.get(key, 0) + 1
+        assert len(cols) == len(set(cols))
+    assert len(pairs) == C * (C - 1) // 2 and set(pairs.values()) == {1}
