@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LTR_VERSION 104            /* major*100 + minor */
+#define LTR_VERSION 105            /* major*100 + minor */
 #define LTR_MAX_LIST_SIZE 4096
 
 /* error codes */
@@ -177,6 +177,20 @@ int ltr_linear_listnet(const float *features, const float *weight, const float *
 int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride, int B, int F,
                                 float *dweight_out, float *dbias_out, void *workspace,
                                 size_t workspace_bytes, void *stream);
+
+/*
+ * Position-biased click model (click_simulation/pbm.py:12-63): for the document
+ * d = rankings[b, r] at rank r,
+ *   propensity_out[b, d] = 1 / (2 + r)^eta  if r < min(n[b], cutoff)  else 0    (cutoff 0 = none)
+ *   click_prob_out[b, d] = relevance_probs[ys[b, d]] * propensity_out[b, d]
+ * both float32 [B*L] in DOCUMENT order (the reference inverts the ranking with a second argsort).
+ * rankings int64 [B*L] must hold a permutation of 0..L-1 per row (ltr_rank_by_score's output);
+ * grades outside 0..n_probs-1 are clamped.  The Bernoulli draw of the clicks is left to the caller.
+ */
+int ltr_pbm_probabilities(const int64_t *rankings, const void *ys, int ys_bytes, const void *n,
+                          int n_bytes, const float *relevance_probs, int n_probs, int cutoff,
+                          float eta, int B, int L, float *click_prob_out, float *propensity_out,
+                          void *stream);
 
 /*
  * Ragged -> padded batch on the device.  Replaces the Python loop of

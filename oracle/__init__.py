@@ -217,3 +217,24 @@ def collate(items, indices, max_list_size=None):
         n[b] = k                                                       # min(sample.n, list_size), :194
         qid[b] = q
     return feats, rel, n, qid
+
+
+def pbm_probabilities(rankings, ys, n, relevance_probs, cutoff=None, eta=1.0):
+    """CPU restatement of the deterministic part of simulate_pbm (click_simulation/pbm.py:32-53,
+    returned in document order like :55-62): -> (click probability, propensity), (B, L) float64."""
+    rk = np.asarray(rankings, dtype=np.int64)
+    y = np.asarray(ys, dtype=np.int64)
+    nn = np.asarray(n, dtype=np.int64).copy()
+    rp = np.asarray(relevance_probs, dtype=np.float64)
+    B, L = rk.shape
+    if cutoff is not None:
+        nn = np.minimum(nn, cutoff)                                       # :33-34
+    obs = 1.0 / (1.0 + (1.0 + np.arange(L))) ** eta                      # :37-39
+    obs = np.where(np.arange(L)[None, :] < nn[:, None], obs[None, :], 0.0)   # :40-42
+    cp = np.zeros((B, L))
+    pr = np.zeros((B, L))
+    for b in range(B):
+        ranked_y = y[b, rk[b]]                                            # :45
+        pr[b, rk[b]] = obs[b]                                             # :58-62 (inverse permutation)
+        cp[b, rk[b]] = rp[ranked_y] * obs[b]                              # :48-53
+    return cp, pr

@@ -17,7 +17,7 @@ SYMBOLS = (
     "ltr_listnet", "ltr_rank_metrics", "ltr_rank_by_score", "ltr_scale_rows",
     "ltr_host_workspace_bytes", "ltr_loss_host", "ltr_schedule_workspace_bytes",
     "ltr_pairwise_additive_ws", "ltr_lambda_ws", "ltr_host_workspace_dscores_offset",
-    "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate",
+    "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate", "ltr_pbm_probabilities",
 )
 
 ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
@@ -80,6 +80,9 @@ def _declare(lib):
     lib.ltr_linear_listnet_backward.restype = c_int
     lib.ltr_linear_listnet_backward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                                 c_void_p, c_size_t, c_void_p]
+    lib.ltr_pbm_probabilities.restype = c_int
+    lib.ltr_pbm_probabilities.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                          c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.ltr_collate.restype = c_int
     lib.ltr_collate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]

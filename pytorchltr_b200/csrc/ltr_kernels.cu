@@ -1180,6 +1180,54 @@ int ltr_scale_rows(const float* g, int g_stride, const float* dscores, float* ou
 
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
+// Position-biased click model (click_simulation/pbm.py:12-63): the document at rank r of query b
+// is observed with probability 1 / (2 + r)^eta if r < min(n, cutoff) (else 0) and, once observed,
+// clicked with probability relevance_probs[grade].  Written in DOCUMENT order (the reference inverts
+// the ranking with a second argsort, :55-62); the Bernoulli draw stays with the caller's generator.
+__global__ void __launch_bounds__(256)
+pbm_probabilities_kernel(const int64_t* __restrict__ rankings, const void* __restrict__ ys, int ys_bytes,
+                         const void* __restrict__ n, int n_bytes, const float* __restrict__ relevance_probs,
+                         int n_probs, int cutoff, float eta, int B, int L, float* __restrict__ click_prob_out,
+                         float* __restrict__ propensity_out) {
+  const size_t total = static_cast<size_t>(B) * L;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / L), r = static_cast<int>(i - static_cast<size_t>(b) * L);
+    int nb = load_n(n, n_bytes, b, L);
+    if (cutoff > 0 && cutoff < nb) nb = cutoff;                       // :33-34
+    long long d = rankings[i];
+    d = d < 0 ? 0 : (d >= L ? L - 1 : d);
+    const float obs = r < nb ? 1.0f / powf(2.0f + static_cast<float>(r), eta) : 0.0f;   // :37-42
+    int y = load_int_clamped(ys, ys_bytes, static_cast<size_t>(b) * L + d);
+    y = y < 0 ? 0 : (y >= n_probs ? n_probs - 1 : y);
+    const size_t o = static_cast<size_t>(b) * L + d;
+    propensity_out[o] = obs;
+    click_prob_out[o] = relevance_probs[y] * obs;                     // :45-53
+  }
+}
+
+int ltr_pbm_probabilities(const int64_t* rankings, const void* ys, int ys_bytes, const void* n, int n_bytes,
+                          const float* relevance_probs, int n_probs, int cutoff, float eta, int B, int L,
+                          float* click_prob_out, float* propensity_out, void* stream) {
+  int rc = check_common(reinterpret_cast<const float*>(rankings), n, n_bytes, B, L);
+  if (rc != LTR_OK) return rc;
+  if ((ys_bytes != 4 && ys_bytes != 8) || n_probs < 1 || cutoff < 0) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!ys || !relevance_probs || !click_prob_out || !propensity_out) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const size_t total = static_cast<size_t>(B) * L;
+  long long want = static_cast<long long>((total + 255) / 256);
+  const long long cap = static_cast<long long>(di.sms) * 8;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  pbm_probabilities_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rankings, ys, ys_bytes, n, n_bytes, relevance_probs, n_probs, cutoff, eta, B, L, click_prob_out,
+      propensity_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 int ltr_collate(const float* features, const int64_t* relevance, const int64_t* offsets, const int64_t* qidx,
                 int B, int L, int F, float* feat_out, int64_t* rel_out, int64_t* n_out, int64_t* count_out,
                 void* stream) {

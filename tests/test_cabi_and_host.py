@@ -28,7 +28,7 @@ def test_library_builds_loads_and_exports_header_symbols():
         assert hasattr(handle, name), f"{name} declared in include/ltr_sm100.h but not exported"
     assert sorted(_lib.SYMBOLS) == names
     lib = _lib.lib()
-    assert lib.ltr_version() >= 104
+    assert lib.ltr_version() >= 105
     assert lib.ltr_strerror(0) == b"success"
     assert b"invalid" in lib.ltr_strerror(-1)
     assert lib.ltr_host_workspace_bytes(4, 8) >= 4 * 8 * 16
