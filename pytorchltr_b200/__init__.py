@@ -7,7 +7,11 @@ PyTorch (device memory, streams, autograd plumbing); all arithmetic runs in
 ``csrc/libltr_sm100.so`` (C ABI in ``include/ltr_sm100.h``).  There is no CPU
 compute path: CPU tensors are staged through the GPU, and a missing extension or
 missing GPU raises.
+
+Beyond the drop-in path: ``fused`` (linear scorer + ListNet in one pass over the features),
+``datasets`` (device-resident ragged dataset, GPU collation) and ``click_simulation`` (the
+reference's PBM click simulators).
 """
-from pytorchltr_b200 import evaluation, loss, utils  # noqa: F401
+from pytorchltr_b200 import click_simulation, datasets, evaluation, fused, loss, utils  # noqa: F401
 
 __version__ = "0.1.0"
