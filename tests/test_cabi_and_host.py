@@ -98,6 +98,13 @@ def test_no_cpu_fallback_fails_loudly():
         p.evaluation.ndcg(s, y, n, k=10)
     with pytest.raises(RuntimeError, match="CUDA only"):
         p.utils.rank_by_score(s, n)
+    # the rows built beyond the loss path fail the same way: no silent CPU path anywhere
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        p.fused.linear_listnet(torch.zeros(2, 3, 4), torch.zeros(4, requires_grad=True), None, y, n)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        p.datasets.DeviceRankingDataset(torch.zeros(5, 4), torch.zeros(5, dtype=torch.long), torch.tensor([0, 2, 5]))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        p.click_simulation.simulate_perfect(torch.tensor([[0, 1, 2], [2, 1, 0]]), y, n)
 
 
 def test_product_code_never_touches_the_oracle():
