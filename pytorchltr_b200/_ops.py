@@ -196,7 +196,7 @@ class _FusedLoss(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, scores, relevance, n, family, mode, sigma):
+    def forward(ctx, scores, relevance, n, family, mode, sigma, loss_sum=None):
         dev = _device_for(scores)
         want_grad = bool(ctx.needs_input_grad[0])
         ctx.scores_shape = scores.shape
@@ -217,7 +217,7 @@ class _FusedLoss(torch.autograd.Function):
             loss = torch.empty(0, dtype=torch.float32, device=dev)
             grad = torch.empty((0, L), dtype=torch.float32, device=dev) if want_grad else None
         else:
-            loss, grad, _ = launch_loss(family, mode, s, y, nn, sigma, want_grad)
+            loss, grad, _ = launch_loss(family, mode, s, y, nn, sigma, want_grad, loss_sum=loss_sum)
         if want_grad:
             ctx.save_for_backward(grad)
         out = loss
@@ -243,17 +243,25 @@ class _FusedLoss(torch.autograd.Function):
                     out = out.to(ctx.scores_dtype)
                 if out.shape != ctx.scores_shape:
                     out = out.reshape(ctx.scores_shape)
-                return out, None, None, None, None, None
+                return out, None, None, None, None, None, None
         out = scale_rows(g, saved)
         if out.dtype != ctx.scores_dtype:
             out = out.to(ctx.scores_dtype)
         if out.device != ctx.scores_device:
             out = to_host(out, g)
-        return out.reshape(ctx.scores_shape), None, None, None, None, None
+        return out.reshape(ctx.scores_shape), None, None, None, None, None, None
 
 
-def fused_loss(scores, relevance, n, family: int, mode: int, sigma: float = 1.0):
-    return _FusedLoss.apply(scores, relevance, n, family, mode, float(sigma))
+def fused_loss(scores, relevance, n, family: int, mode: int, sigma: float = 1.0,
+               loss_sum: Optional[torch.Tensor] = None):
+    """``loss_sum`` (extension, CUDA callers only): a float32 device scalar to which the kernel
+    adds ``sum_b loss_b`` in its epilogue (atomically; the caller zeroes it) -- the input of the
+    scalar all-reduce behind a global mean (``pytorchltr_b200.distributed``)."""
+    if loss_sum is not None:
+        if not (scores.is_cuda and loss_sum.is_cuda and loss_sum.dtype == torch.float32 and loss_sum.numel() >= 1):
+            raise ValueError("loss_sum must be a float32 CUDA tensor and needs CUDA inputs")
+        loss_sum = loss_sum.detach()
+    return _FusedLoss.apply(scores, relevance, n, family, mode, float(sigma), loss_sum)
 
 
 def rank_metric(metric: int, scores, relevance, n, k: Optional[int], exp: bool):

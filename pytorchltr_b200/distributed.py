@@ -59,6 +59,31 @@ def global_mean(per_query: torch.Tensor, group=None) -> torch.Tensor:
     return (buf[0] / buf[1].clamp(min=1.0)).to(per_query.dtype)
 
 
+class _MeanOfShards(torch.autograd.Function):
+    """``buf[0] / max(buf[1], 1)`` as a function of the local per-query losses: ``buf`` already holds
+    the all-reduced ``[sum, count]``; the backward pass hands every local query the broadcast
+    gradient ``g / count`` (a stride-0 view, which the loss's backward reads in place)."""
+
+    @staticmethod
+    def forward(ctx, per_query, buf):
+        count = buf[1].clamp(min=1.0)
+        ctx.save_for_backward(count)
+        ctx.num_queries = per_query.shape[0]
+        ctx.out_dtype = per_query.dtype
+        return (buf[0] / count).to(per_query.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (count,) = ctx.saved_tensors
+        return (g / count.to(g.dtype)).to(ctx.out_dtype).reshape(1).expand(ctx.num_queries), None
+
+
+def _accepts_loss_sum(loss_fn) -> bool:
+    fwd = getattr(loss_fn, "forward", None)
+    code = getattr(fwd, "__code__", None)
+    return code is not None and "loss_sum" in code.co_varnames[:code.co_argcount]
+
+
 def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.Tensor,
                       n: torch.Tensor, group=None) -> torch.Tensor:
     """Global mean loss over the query shards of all ranks.
@@ -67,10 +92,25 @@ def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.
     equals the mean over every query of every rank; its backward gives each rank
     ``d mean / d scores_local = grad_local / B_global`` (other ranks' terms do not depend
     on the local scores), so no gradient collective is needed for the scores.
+
+    With CUDA inputs and a loss module of this package the local sum is produced by the loss
+    kernel's own epilogue (``loss_sum``: one atomic add per query), so the 2-element
+    ``[sum, count]`` all-reduce follows the kernel with no reduction launch in between; the whole
+    step (kernel, collective, backward) is CUDA-graph capturable.  The float32 atomics make the
+    last bits of the reported mean depend on the summation order; gradients do not depend on it.
+
+    Parameter gradients of a model in front of the loss must be SUM-reduced across ranks
+    (the 1 / B_global factor is already in the scalar's backward).  Under
+    ``torch.nn.parallel.DistributedDataParallel``, which AVERAGES gradients, multiply the
+    returned loss by the world size to compensate.
     """
-    per_query = loss_fn(scores, relevance, n)
-    local_sum = per_query.sum()
-    buf = global_sum_count(per_query, group)
-    count = buf[1].clamp(min=1.0).to(local_sum.dtype)
-    others = (buf[0].to(local_sum.dtype) - local_sum.detach())
-    return (local_sum + others) / count
+    if scores.is_cuda and _accepts_loss_sum(loss_fn):
+        buf = torch.zeros(2, dtype=torch.float32, device=scores.device)
+        buf[1:].fill_(float(scores.shape[0]))
+        per_query = loss_fn(scores, relevance, n, loss_sum=buf[:1])
+        if _world(group) > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    else:
+        per_query = loss_fn(scores, relevance, n)
+        buf = global_sum_count(per_query, group)
+    return _MeanOfShards.apply(per_query, buf)

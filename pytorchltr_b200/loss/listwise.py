@@ -21,5 +21,5 @@ class ListNetLoss(_torch.nn.Module):
         super().__init__()
 
     def forward(self, scores: _torch.FloatTensor, relevance: _torch.LongTensor,
-                n: _torch.LongTensor) -> _torch.FloatTensor:
-        return _ops.fused_loss(scores, relevance, n, _lib.FAMILY_LISTNET, 0, 1.0)
+                n: _torch.LongTensor, loss_sum=None) -> _torch.FloatTensor:
+        return _ops.fused_loss(scores, relevance, n, _lib.FAMILY_LISTNET, 0, 1.0, loss_sum)

@@ -24,16 +24,18 @@ class _PairwiseAdditiveLoss(_torch.nn.Module):
         return 1.0
 
     def forward(self, scores: _torch.FloatTensor, relevance: _torch.LongTensor,
-                n: _torch.LongTensor) -> _torch.FloatTensor:
+                n: _torch.LongTensor, loss_sum=None) -> _torch.FloatTensor:
         """Computes the per-query loss for a padded batch.
 
         Args:
             scores: ``(B, L)`` or ``(B, L, 1)`` scores.
             relevance: ``(B, L)`` or ``(B, L, 1)`` integer relevance labels.
             n: ``(B,)`` number of documents per query; documents ``>= n`` are padding.
+            loss_sum: extension (not in the reference): float32 CUDA scalar to which the kernel
+                adds the sum of the per-query losses (see ``pytorchltr_b200.distributed``).
         """
         return _ops.fused_loss(scores, relevance, n, _lib.FAMILY_ADDITIVE, self._mode,
-                               self._sigma())
+                               self._sigma(), loss_sum)
 
 
 class PairwiseHingeLoss(_PairwiseAdditiveLoss):

@@ -30,18 +30,20 @@ class LambdaLoss(_torch.nn.Module):
         self.sigma = sigma
 
     def forward(self, scores: _torch.FloatTensor, relevance: _torch.LongTensor,
-                n: _torch.LongTensor) -> _torch.FloatTensor:
+                n: _torch.LongTensor, loss_sum=None) -> _torch.FloatTensor:
         """Computes the per-query loss for a padded batch.
 
         Args:
             scores: ``(B, L)`` or ``(B, L, 1)`` scores.
             relevance: ``(B, L)`` or ``(B, L, 1)`` integer relevance labels.
             n: ``(B,)`` number of documents per query; documents ``>= n`` are padding.
+            loss_sum: extension (not in the reference): float32 CUDA scalar to which the kernel
+                adds the sum of the per-query losses (see ``pytorchltr_b200.distributed``).
         """
         if self._mode is None:
             raise NotImplementedError
         return _ops.fused_loss(scores, relevance, n, _lib.FAMILY_LAMBDA, self._mode,
-                               float(self.sigma))
+                               float(self.sigma), loss_sum)
 
 
 class LambdaARPLoss1(LambdaLoss):
