@@ -1,32 +1,46 @@
 #!/usr/bin/env python
-"""Benchmark of the loss hot path: `loss = fn(scores, relevance, n); loss.sum().backward()`.
+"""Benchmark of the loss hot path: `loss_fn(scores, relevance, n).mean().backward()`.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one forward+backward pass of the hot path over one padded batch of synthetic
-queries (BASELINE.json metric "loss fwd+bwd queries/sec at (B, L)").  The default workload
-is BASELINE.json configs[1]: LambdaNDCGLoss2, B=4096 queries x L=128 documents per GPU, fp32,
-n ~ U[L/2, L], 5 relevance grades.  Successive steps use different batches of a resident
-pool that is larger than the 126 MB L2, so no step finds its inputs in cache.
+queries (BASELINE.json metric "loss fwd+bwd queries/sec at (B, L)"), written the way the
+reference's own training loop writes it (examples/01-basic-usage.py:72-74).
+
+Default workload = BASELINE.json configs[4], the largest single-GPU configuration and the split
+`north_star` names for 1/2/4/8 GPUs: LambdaNDCGLoss2, B=65536 queries x L=512 documents, fp32,
+n ~ U[L/2, L], 5 relevance grades, STRONG scaling: the 65536 queries are sharded over the ranks
+(contiguous blocks, no data-path collective) and the step of a multi-rank run is
+`pytorchltr_b200.distributed.sharded_mean_loss(...).backward()`, whose 2-element [sum, count]
+all-reduce (fed by the loss kernel's own epilogue) is captured into the step's CUDA graph.
+Successive steps use different batches of a resident pool that is larger than the 126 MB L2.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (the fused loss+gradient kernel) vs the measured HBM peak
-  issue_roofline  the same kernel vs the FP32-issue / MUFU pair-rate ceiling, which is the
-                binding limit of every O(L^2) loss
-  cpu_baseline  the CPU oracle (a C port of the reference algorithm; the reference itself is
-                Python and cannot travel to the GPU box) on this host's cores, bounded sample
-  e2e           same metric through the public API with pinned HOST tensors: H2D of the inputs
-                and D2H of loss + gradient inside the timed region
-  clocks        SM clock / throttle reasons sampled during the timed region
-`--impl reference` times the CPU oracle port with all host threads on the same workload.
+  roofline        dominant kernel (the fused loss+gradient kernel) vs the measured HBM peak
+  issue_roofline  the same kernel vs the MEASURED MUFU pair-rate ceiling (profiles/issue_peaks.json,
+                  tools/issue_peak.cu), the binding limit of every O(L^2) loss
+  windows         best / median ms per step over repeated K-step windows of the same run
+  cpu_baseline    the CPU oracle (C port of the reference algorithm, OpenMP) on this host's cores,
+                  bounded sample; plus the unmodified Python reference on CPU and eager on the B200
+                  (live when git-ignored baseline/_ref is present, else profiles/reference_timing.json)
+  e2e             same metric through the public API with pinned HOST tensors (reference dtypes:
+                  float32 scores, int64 relevance, int64 n): H2D of the inputs and D2H of loss +
+                  gradient inside the timed region; e2e_compact = same with uint8 relevance /
+                  int32 n (an extension of this package)
+  configs         (N = 1 only) the other BASELINE.json configurations measured in the same run:
+                  ns (4096, 1024) north-star point, c2, c3, c4, c4m, c4a, c4d -- ms_per_step,
+                  kernel_ms, HBM frac, issue frac, parity spot check
+  clocks          SM clock / throttle reasons sampled during the timed region
+`--impl reference` times the reference's CPU implementation of the same workload on the host cores:
+the unmodified Python reference from baseline/_ref when present ("kind": "reference"), else the C
+oracle port ("kind": "port"); each step is a bounded sample of the workload's batch.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -36,8 +50,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 L2_BYTES = 126 * 1024 * 1024
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
-# name -> (loss, B per GPU, L, relevance distribution)
+# name -> workload
 CONFIGS = {
     "c2": dict(loss="LambdaNDCGLoss2", B=4096, L=128, workload="LambdaNDCGLoss2 synthetic (B=4096, L=128) fp32"),
     "c3": dict(loss="PairwiseDCGHingeLoss", B=1024, L=1024,
@@ -64,19 +79,27 @@ CONFIGS = {
     "c4d": dict(metric="dcg", k=None, B=8192, L=200, skew=True,
                 workload="dcg at every rank synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
 }
+DEFAULT_SUB = "ns,c2,c3,c4,c4m,c4a,c4d"
 ORACLE_MODE = {"LambdaNDCGLoss2": ("lambda", "ndcg2"), "LambdaNDCGLoss1": ("lambda", "ndcg1"),
                "LambdaARPLoss1": ("lambda", "arp1"), "LambdaARPLoss2": ("lambda", "arp2"),
                "PairwiseHingeLoss": ("additive", "hinge"), "PairwiseDCGHingeLoss": ("additive", "dcg_hinge"),
                "PairwiseLogisticLoss": ("additive", "logistic"), "ListNetLoss": ("listnet", None)}
+# MUFU instructions the shipped kernels spend per unordered pair of a sigmoid-weighted loss
+# (lg2 of every pair + one rcp per TWO pairs)
+MUFU_PER_PAIR = 1.5
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
+    ap.add_argument("--sub", default=DEFAULT_SUB,
+                    help="comma list of other configs measured in the same run at N = 1 ('' = none)")
+    ap.add_argument("--no-sub", action="store_true")
+    ap.add_argument("--windows", type=int, default=5, help="extra K-step windows for best / median")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -102,6 +125,13 @@ def metric_name(cfg):
     return "loss fwd+bwd queries/sec" if "loss" in cfg else "ranking metric queries/sec"
 
 
+def config_block(cfg, world):
+    """Names the workload; identical in both arms (`--impl ours` / `--impl reference`)."""
+    return {"workload": cfg["workload"], "loss": cfg.get("loss", cfg.get("metric")), "B": cfg["B"], "L": cfg["L"],
+            "n_distribution": "n ~ U[L/2, L]", "sigma": 1.0,
+            "parallelism": f"query-sharded dp{world}"}
+
+
 def valid_pairs(n):
     import numpy as np
     n = np.asarray(n, dtype=np.float64)
@@ -121,66 +151,282 @@ def oracle_step(oracle, family, mode, cfg, s, y, n):
     return oracle.dcg(s, y, n, k=cfg.get("k"), normalized=mode == "ndcg"), None
 
 
+def family_mode(cfg):
+    return ORACLE_MODE[cfg["loss"]] if "loss" in cfg else ("metric", cfg["metric"])
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def mufu_peak():
+    """Measured MUFU lane-operations per second of one B200 (tools/issue_peak.cu)."""
+    path = os.path.join(ROOT, "profiles", "issue_peaks.json")
+    if os.path.exists(path):
+        try:
+            st = json.load(open(path))["streams"]
+            rate = max(float(st[k]["per_s"]) for k in ("mufu_lg2", "mufu_ex2", "mufu_rcp_lg2") if k in st)
+            return rate, "profiles/issue_peaks.json (tools/issue_peak.cu: measured MUFU lane-ops/s)"
+        except Exception:  # pragma: no cover
+            pass
+    return 148 * 1.965e9 * 16, "derived: 148 SMs x 1965 MHz x 16 MUFU lanes/clk (no measurement found)"
+
+
+# --------------------------------------------------------------------------- the real reference
+def import_reference():
+    """The unmodified reference installed into git-ignored baseline/_ref (pip --target), or None."""
+    if not os.path.isdir(os.path.join(REF_DIR, "pytorchltr")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import pytorchltr  # noqa: F401
+        import pytorchltr.evaluation
+        import pytorchltr.loss
+        return pytorchltr
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write(f"[bench] baseline/_ref present but not importable: {e!r}\n")
+        return None
+
+
+def reference_callable(ref, cfg):
+    """(callable(scores, relevance, n), is_loss) of the reference for this workload, or (None, _)."""
+    if "metric" in cfg:
+        if cfg["metric"] == "arp":
+            return (lambda s, y, n: ref.evaluation.arp(s, y, n)), False
+        fn, k = getattr(ref.evaluation, cfg["metric"]), cfg.get("k")
+        return (lambda s, y, n: fn(s, y, n, k=k)), False
+    if not hasattr(ref.loss, cfg["loss"]):
+        return None, True                     # ListNet: absent from the reference (SURVEY.md F2)
+    return getattr(ref.loss, cfg["loss"])(), True
+
+
+def time_python_reference(ref, cfg, device, chunk, n_chunks, warm=1):
+    """Seconds per chunk (median) of `fn(s, y, n).mean().backward()` of the unmodified reference."""
+    import torch
+    fn, is_loss = reference_callable(ref, cfg)
+    if fn is None:
+        return None
+    s_np, y_np, n_np = make_batch_numpy(1235, chunk, cfg["L"], cfg.get("skew", False))
+    s = torch.from_numpy(s_np).to(device).requires_grad_(is_loss)
+    y, n = torch.from_numpy(y_np).to(device), torch.from_numpy(n_np).to(device)
+
+    def step():
+        if is_loss:
+            s.grad = None
+            fn(s, y, n).mean().backward()
+        else:
+            fn(s, y, n)
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step()
+    times = []
+    for _ in range(n_chunks):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def committed_reference_timing(name):
+    path = os.path.join(ROOT, "profiles", "reference_timing.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        doc = json.load(open(path))
+        e = doc["configs"].get(name)
+        if e is None:
+            return None
+        return {"source": "profiles/reference_timing.json (tools/time_reference.py on a gpurun B200 box; "
+                          "baseline/_ref absent in this run)",
+                "cpu_cores": doc.get("cpu_cores"),
+                "cpu_queries_per_s": (e.get("cpu") or {}).get("queries_per_s"),
+                "cpu_chunk": (e.get("cpu") or {}).get("chunk"),
+                "gpu_eager_queries_per_s": (e.get("gpu_eager") or {}).get("queries_per_s"),
+                "gpu_eager_chunk": (e.get("gpu_eager") or {}).get("chunk")}
+    except Exception:  # pragma: no cover
+        return None
+
+
+def pair_chunk(cfg, budget_bytes):
+    """Queries per call of the reference that keep its ~78 L^2 B/query of pair tensors in budget."""
+    L = cfg["L"]
+    pair = "metric" not in cfg and cfg["loss"] != "ListNetLoss"
+    per_q = 82e6 * (L / 1024.0) ** 2 if pair else 64.0 * L
+    return int(max(8, min(cfg["B"], budget_bytes // per_q)))
+
+
 # --------------------------------------------------------------------------- reference arm
-def run_reference(args, cfg, rank, world):
-    """CPU oracle port of the reference algorithm, all host threads, bounded sample per step."""
+def run_reference(args, name, cfg, rank, world):
+    """The reference's own CPU implementation of the workload on the host cores, all threads:
+    the unmodified Python reference when baseline/_ref is present, else the C oracle port.
+    EXACTLY --steps timed steps after --warmup; a step is a bounded sample of the batch."""
     if rank != 0:
         return
     import numpy as np
     import oracle
     oracle.build()
-    oracle.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: use every host core
-    threads = oracle.max_threads()
-    family, mode = ORACLE_MODE[cfg["loss"]] if "loss" in cfg else ("metric", cfg["metric"])
+    cores = os.cpu_count() or 1
+    oracle.set_threads(cores)   # torchrun exports OMP_NUM_THREADS=1: use every host core
+    family, mode = family_mode(cfg)
     L = cfg["L"]
-    # bounded sample: a slice of the workload's batch sized for ~1 s per step
-    probe_B = 64
-    s, y, n = make_batch_numpy(1234, probe_B, L, cfg.get("skew", False))
     fused_F = cfg.get("F") if cfg.get("fused") else None
+    total_budget_s = 90.0
+    n_steps = args.steps + args.warmup
+
+    # ---- the C port (always measured: continuity with round 1, and the fallback arm) --------
     rng = np.random.default_rng(7)
     fused_w = rng.standard_normal(fused_F or 1).astype(np.float32) * 0.1
+    feat_cache = {}
 
-    def step(s, y, n):
+    def port_step(s, y, n):
         if fused_F:
-            # scorer + ListNet + weight gradient (numpy float64 port; features drawn once per size)
             key = len(n)
-            if key not in step.feat:
-                step.feat[key] = rng.standard_normal((key, L, fused_F), dtype=np.float32)
-            return oracle.linear_listnet(step.feat[key], fused_w, None, y, n)
+            if key not in feat_cache:
+                feat_cache[key] = rng.standard_normal((key, L, fused_F), dtype=np.float32)
+            return oracle.linear_listnet(feat_cache[key], fused_w, None, y, n)
         return oracle_step(oracle, family, mode, cfg, s, y, n)
 
-    step.feat = {}
+    s, y, n = make_batch_numpy(1234, 64, L, cfg.get("skew", False))
+    port_step(s, y, n)
+    t0 = time.perf_counter()
+    port_step(s, y, n)
+    port_per_q = (time.perf_counter() - t0) / 64
 
-    step(s, y, n)
+    ref = None if fused_F else import_reference()
+    fn = reference_callable(ref, cfg)[0] if ref is not None else None
+    if fn is not None:
+        import torch
+        torch.set_num_threads(cores)
+        kind = "reference"
+        probe = pair_chunk(cfg, 1e9)
+        t = time_python_reference(ref, cfg, torch.device("cpu"), probe, 1, warm=1)
+        per_q = t[0] / probe
+        sample_B = int(max(8, min(cfg["B"], pair_chunk(cfg, 8e9), (total_budget_s / n_steps) / max(per_q, 1e-9))))
+        s_np, y_np, n_np = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
+        ts = torch.from_numpy(s_np).requires_grad_("loss" in cfg)
+        ty, tn = torch.from_numpy(y_np), torch.from_numpy(n_np)
+        is_loss = "loss" in cfg
+
+        def step():
+            if is_loss:
+                ts.grad = None
+                fn(ts, ty, tn).mean().backward()
+            else:
+                fn(ts, ty, tn)
+
+        threads = torch.get_num_threads()
+        what = (f"unmodified rjagerman/pytorchltr from baseline/_ref on CPU, torch {torch.__version__}, "
+                f"{threads} threads: loss_fn(scores, relevance, n).mean().backward()")
+        dtype = "f32"
+    else:
+        kind = "port"
+        sample_B = int(max(cores * 8, min(cfg["B"], (total_budget_s / n_steps) / max(port_per_q, 1e-9))))
+        s, y, n = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
+
+        def step():
+            port_step(s, y, n)
+
+        threads = oracle.max_threads()
+        what = ("oracle.linear_listnet (numpy float64 port of Linear + ListNet + weight gradient, BLAS threads)"
+                if fused_F else "oracle/ltr_oracle.c (C port of the reference algorithm, OpenMP over queries); "
+                                "baseline/_ref (the Python reference) is absent in this run")
+        dtype = "f64"
+    for _ in range(args.warmup):
+        step()
     t0 = time.perf_counter()
-    step(s, y, n)
-    per_q = (time.perf_counter() - t0) / probe_B
-    sample_B = int(max(threads * 8, min(cfg["B"], 1.0 / max(per_q, 1e-9))))
-    s, y, n = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
-    for _ in range(min(args.warmup, 3)):
-        step(s, y, n)
-    steps = max(1, min(args.steps, 30))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step(s, y, n)
+    for _ in range(args.steps):
+        step()
     dt = time.perf_counter() - t0
-    qps = sample_B * steps / dt
-    sample = (f"{sample_B} of the {cfg['B']} queries of one batch per step, {steps} steps; " +
-              ("oracle.linear_listnet (numpy float64 port of Linear + ListNet + weight gradient, BLAS threads)"
-               if fused_F else "oracle/ltr_oracle.c (C port of the reference algorithm, OpenMP over queries)"))
+    qps = sample_B * args.steps / dt
+    sample = f"{sample_B} of the {cfg['B']} queries of one batch per step, {args.steps} steps; {what}"
     line = {
         "impl": "reference", "metric": metric_name(cfg), "value": qps, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
-        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "loss": cfg.get("loss", cfg.get("metric")),
-                   "B_per_step": sample_B, "L": L},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": sample},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if cfg.get("strong") else "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": config_block(cfg, world),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind, "sample": sample,
+                         "c_port_queries_per_s": 1.0 / port_per_q,
+                         "c_port_note": "oracle/ltr_oracle.c with OpenMP on a 64-query probe (never builds the "
+                                        "(B, L, L, 2) pair tensors: a stronger baseline than the reference itself)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every ~20 ms (NVML)."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, torch_device_index):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.nv = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append(mhz)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+
+    def summary(self, window):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "window": "unavailable: " + getattr(self, "err", "no samples")}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "window": window}
 
 
 # --------------------------------------------------------------------------- fused scorer + loss
@@ -209,7 +455,6 @@ def run_fused(args, cfg, rank, local_rank, world):
     plain = torch.nn.Linear(F, 1).to(dev)
     plain.load_state_dict(model.linear.state_dict())
     plain_loss = ListNetLoss()
-    red = torch.zeros(2, device=dev)
 
     def step():
         model.zero_grad(set_to_none=True)
@@ -297,11 +542,7 @@ def run_fused(args, cfg, rank, local_rank, world):
     kernel_ms = timed(kernel_only, k_reps, 3) / k_reps
     backward_ms = timed(backward_only, k_reps, 3) / k_reps
     alg_bytes = B * (4 * L * F + 12 * L + 12 + 4 * (F + 1))   # + the per-query gradient row
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6548.2, "fallback: B200_PROFILING.md measured copy bandwidth"
+    peak, peak_src = hbm_peak()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -373,17 +614,18 @@ def run_fused(args, cfg, rank, local_rank, world):
                "path": f"LinearListNet on {hB} queries per step from pinned host memory: H2D of features / "
                        "relevance / n, fused kernel, D2H of the loss and the weight gradient"}
     if rank == 0:
+        cb = config_block(cfg, world)
+        cb.update({"F": F, "loss": "LinearListNet"})
         line = {
             "metric": "loss fwd+bwd queries/sec", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "loss": "LinearListNet", "B_per_gpu": B, "L": L, "F": F,
-                       "global_batch": B * world, "parallelism": f"query-sharded dp{world}", "launch": launch,
-                       "l2_policy": "inputs larger than L2: one 891 MB feature batch per step",
-                       "n_distribution": "n ~ U[L/2, L]",
-                       "unfused_ms_per_step": unfused_ms,
-                       "unfused_path": "ListNetLoss()(torch.nn.Linear(F, 1)(xs), ys, n).mean().backward(): "
-                                       "two passes over the features (cuBLAS) + ltr_listnet"},
+            "config": cb,
+            "details": {"B_per_gpu": B, "global_batch": B * world, "launch": launch,
+                        "l2_policy": "inputs larger than L2: one 891 MB feature batch per step",
+                        "unfused_ms_per_step": unfused_ms,
+                        "unfused_path": "ListNetLoss()(torch.nn.Linear(F, 1)(xs), ys, n).mean().backward(): "
+                                        "two passes over the features (cuBLAS) + ltr_listnet"},
             "roofline": {"bound": "hbm", "kernel": "linear_listnet_kernel (ltr_linear_listnet)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel_ms": kernel_ms, "backward_ms": backward_ms,
@@ -401,100 +643,29 @@ def run_fused(args, cfg, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-# --------------------------------------------------------------------------- clocks
-class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU every ~20 ms (NVML)."""
-
-    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
-               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
-               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
-
-    def __init__(self, torch_device_index):
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
-        self._stop = threading.Event()
-        self._thread = None
-        self.ok = False
-        try:
-            import pynvml
-            import torch
-            pynvml.nvmlInit()
-            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
-            if not uuid.startswith("GPU-"):
-                uuid = "GPU-" + uuid
-            try:
-                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
-            except Exception:
-                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
-            self.nv = pynvml
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
-        except Exception as e:  # pragma: no cover
-            self.err = repr(e)
-
-    def _loop(self):
-        nv = self.nv
-        while not self._stop.is_set():
-            try:
-                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append(mhz)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.02)
-
-    def start(self):
-        if self.ok:
-            self._thread = threading.Thread(target=self._loop, daemon=True)
-            self._thread.start()
-
-    def stop(self):
-        if self._thread is not None:
-            self._stop.set()
-            self._thread.join()
-
-    def summary(self, window):
-        if not self.ok or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
-                    "window": "unavailable: " + getattr(self, "err", "no samples")}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples), "window": window}
-
-
-# --------------------------------------------------------------------------- our arm
-def run_ours(args, cfg, rank, local_rank, world):
+# --------------------------------------------------------------------------- one workload on the device
+def measure_config(args, name, cfg, rank, world, dev, steps, warmup, windows, sampler=None):
+    """Device-resident measurement of one workload: the step through the public API (CUDA graph per
+    resident batch), K timed steps + extra windows, the dominant kernel alone, a parity spot check.
+    Returns a dict; `ms` is this rank's time for the K steps (the caller takes the max over ranks)."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import pytorchltr_b200.evaluation as ltr_eval
     import pytorchltr_b200.loss as ltr_loss
-    from pytorchltr_b200 import _lib, _ops
-    from pytorchltr_b200.distributed import shard_bounds
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    from pytorchltr_b200 import _lib
+    from pytorchltr_b200.distributed import global_sum_count, shard_bounds, sharded_mean_loss
 
     L = cfg["L"]
     if cfg.get("strong"):
         lo, hi = shard_bounds(cfg["B"], rank, world)
         B = hi - lo
-        scaling = "strong"
     else:
         B = cfg["B"]
-        scaling = "weak"
     is_metric = "metric" in cfg
+    family, mode = family_mode(cfg)
     if is_metric:
-        family, mode = "metric", cfg["metric"]
         if mode == "arp":
             loss_fn = ltr_eval.arp
         else:
@@ -502,12 +673,10 @@ def run_ours(args, cfg, rank, local_rank, world):
             loss_fn = lambda s, y, n: _fn(s, y, n, k=_k)  # noqa: E731
     else:
         loss_fn = getattr(ltr_loss, cfg["loss"])()
-        family, mode = ORACLE_MODE[cfg["loss"]]
 
     # ---- resident pool of distinct batches, larger than L2 ---------------------------------
     in_bytes = B * L * 12 + B * 8
-    pool_n = max(4, -(-2 * L2_BYTES // in_bytes))
-    pool_n = min(pool_n, 64)
+    pool_n = min(64, max(4, -(-2 * L2_BYTES // in_bytes)))
     pool, pairs_per_batch = [], []
     for i in range(pool_n):
         s, y, n = make_batch_numpy(1234 + 1000 * rank + i, B, L, cfg.get("skew", False))
@@ -516,37 +685,28 @@ def run_ours(args, cfg, rank, local_rank, world):
                      torch.from_numpy(n).to(dev)))
     pool_bytes = pool_n * in_bytes
     torch.cuda.synchronize()
-
-    # N > 1: the path's only exchange is the 2-element [sum loss, #queries] all-reduce behind the
-    # global mean.  Its input is produced inside the (graph-captured) step; the collective itself
-    # is enqueued after the step, asynchronously, so it overlaps the next step's kernels.
-    red = [torch.tensor([0.0, float(B)], device=dev) for _ in range(pool_n)] if world > 1 else None
-    pending = []
-
-    metric_out = [None] * pool_n
+    outs = [None] * pool_n
 
     def step(i):
         s, y, n = pool[i % pool_n]
         if is_metric:
             out = loss_fn(s, y, n)
-            metric_out[i % pool_n] = out
+            if world > 1:
+                global_sum_count(out)      # [sum metric, #queries] all-reduce behind the global mean
         else:
             s.grad = None
-            out = loss_fn(s, y, n)
-        if world > 1:
-            r = red[i % pool_n]
-            torch.sum(out.detach(), dim=0, keepdim=True, out=r[:1])   # r[1] (the count) is constant
-        if not is_metric:
-            out.sum().backward()
+            if world > 1:
+                # the path's only exchange: the loss kernel's epilogue leaves the local sum on the
+                # device, the 2-element all-reduce follows inside the same captured step
+                out = sharded_mean_loss(loss_fn, s, y, n)
+                out.backward()
+            else:
+                out = loss_fn(s, y, n)
+                out.mean().backward()
+        outs[i % pool_n] = out
         return out
 
-    def exchange(i):
-        if world > 1:
-            pending.append(dist.all_reduce(red[i % pool_n], async_op=True))
-            if len(pending) > 8:
-                pending.pop(0).wait()
-
-    # ---- CUDA graphs: one per pool entry (launch-bound otherwise: ~25 us of GPU work/step) ---
+    # ---- CUDA graphs: one per pool entry --------------------------------------------------
     graphs = None
     launch = "eager"
     if not args.no_graph:
@@ -565,82 +725,83 @@ def run_ours(args, cfg, rank, local_rank, world):
                 with torch.cuda.graph(g):
                     step(i)
                 graphs.append(g)
-            launch = "cuda_graph"
+            launch = "cuda_graph (collective captured)" if world > 1 else "cuda_graph"
         except Exception as e:  # pragma: no cover
             sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); falling back to eager\n")
             graphs = None
             torch.cuda.synchronize()
 
-    def run_step(i, collective=True):
+    def run_step(i):
         if graphs is not None:
             graphs[i % pool_n].replay()
         else:
             step(i)
-        if collective:
-            exchange(i)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    def window(first, count):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(count):
+            run_step(first + i)
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    for i in range(warmup):
         run_step(i)
     barrier()
+    if sampler is not None:
+        sampler.start()
+    ms = window(warmup, steps)                       # the contract's K timed steps
+    extra = [window(warmup + (w + 1) * steps, steps) / steps for w in range(max(0, windows))]
+    clock_window = "timed region + %d more windows of the same load" % len(extra)
+    if sampler is not None:
+        # keep the same load running until NVML has a few samples; the decision and the step count are
+        # made collective, because every replay carries a collective at N > 1
+        need = torch.tensor([1.0 if len(sampler.samples) < 5 else 0.0, ms / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(need, op=dist.ReduceOp.MAX)
+        if float(need[0]) > 0:
+            n_more = max(1, int(0.5 / max(float(need[1]) * 1e-3, 1e-6)))
+            for i in range(n_more):
+                run_step(i)
+                if i % 64 == 63:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            clock_window += " + ~0.5 s more"
+        sampler.stop()
+    all_ms = [ms / steps] + extra
+    win = {"n": len(all_ms), "steps_each": steps, "best_ms_per_step": min(all_ms),
+           "median_ms_per_step": statistics.median(all_ms), "max_ms_per_step": max(all_ms),
+           "scope": "this rank's CUDA events (rank 0)"}
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        run_step(args.warmup + i)
-    while pending:
-        pending.pop(0).wait()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    clock_window = "timed region"
-    if len(sampler.samples) < 5:
-        # the timed region was shorter than a few NVML periods: keep the same load running
-        t_end = time.perf_counter() + 0.5
-        i = 0
-        while time.perf_counter() < t_end:
-            run_step(i, collective=False)   # time-bounded: ranks may differ in step count
-            i += 1
-            if i % 64 == 0:
-                torch.cuda.synchronize()
-        while pending:
-            pending.pop(0).wait()
-        torch.cuda.synchronize()
-        clock_window = "timed region + 0.5 s of the same load"
-    sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    total_queries = B * world if not cfg.get("strong") else cfg["B"]
-    value = total_queries * args.steps / (ms * 1e-3)
-
-    # parity spot check of the timed path (not timed): last batch vs the oracle on a sample
+    # ---- parity spot check of the timed path (not timed): batch 0 vs the oracle on a sample ---
     parity = None
+    run_step(0)                                      # every rank: the captured collective must match
+    torch.cuda.synchronize()
     if rank == 0:
         import oracle
         s, y, n = pool[0]
         idx = np.arange(0, B, max(1, B // 16))
-        run_step(0, collective=False)   # rank 0 only: must not enqueue an unmatched collective
-        torch.cuda.synchronize()
         sn, yn, nn = s.detach().cpu().numpy()[idx], y.cpu().numpy()[idx], n.cpu().numpy()[idx]
         # (hinge: float32 restatement -- pairs on the kink flip between f32 and f64 rounding)
         rl, rg = oracle_step(oracle, family, mode, cfg, sn, yn, nn)
         if is_metric:
-            got = metric_out[0].detach().cpu().double().numpy()[idx]
+            got = outs[0].detach().cpu().double().numpy()[idx]
             err = float(np.abs(got - rl).max())
             parity = {"max_abs_err": err, "queries_checked": int(len(idx)), "ok": err <= 1e-5}
         else:
-            got = s.grad.detach().cpu().double().numpy()[idx]
+            # the step is the MEAN over all queries of all ranks: undo the 1 / B_global factor
+            got = s.grad.detach().cpu().double().numpy()[idx] * float(cfg["B"] if cfg.get("strong") else B * world)
             gerr = float((np.abs(got - rg) / (np.abs(rg).max(axis=1, keepdims=True) + 1e-30)).max())
             parity = {"max_grad_err_rel_to_rowmax": gerr, "queries_checked": int(len(idx)), "ok": gerr <= 1e-5}
+            if world > 1:
+                parity["global_mean_loss"] = float(outs[0].detach().cpu())
 
     # ---- dominant kernel alone: the fused loss + gradient kernel -----------------------------
     lib_family = {"lambda": _lib.FAMILY_LAMBDA, "additive": _lib.FAMILY_ADDITIVE,
@@ -659,7 +820,6 @@ def run_ours(args, cfg, rank, local_rank, world):
     st = torch.cuda.current_stream().cuda_stream
 
     def kernel_only(i):
-        nonlocal st
         s, y, n = pool[i % pool_n]
         # the _ws entry points are what the public modules call: the timed launch includes the
         # small query-ordering kernel that precedes the fused kernel
@@ -679,10 +839,11 @@ def run_ours(args, cfg, rank, local_rank, world):
                                       min(metric_k, L), 1, metric_buf.data_ptr(), metric_ld, st)
         _lib.check(rc)
 
-    for i in range(8):
+    for i in range(min(8, pool_n)):
         kernel_only(i)
     torch.cuda.synchronize()
-    reps = max(1, min(20, 2000 // pool_n))
+    approx_ms = max(ms / steps, 1e-3)
+    reps = max(1, min(20, int(200.0 / (approx_ms * pool_n)) or 1))
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kgraph = None
     if not args.no_graph:
@@ -712,16 +873,13 @@ def run_ours(args, cfg, rank, local_rank, world):
     kernel_ms = k0.elapsed_time(k1) / (reps * pool_n)
     alg_bytes = B * (12 * L + 8 + 4 * metric_ld) if is_metric else B * (16 * L + 16)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"])
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    peak, peak_src = hbm_peak()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.config, {}).get("dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get(name, {}).get("dram_bytes_per_launch")
+        if traffic is not None and world > 1 and cfg.get("strong"):
+            traffic = traffic / world            # captured at N = 1: per-launch bytes scale with the shard
     roofline = {"bound": "hbm", "kernel": "ltr_rank_metrics kernel" if is_metric else
                 "fused loss+gradient kernel (ltr_lambda / ltr_pairwise_additive / ltr_listnet)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -730,109 +888,218 @@ def run_ours(args, cfg, rank, local_rank, world):
     issue = None
     if family not in ("listnet", "metric"):
         mean_pairs = sum(pairs_per_batch) / len(pairs_per_batch)
-        sm_hz = (sampler.max_mhz or 1965) * 1e6
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        # sigmoid losses: the tile kernels spend 2 MUFU (rcp, lg2) per unordered pair at 16 MUFU
-        # lanes / clk / SM (a naive evaluation needs 3: ex2, rcp, lg2); hinge: FP32 issue, ~6
-        # lane-ops per pair at 128 lanes / clk / SM
-        per_pair_clk = (6.0 / 128.0) if "Hinge" in cfg["loss"] else (2.0 / 16.0)
-        peak_pairs = sms * sm_hz / per_pair_clk
         ach_pairs = mean_pairs / (kernel_ms * 1e-3)
-        issue = {"bound": "mufu" if "Hinge" not in cfg["loss"] else "fp32_issue",
-                 "achieved": ach_pairs, "peak": peak_pairs, "unit": "unordered pairs/s",
-                 "frac": ach_pairs / peak_pairs, "pairs_per_launch": mean_pairs,
-                 "note": "binding roofline of the O(L^2) losses (SURVEY.md F4); peak derived from "
-                         "SM count x max SM clock x pipe width"}
-        if "Hinge" in cfg["loss"] and 128 < L <= 4096 and os.environ.get("LTR_HINGE") != "pairs" \
-                and os.environ.get("LTR_KERNEL") not in ("tiles", "generic"):
-            # the hinge losses no longer enumerate pairs at these sizes (sort + scans, O(n log n)):
-            # "achieved" is the pair rate an O(L^2) kernel would need to match it, not an issue rate
-            issue.update({"bound": "latency (O(n log n) sort + scans; pairs are not enumerated)",
-                          "frac": None, "equivalent_pair_rate_vs_fp32_issue_peak": ach_pairs / peak_pairs})
+        if "Hinge" in cfg["loss"]:
+            # hinge: FP32 issue, ~6 lane-ops per pair at 128 lanes / clk / SM (measured ~118, issue_peaks.json)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_pairs = sms * 1.965e9 * 128.0 / 6.0
+            issue = {"bound": "fp32_issue", "achieved": ach_pairs, "peak": peak_pairs, "unit": "unordered pairs/s",
+                     "frac": ach_pairs / peak_pairs, "pairs_per_launch": mean_pairs}
+            if 128 < L <= 4096 and os.environ.get("LTR_HINGE") != "pairs" \
+                    and os.environ.get("LTR_KERNEL") not in ("tiles", "generic"):
+                # the hinge losses do not enumerate pairs at these sizes (sort + scans, O(n log n)):
+                # "achieved" is the pair rate an O(L^2) kernel would need to match it, not an issue rate
+                issue.update({"bound": "latency (O(n log n) sort + scans; pairs are not enumerated)",
+                              "frac": None, "equivalent_pair_rate_vs_fp32_issue_peak": ach_pairs / peak_pairs})
+        else:
+            mufu_rate, mufu_src = mufu_peak()
+            peak_pairs = mufu_rate / MUFU_PER_PAIR
+            issue = {"bound": "mufu", "achieved": ach_pairs, "peak": peak_pairs, "unit": "unordered pairs/s",
+                     "frac": ach_pairs / peak_pairs, "pairs_per_launch": mean_pairs,
+                     "mufu_per_pair": MUFU_PER_PAIR, "mufu_lane_ops_per_s": mufu_rate, "peak_source": mufu_src,
+                     "frac_vs_2_mufu_per_pair": ach_pairs / (mufu_rate / 2.0),
+                     "note": "binding roofline of the O(L^2) losses (SURVEY.md F4): the kernel needs lg2 of every "
+                             "pair and one rcp per two pairs on the 16-lane/clk/SM MUFU pipe"}
+    launches_per_step = 1 if is_metric else (2 if family == "listnet" else 3)
+    return {"ms": ms, "B": B, "L": L, "launch": launch, "pool_n": pool_n, "pool_bytes": pool_bytes,
+            "windows": win, "parity": parity, "roofline": roofline, "issue": issue, "loss_fn": loss_fn,
+            "is_metric": is_metric, "family": family, "mode": mode, "metric_ld": metric_ld,
+            "launches_per_step": launches_per_step, "clock_window": clock_window}
 
-    # ---- e2e: public API, pinned host tensors in, host loss + gradient out -------------------
-    e2e = None
-    if not args.no_e2e:
-        host_n = 4
-        host_pool = []
-        for i in range(host_n):
-            s, y, n = make_batch_numpy(99 + 1000 * rank + i, B, L, cfg.get("skew", False))
-            host_pool.append((torch.from_numpy(s).pin_memory().requires_grad_(not is_metric),
-                              torch.from_numpy(y).pin_memory(), torch.from_numpy(n).pin_memory()))
 
-        def e2e_step(i):
-            s, y, n = host_pool[i % host_n]
-            if is_metric:
-                return loss_fn(s, y, n)     # H2D scores/relevance/n, kernel, D2H metric
-            s.grad = None
-            out = loss_fn(s, y, n)          # H2D scores/relevance/n, kernel, D2H loss
-            out.sum().backward()            # H2D g, scale kernel, D2H gradient
-            return out
+def run_e2e(cfg, m, rank, world, dev, steps, compact):
+    """Public API with pinned HOST tensors: H2D of scores / relevance / n, kernel, D2H of the loss and of
+    the gradient inside the timed region.  `compact`: uint8 relevance and int32 n (extension)."""
+    import torch
+    import torch.distributed as dist
+    B, L, is_metric, loss_fn = m["B"], m["L"], m["is_metric"], m["loss_fn"]
+    host_n = 2 if B * L > (1 << 24) else 4
+    host_pool = []
+    for i in range(host_n):
+        s, y, n = make_batch_numpy(99 + 1000 * rank + i, B, L, cfg.get("skew", False))
+        ty, tn = torch.from_numpy(y), torch.from_numpy(n)
+        if compact:
+            ty, tn = ty.to(torch.uint8), tn.to(torch.int32)
+        host_pool.append((torch.from_numpy(s).pin_memory().requires_grad_(not is_metric), ty.pin_memory(),
+                          tn.pin_memory()))
 
-        e_steps = max(5, min(args.steps, 100))
-        for i in range(3):
-            e2e_step(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e_steps):
-            e2e_step(i)
+    def e2e_step(i):
+        s, y, n = host_pool[i % host_n]
+        if is_metric:
+            return loss_fn(s, y, n)        # H2D scores/relevance/n, kernel, D2H metric
+        s.grad = None
+        out = loss_fn(s, y, n)             # H2D scores/relevance/n, kernel, D2H loss
+        out.mean().backward()              # device row scale by the broadcast 1/B, D2H gradient
+        return out
+
+    for i in range(3):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    total_queries = cfg["B"] if cfg.get("strong") else B * world
+    rel_b, n_b = (1, 4) if compact else (8, 8)
+    return {"value": total_queries * steps / dt, "unit": "queries/s",
+            "h2d_bytes_per_step": B * L * (4 + rel_b) + B * n_b,
+            "d2h_bytes_per_step": B * 4 * m["metric_ld"] if is_metric else B * 4 + B * L * 4,
+            "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "dtypes": "float32 scores, %s relevance, %s n" % (("uint8", "int32") if compact else ("int64", "int64")),
+            "path": "loss_fn(pinned CPU tensors).mean().backward(): loss and gradient returned as CPU tensors"
+                    if not is_metric else "metric(pinned CPU tensors): result returned as a CPU tensor"}
+
+
+def cpu_port_baseline(cfg, m):
+    import oracle
+    oracle.set_threads(os.cpu_count() or 1)
+    threads = oracle.max_threads()
+    B, L = m["B"], m["L"]
+    family, mode = m["family"], m["mode"]
+    s, y, n = make_batch_numpy(1234, min(B, 64), L, cfg.get("skew", False))
+    oracle_step(oracle, family, mode, cfg, s, y, n)
+    t0 = time.perf_counter()
+    oracle_step(oracle, family, mode, cfg, s, y, n)
+    per_q = (time.perf_counter() - t0) / len(n)
+    sample_B = int(max(threads * 8, min(4 * B, 8.0 / max(per_q, 1e-9))))
+    s, y, n = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
+    t0 = time.perf_counter()
+    oracle_step(oracle, family, mode, cfg, s, y, n)
+    dt = time.perf_counter() - t0
+    return {"value": sample_B / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_B} queries of the same synthetic workload in one call "
+                      f"({dt:.1f} s wall), oracle/ltr_oracle.c with OpenMP over queries"}
+
+
+def python_reference_baseline(name, cfg, dev):
+    """The unmodified Python reference on the host cores and eager on this GPU: live when baseline/_ref
+    is present, else the committed measurement."""
+    ref = import_reference()
+    if ref is None or reference_callable(ref, cfg)[0] is None:
+        return committed_reference_timing(name)
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {"source": "live: unmodified rjagerman/pytorchltr from baseline/_ref, "
+                     "loss_fn(scores, relevance, n).mean().backward()",
+           "cpu_cores": os.cpu_count()}
+    chunk = pair_chunk(cfg, 4e9)
+    t = time_python_reference(ref, cfg, torch.device("cpu"), chunk, 3)
+    out.update({"cpu_queries_per_s": chunk / statistics.median(t), "cpu_chunk": chunk})
+    try:
+        gchunk = pair_chunk(cfg, 40e9)
+        t = time_python_reference(ref, cfg, dev, gchunk, 5)
+        out.update({"gpu_eager_queries_per_s": gchunk / statistics.median(t), "gpu_eager_chunk": gchunk})
+    except Exception as e:  # pragma: no cover
+        out["gpu_eager_unavailable"] = repr(e)[:200]
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, name, cfg, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(2, device=dev))          # communicator set-up before any capture
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_queries * e_steps / dt, "unit": "queries/s",
-               "h2d_bytes_per_step": B * L * 12 + B * 8 + (0 if is_metric else B * 4),
-               "d2h_bytes_per_step": B * 4 * metric_ld if is_metric else B * 4 + B * L * 4,
-               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
-               "path": "loss_fn(pinned CPU tensors).sum().backward(): results returned as CPU tensors"}
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    m = measure_config(args, name, cfg, rank, world, dev, args.steps, args.warmup, args.windows, sampler)
+    ms = m["ms"]
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    B, L = m["B"], m["L"]
+    total_queries = cfg["B"] if cfg.get("strong") else B * world
+    value = total_queries * args.steps / (ms * 1e-3)
+
+    e2e = e2e_compact = None
+    if not args.no_e2e:
+        e_steps = max(5, min(args.steps, 100)) if B * L <= (1 << 24) else max(3, min(args.steps, 10))
+        e2e = run_e2e(cfg, m, rank, world, dev, e_steps, compact=False)
+        e2e_compact = run_e2e(cfg, m, rank, world, dev, e_steps, compact=True)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle
-        oracle.set_threads(os.cpu_count() or 1)
-        threads = oracle.max_threads()
-        s, y, n = make_batch_numpy(1234, min(B, 64), L, cfg.get("skew", False))
+        cpu_baseline = cpu_port_baseline(cfg, m)
+        cpu_baseline["python_reference"] = python_reference_baseline(name, cfg, dev)
 
-        def ostep(s, y, n):
-            oracle_step(oracle, family, mode, cfg, s, y, n)
-
-        ostep(s, y, n)
-        t0 = time.perf_counter()
-        ostep(s, y, n)
-        per_q = (time.perf_counter() - t0) / len(n)
-        sample_B = int(max(threads * 8, min(4 * B, 5.0 / max(per_q, 1e-9))))
-        s, y, n = make_batch_numpy(1235, sample_B, L, cfg.get("skew", False))
-        t0 = time.perf_counter()
-        ostep(s, y, n)
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": sample_B / dt, "unit": "queries/s", "cores": threads, "kind": "port",
-                        "sample": f"{sample_B} queries of the same synthetic workload in one call "
-                                  f"({dt:.1f} s wall), oracle/ltr_oracle.c with OpenMP over queries"}
+    # ---- the other BASELINE configurations, same run (N = 1 only) -----------------------------
+    sub = {}
+    if world == 1 and not args.no_sub and args.sub:
+        import gc
+        for sname in [x for x in args.sub.split(",") if x and x != name]:
+            scfg = CONFIGS[sname]
+            if scfg.get("fused"):
+                continue
+            m.pop("loss_fn", None)
+            gc.collect()
+            torch.cuda.empty_cache()
+            approx = {"ns": 0.9, "c3": 0.08, "c5": 4.0}.get(sname, 0.04)
+            s_steps = int(max(20, min(2000, 60.0 / approx)))
+            sm = measure_config(args, sname, scfg, 0, 1, dev, s_steps, max(3, s_steps // 10), 2)
+            entry = {"workload": scfg["workload"], "B": sm["B"], "L": sm["L"], "steps": s_steps,
+                     "ms_per_step": sm["ms"] / s_steps, "queries_per_s": sm["B"] * s_steps / (sm["ms"] * 1e-3),
+                     "windows": sm["windows"], "kernel_ms": sm["roofline"]["kernel_ms"],
+                     "hbm_frac": sm["roofline"]["frac"], "hbm_gbs": sm["roofline"]["achieved"],
+                     "issue_frac": (sm["issue"] or {}).get("frac"), "issue_bound": (sm["issue"] or {}).get("bound"),
+                     "pairs_per_s": (sm["issue"] or {}).get("achieved"),
+                     "parity_spot_check": sm["parity"], "launch": sm["launch"]}
+            if not args.no_e2e and sname in ("c2", "c4m"):
+                entry["e2e"] = run_e2e(scfg, sm, 0, 1, dev, 50, compact=False)
+                entry["e2e_compact"] = run_e2e(scfg, sm, 0, 1, dev, 50, compact=True)
+            if not args.no_cpu_baseline:
+                entry["python_reference"] = committed_reference_timing(sname)
+            sub[sname] = entry
 
     if rank == 0:
-        # fused kernel (+ backward row-scale kernel; + the query-ordering kernel of the O(L^2) losses)
-        launches_per_step = 1 if is_metric else (2 if family == "listnet" else 3)
         line = {
             "metric": metric_name(cfg), "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": cfg["workload"], "loss": cfg.get("loss", cfg.get("metric")), "B_per_gpu": B, "L": L,
-                       "global_batch": total_queries, "parallelism": f"query-sharded dp{world}",
-                       "launch": launch,
-                       "l2_policy": f"inputs larger than L2: {pool_n} distinct resident batches "
-                                    f"({pool_bytes / 2**20:.0f} MiB) visited round-robin",
-                       "n_distribution": "n ~ U[L/2, L]", "sigma": 1.0},
-            "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "clocks": sampler.summary(clock_window),
-            "gpu_launches": launches_per_step * args.steps,
+            "higher_is_better": True, "scaling": "strong" if cfg.get("strong") else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, world),
+            "details": {"B_per_gpu": B, "global_batch": total_queries, "launch": m["launch"],
+                        "step": "sharded_mean_loss(loss_fn, scores, relevance, n).backward() "
+                                "(2-element NCCL all-reduce inside the captured step)" if world > 1 and not m["is_metric"]
+                        else "loss_fn(scores, relevance, n).mean().backward()" if not m["is_metric"]
+                        else "metric(scores, relevance, n)",
+                        "l2_policy": f"inputs larger than L2: {m['pool_n']} distinct resident batches "
+                                     f"({m['pool_bytes'] / 2**20:.0f} MiB) visited round-robin"},
+            "windows": m["windows"],
+            "roofline": m["roofline"], "issue_roofline": m["issue"], "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "e2e_compact": e2e_compact,
+            "clocks": sampler.summary(m["clock_window"]),
+            "gpu_launches": m["launches_per_step"] * args.steps,
             "gpu_launches_note": "per step: 1 fused kernel (+ 1 row-scale kernel in the backward pass, + 1 "
                                  "query-ordering kernel before the O(L^2) losses when queries queue) of "
-                                 "libltr_sm100.so (plus torch's sum / ones_like fill)",
-            "parity_spot_check": parity,
+                                 "libltr_sm100.so (plus torch's mean / fill kernels and, for N > 1, NCCL's all-reduce)",
+            "parity_spot_check": m["parity"],
+            "configs": sub or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -847,7 +1114,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, cfg, rank, world)
+        run_reference(args, args.config, cfg, rank, world)
         return
     if world != args.gpus and rank == 0:
         sys.stderr.write(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun "
@@ -855,7 +1122,7 @@ def main():
     if cfg.get("fused"):
         run_fused(args, cfg, rank, local_rank, world)
         return
-    run_ours(args, cfg, rank, local_rank, world)
+    run_ours(args, args.config, cfg, rank, local_rank, world)
 
 
 if __name__ == "__main__":
