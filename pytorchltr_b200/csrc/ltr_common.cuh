@@ -149,6 +149,23 @@ __device__ __forceinline__ float cta_sum(float v, float* red) {
   return red[32];
 }
 
+// Minimum over the CTA; `red` is >= 33 floats of shared memory.  Result returned to all threads.
+__device__ __forceinline__ float cta_min(float v, float* red) {
+  v = -warp_max(-v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    float x = lane < nw ? red[lane] : INFINITY;
+    x = -warp_max(-x);
+    if (lane == 0) red[32] = x;
+  }
+  __syncthreads();
+  return red[32];
+}
+
 // gain of a relevance grade: 2^rel - 1 in float32 (pairwise_lambda.py:224-225, dcg.py:91-92)
 __device__ __forceinline__ float exp_gain_f32(int rel) {
   return exp2f(static_cast<float>(rel)) - 1.0f;

@@ -285,10 +285,23 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
     const float mid = 0.5f * (smax + smin);
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
     const int fill = Lp > L ? Lp : L;
+    // factored winner-by-relevance losses: padded columns carry the smallest valid (halved) weight (pair_fact)
+    float gpad = 0.0f;
+    if constexpr (tw_winner(TW)) {
+      if (factored && !(TW == TW_DELTA && m.hist[32] == 0)) {
+        float lmin = INFINITY;
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+          const int y = m.raw_y[j];
+          lmin = fminf(lmin, 0.5f * (TW == TW_DELTA ? gain_of_grade(y) * inv_max_dcg : static_cast<float>(y)));
+        }
+        gpad = cta_min(lmin, m.red);
+        if (!(gpad < INFINITY)) gpad = 0.0f;
+      }
+    }
     float diag = 0.0f;
     for (int p = threadIdx.x; p < fill; p += blockDim.x) {
       float fa = factored ? 0.0f : -1.0e30f, fb = 0.0f, fe = 0.0f;                // padding
-      float fg = TW == TW_HINGE ? -1.0e30f : 0.0f;
+      float fg = TW == TW_HINGE ? -1.0e30f : gpad;
       int d = p;
       if (p < L) {
         d = static_cast<int>(m.keys[p] & 0xffffffffu);
@@ -297,19 +310,16 @@ pair_cta_kernel(const float* __restrict__ scores, const void* __restrict__ rel, 
       if (p < nb) {
         const float s = m.raw_s[d];
         const int y = m.raw_y[d];
-        if constexpr (TW == TW_DELTA) fg = gain_of_grade(y) * inv_max_dcg;
-        else if (TW == TW_TWO && variant != 0) fg = gain_of_grade(y) * inv_max_dcg / tb.disc[p];
-        else fg = static_cast<float>(y);
-        if constexpr (TW == TW_TWO) diag += fg;   // the pairs (i, i): w_i * log2(1 + e^0)
+        float w;
+        if constexpr (TW == TW_DELTA) w = gain_of_grade(y) * inv_max_dcg;
+        else if (TW == TW_TWO && variant != 0) w = gain_of_grade(y) * inv_max_dcg / tb.disc[p];
+        else w = static_cast<float>(y);
+        if constexpr (TW == TW_TWO) diag += w;   // the pairs (i, i): w_i * log2(1 + e^0)
+        fg = w;
         if constexpr (TW == TW_HINGE) {
           fa = s;                                // raw score: the hinge works on s_i - s_j itself
         } else if (factored) {
-          const float c = s - mid;
-          const float eh = c * k_hi;
-          const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;
-          fe = eh;
-          fa = ex2_approx(-eh) * (1.0f - el);
-          fb = ex2_approx(eh) * (1.0f + el);
+          doc_factors<TW>(s, mid, k_hi, k_lo, w, fa, fb, fe, fg);
         } else {
           fa = sigma * s;
         }

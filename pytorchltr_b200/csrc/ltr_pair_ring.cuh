@@ -264,6 +264,49 @@ __device__ __forceinline__ void ring_step(const PairSoA& it, const float* __rest
   __syncwarp();
 }
 
+// Factored form of ring_step: packed pair math (chunk_pairs, ltr_pair_tiles.cuh), accumulators in RowAcc.
+template <int TW, bool FAST>
+__device__ __forceinline__ void ring_step_fact(const PairSoA& it, float* __restrict__ gw,
+                                               const float* __restrict__ symc, int c, bool active, int m, int C,
+                                               bool dup_step, const float (&ra)[4], const float (&re)[4],
+                                               const float (&rg)[4], const float (&rv)[4], RowAcc<4>& acc) {
+  int pc = c + m;
+  int sd = m;                                   // signed chunk distance column - row
+  if (pc >= C) { pc -= C; sd = m - C; }         // wrapped: the column ranks above the row
+  float4* g4 = reinterpret_cast<float4*>(gw) + pc;
+  float dwin[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if constexpr (TW == TW_DELTA) {
+    // rank distance of row r and column k: |4 sd + (k - r)|, slot k - r + 3
+    const float4* w4 = reinterpret_cast<const float4*>(symc + 4 * sd - 4);
+    const float4 w0 = w4[0], w1 = w4[1];
+    dwin[0] = w0.y; dwin[1] = w0.z; dwin[2] = w0.w;
+    dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w;
+  }
+  float cx[4], ce[4], cg[4];
+  load_cols<4, 4>(it.b, pc, cx);
+  load_cols<4, 4>(it.g, pc, cg);
+  load_cols<4, 4>(it.e, pc, ce);
+  if constexpr (FAST) {
+    const float4 gold = *g4;
+    float tc[4] = {gold.x, gold.y, gold.z, gold.w};
+    chunk_pairs<TW, 4>(ra, re, rg, rv, cx, ce, cg, dwin, acc, tc);
+    *g4 = make_float4(tc[0], tc[1], tc[2], tc[3]);
+  } else {
+    const bool commit = active && !(dup_step && sd < 0);
+    RowAcc<4> tmp;
+    tmp.clear();
+    float tc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    chunk_pairs<TW, 4>(ra, re, rg, rv, cx, ce, cg, dwin, tmp, tc);
+    if (commit) {
+      acc.add(tmp);
+      float4 gold = *g4;
+      gold.x += tc[0]; gold.y += tc[1]; gold.z += tc[2]; gold.w += tc[3];
+      *g4 = gold;
+    }
+  }
+  __syncwarp();
+}
+
 //   it    : rank-ordered factors, padded to 4 C entries
 //   gw    : THIS warp's private rank-order gradient array, zero on entry
 //   symc  : centre of the signed-distance delta table in shared memory (TW_DELTA)
@@ -327,6 +370,9 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
       }
       racc[r] = 0.0f;
     }
+    RowAcc<R> acc;          // factored form: packed accumulators of this run (racc / run_l: triangle only)
+    acc.clear();
+    float run_l = 0.0f;     // this run's loss in pair_fact units (the factored winner losses accumulate loss / 2)
     if (m0 == 0) {
       // ---- triangle inside the chunk (rank distance k - r > 0); replica 0 only ----------------------------
       float dwin[8];
@@ -334,26 +380,35 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
         const float4 w1 = *reinterpret_cast<const float4*>(symc);
         dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w;
         dwin[0] = dwin[1] = dwin[2] = dwin[7] = 0.0f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dwin[k] = 0.0f;
       }
-      float cx[R], ce[R], cg[R];
-      load_chunk<R>(colx, me * R, cx);
-      load_chunk<R>(it.g, me * R, cg);
-      if constexpr (FACTORED) load_chunk<R>(it.e, me * R, ce);
       float tl = 0.0f, tr[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) tr[r] = 0.0f;
+      if constexpr (FACTORED) {
+        float cx[4], ce[4], cg[4];
+        load_cols<R, 4>(it.b, me, cx);
+        load_cols<R, 4>(it.g, me, cg);
+        load_cols<R, 4>(it.e, me, ce);
+        chunk_triangle<TW, R>(ra, re, rg, rv, cx, ce, cg, dwin, tl, tr);
+      } else {
+        float cx[R], cg[R];
+        load_chunk<R>(colx, me * R, cx);
+        load_chunk<R>(it.g, me * R, cg);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < R; ++r) {
 #pragma unroll
-        for (int k = r + 1; k < R; ++k) {
-          float dw = rv[r];
-          if constexpr (TW == TW_DELTA) dw = dwin[k - r + R - 1];
-          pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[k], FACTORED ? ce[k] : 0.0f, cg[k], dw, tl, tr[r],
-                                  tr[k]);
+          for (int k = r + 1; k < R; ++k) {
+            float dw = rv[r];
+            if constexpr (TW == TW_DELTA) dw = dwin[k - r + R - 1];
+            pair_once<TW, false>(ra[r], re[r], rg[r], cx[k], 0.0f, cg[k], dw, tl, tr[r], tr[k]);
+          }
         }
       }
       if (active && sub == 0) {
-        lacc += tl;
+        run_l += tl;
 #pragma unroll
         for (int r = 0; r < R; ++r) racc[r] += tr[r];
       }
@@ -363,16 +418,24 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
       // even ring: the last step meets chunk c + C/2 from both ends; only the unwrapped end commits
       const int m_plain = (even && m1 == M + 1) ? M : m1;
       const int m_fast = full ? m_plain : m0;
-      for (int m = m0; m < m_fast; ++m)
-        ring_step<TW, FACTORED, true>(it, colx, gw, symc, c, true, m, C, false, ra, re, rg, rv, racc, lacc);
-      for (int m = max(m0, m_fast); m < m1; ++m)
-        ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, active, m, C, even && m == M, ra, re, rg, rv, racc,
-                                       lacc);
+      if constexpr (FACTORED) {
+        for (int m = m0; m < m_fast; ++m)
+          ring_step_fact<TW, true>(it, gw, symc, c, true, m, C, false, ra, re, rg, rv, acc);
+        for (int m = max(m0, m_fast); m < m1; ++m)
+          ring_step_fact<TW, false>(it, gw, symc, me, active, m, C, even && m == M, ra, re, rg, rv, acc);
+      } else {
+        for (int m = m0; m < m_fast; ++m)
+          ring_step<TW, FACTORED, true>(it, colx, gw, symc, c, true, m, C, false, ra, re, rg, rv, racc, run_l);
+        for (int m = max(m0, m_fast); m < m1; ++m)
+          ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, active, m, C, even && m == M, ra, re, rg, rv, racc,
+                                         run_l);
+      }
       // ---- flush the rows ----------------------------------------------------------------------------------
       if (active) {
         float4* g4 = reinterpret_cast<float4*>(gw) + c;
         float4 t = *g4;
-        t.x += racc[0]; t.y += racc[1]; t.z += racc[2]; t.w += racc[3];
+        t.x += racc[0] + acc.row(0); t.y += racc[1] + acc.row(1);
+        t.z += racc[2] + acc.row(2); t.w += racc[3] + acc.row(3);
         *g4 = t;
       }
       __syncwarp();
@@ -381,20 +444,25 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
       for (int t = m0; t < m1; ++t) {
         const int m = sub * T + t;
         const bool on = active && m >= 1 && m <= M;
-        ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, on, on ? m : 1, C, even && m == M, ra, re, rg, rv,
-                                       racc, lacc);
+        if constexpr (FACTORED)
+          ring_step_fact<TW, false>(it, gw, symc, me, on, on ? m : 1, C, even && m == M, ra, re, rg, rv, acc);
+        else
+          ring_step<TW, FACTORED, false>(it, colx, gw, symc, me, on, on ? m : 1, C, even && m == M, ra, re, rg, rv,
+                                         racc, run_l);
       }
       // the f replicas of a chunk add their row sums one after the other
       for (int s = 0; s < f; ++s) {
         if (active && sub == s) {
           float4* g4 = reinterpret_cast<float4*>(gw) + c;
           float4 tt = *g4;
-          tt.x += racc[0]; tt.y += racc[1]; tt.z += racc[2]; tt.w += racc[3];
+          tt.x += racc[0] + acc.row(0); tt.y += racc[1] + acc.row(1);
+          tt.z += racc[2] + acc.row(2); tt.w += racc[3] + acc.row(3);
           *g4 = tt;
         }
         __syncwarp();
       }
     }
+    lacc += (FACTORED && tw_winner(TW) ? 2.0f : 1.0f) * (run_l + acc.loss());
   }
   return lacc;
 }
@@ -593,10 +661,24 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
     const float mid = 0.5f * (smax + smin);
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
+    // factored winner-by-relevance losses: padded columns carry the smallest valid (halved) weight, so that
+    // they lose every pair (pair_fact).  Grades 0..31 give gains >= 0: the padding value 0 is small enough.
+    float gpad = 0.0f;
+    if constexpr (tw_winner(TW)) {
+      if (factored && !(TW == TW_DELTA && m.hist[32] == 0)) {
+        float lmin = INFINITY;
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+          const int y = m.raw_y[j];
+          lmin = fminf(lmin, 0.5f * (TW == TW_DELTA ? gain_of_grade(y) * inv_max_dcg : static_cast<float>(y)));
+        }
+        gpad = cta_min(lmin, m.red);
+        if (!(gpad < INFINITY)) gpad = 0.0f;
+      }
+    }
     float diag = 0.0f;
     for (int p = threadIdx.x; p < Lp; p += blockDim.x) {
       float fa = factored ? 0.0f : -1.0e30f, fb = 0.0f, fe = 0.0f;                // padding
-      float fg = TW == TW_HINGE ? -1.0e30f : 0.0f;
+      float fg = TW == TW_HINGE ? -1.0e30f : gpad;
       int d = p;
       if (p < L) {
         d = static_cast<int>(m.keys[p] & 0xffffffffu);
@@ -605,19 +687,16 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       if (p < nb) {
         const float s = m.raw_s[d];
         const int y = m.raw_y[d];
-        if constexpr (TW == TW_DELTA) fg = gain_of_grade(y) * inv_max_dcg;
-        else if (TW == TW_TWO && variant != 0) fg = gain_of_grade(y) * inv_max_dcg / tb.disc[p];
-        else fg = static_cast<float>(y);
-        if constexpr (TW == TW_TWO) diag += fg;   // the pairs (i, i): w_i * log2(1 + e^0)
+        float w;
+        if constexpr (TW == TW_DELTA) w = gain_of_grade(y) * inv_max_dcg;
+        else if (TW == TW_TWO && variant != 0) w = gain_of_grade(y) * inv_max_dcg / tb.disc[p];
+        else w = static_cast<float>(y);
+        if constexpr (TW == TW_TWO) diag += w;   // the pairs (i, i): w_i * log2(1 + e^0)
+        fg = w;
         if constexpr (TW == TW_HINGE) {
           fa = s;                                // raw score: the hinge works on s_i - s_j itself
         } else if (factored) {
-          const float c = s - mid;
-          const float eh = c * k_hi;
-          const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;
-          fe = eh;
-          fa = ex2_approx(-eh) * (1.0f - el);
-          fb = ex2_approx(eh) * (1.0f + el);
+          doc_factors<TW>(s, mid, k_hi, k_lo, w, fa, fb, fe, fg);
         } else {
           fa = sigma * s;
         }

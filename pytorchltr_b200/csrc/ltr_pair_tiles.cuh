@@ -15,20 +15,30 @@
 // are added to a warp-private shared array with one vector read-modify-write (every lane
 // touches a different chunk, so there are no conflicts and no atomics).
 //
-// Pair math (2 MUFU + 11 FP32 ops per pair, branch-free in the winner: see pair_once).
+// Pair math of the factored form (pair_fact): per unordered pair 1.5 MUFU + 11 FP32 lane-operations,
+// issued as packed f32x2 instructions on TWO adjacent columns at a time (FFMA2 / FADD2 / FMUL2: abs,
+// negation and the broadcast of a row value are operand modifiers, so the 11 operations cost 5.5
+// issue slots per pair), branch-free in the winner.
 // exp(-sigma (s_i - s_j)) is FACTORED as a_i * b_j with a_i = exp(-sigma (s_i - mid)), b_j = exp(+sigma (s_j - mid)) computed once per
 // document (double-precision exponent, so the product is good to a few float32 ulps); the pair
-// then needs only rcp and lg2 on the MUFU pipe.  With q = a_i b_j and p = 1 + q:
+// then needs only rcp and lg2 on the MUFU pipe, and the two pairs of a packed instruction share ONE
+// reciprocal: R = 1 / (p_0 p_1), 1 / p_0 = R p_1, 1 / p_1 = R p_0.  With q = a_i b_j and p = 1 + q:
 //     i wins (G_i > G_j):  sigmoid(-x) = q / p,  log2(1 + e^-x) = lg2(p)
 //     j wins (G_i < G_j):  sigmoid(-x) = 1 / p,  log2(1 + e^-x) = lg2(p) + (e_i - e_j)
 // (e = sigma (s - mid) log2 e, so e_i - e_j = -lg2 q).  The factored form needs
-// sigma * (max - min) * log2 e <= kFactoredRange so that q stays finite; queries outside that
-// range take the stable form exp(-|x|) (3 MUFU) instead.
+// sigma * (max - min) * log2 e <= kFactoredRange so that p_0 p_1 stays finite; queries outside that
+// range take the stable form exp(-|x|) (3 MUFU, scalar) instead.
+// The winner-by-relevance losses work on HALVED weights and exponents (h = ws / 2, e' = e / 2; the
+// tables and factors are stored halved, the loss is doubled at the end -- all exact in binary):
+//     a = |h|:   loss / 2 += a lg2(p) + (a - h)(e'_i - e'_j),   row += a (2 r - 1) - h,   column -= the same.
 //
-// Padding costs nothing per pair: a padded document is given b = 0 and G = 0 as a column and
-// a = 0, G = +BIG as a row, which sends every pair that involves it down the "i wins" branch
-// with q = 0, i.e. an exact zero contribution to loss and gradients.  (Stable form: padding is
-// a document of gain 0 scored -1e30, whose pairs evaluate to exp(-1e30) = 0 exactly.)
+// Padding: a padded ROW carries a = 0 (so p = 1, lg2 = 0, r = 1 exactly: both pairs of its packed
+// instruction have p = 1) and the gain +BIG (it "wins" everything: a - h = 0); a padded COLUMN carries
+// b = 0 and the smallest gain of the query, min(0, min_valid G) (it loses everything: a - h = 0 and
+// a lg2(1) = 0).  Every pair that involves padding contributes an exact zero to the loss; a padded
+// column that shares its reciprocal with a valid one sees r = 1 +- 1 ulp instead of 1 and leaves
+// a (2 r - 2) ~ 1e-7 of ONE pair weight in that row's gradient (once per row at most).
+// (Stable form: padding is a document of gain 0 scored -1e30, whose pairs evaluate to exp(-1e30) = 0.)
 //
 // delta_|i-j| (LambdaNDCGLoss2, pairwise_lambda.py:206-211) only depends on the rank distance:
 // a step with chunk distance d needs the 2R-1 values delta[|R d + e|], e in (-R, R), which are
@@ -40,8 +50,11 @@
 
 namespace ltr {
 
-constexpr float kFactoredRange = 64.0f;    // max |sigma| * (max - min) * log2(e) for q = a_i * b_j
+constexpr float kFactoredRange = 60.0f;    // max |sigma| * (max - min) * log2(e): p_0 * p_1 <= 2^121 stays finite
 constexpr float kBigGain = 1.0e30f;
+
+// winner decided by relevance (halved weights / exponents in the factored form, see pair_fact)
+__host__ __device__ constexpr bool tw_winner(int tw) { return tw == 0 || tw == 1 || tw == 2; }   // UNIT, DIFF, DELTA
 
 // Per-document factors of one query in shared memory, RANK order, structure of arrays so that
 // the 32 lanes of a step read 32 consecutive chunks (conflict-free 128-bit loads).
@@ -158,6 +171,166 @@ __device__ __forceinline__ void pair_once(float ra, float re, float rg, float cx
   }
 }
 
+// ---- one pair (float) or the pairs of two adjacent columns (float2, packed f32x2 arithmetic) -----------
+template <typename V> __device__ __forceinline__ V vsplat(float x);
+template <> __device__ __forceinline__ float vsplat<float>(float x) { return x; }
+template <> __device__ __forceinline__ float2 vsplat<float2>(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float vabs(float a) { return fabsf(a); }
+__device__ __forceinline__ float2 vabs(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float vclamp_half(float a) { return fminf(fmaxf(a, -0.5f), 0.5f); }
+__device__ __forceinline__ float2 vclamp_half(float2 a) { return make_float2(vclamp_half(a.x), vclamp_half(a.y)); }
+__device__ __forceinline__ float vhsum(float a) { return a; }
+__device__ __forceinline__ float vhsum(float2 a) { return a.x + a.y; }
+// p -> (1 / p, lg2 p); the two pairs of the packed form share one reciprocal
+__device__ __forceinline__ void rcp_lg2(float p, float& r, float& lg) {
+  r = rcp_approx(p);
+  lg = lg2_approx(p);
+}
+__device__ __forceinline__ void rcp_lg2(float2 p, float2& r, float2& lg) {
+  const float R = rcp_approx(p.x * p.y);
+  r = make_float2(R * p.y, R * p.x);
+  lg = make_float2(lg2_approx(p.x), lg2_approx(p.y));
+}
+
+// Factored pair(s): row (ra, re, rg, rv) against column(s) (cx = b_j, ce, cg); dwh = halved delta
+// window value(s) (TW_DELTA).  Winner-by-relevance losses: re / ce hold e / 2, rg / cg half weights
+// (TW_DELTA: G; TW_DIFF / TW_UNIT: rel / 2) and lacc accumulates loss / 2.  TW_TWO: plain weights and
+// exponents, rv = validity of the row (1 or 0).  racc / cacc receive -lambda' / +lambda'.
+template <int TW, typename V>
+__device__ __forceinline__ void pair_fact(V ra, V re, V rg, V rv, V cx, V ce, V cg, V dwh, V& lacc, V& racc,
+                                          V& cacc) {
+  if constexpr (TW == TW_TWO) {
+    // w_i log2(1 + e^-x) + w_j log2(1 + e^+x), x = sigma (s_i - s_j) (see pair_once)
+    const V q = vmul(ra, cx);
+    const V p = vadd(q, vsplat<V>(1.0f));
+    V r, lg;
+    rcp_lg2(p, r, lg);
+    const V wj = vmul(cg, rv);
+    lacc = vfma(vadd(rg, wj), lg, lacc);
+    lacc = vfma(wj, vadd(re, vneg(ce)), lacc);
+    const V gc = vmul(r, vfma(vneg(rg), q, wj));
+    racc = vadd(racc, gc);
+    cacc = vadd(cacc, vneg(gc));
+  } else {
+    const V gd = vadd(rg, vneg(cg));
+    V h;
+    if constexpr (TW == TW_DELTA) h = vmul(dwh, gd);
+    else if constexpr (TW == TW_DIFF) h = gd;
+    else h = vclamp_half(gd);                   // integer grades, halved: sign(gd) / 2
+    const V a = vabs(h);
+    const V p = vfma(ra, cx, vsplat<V>(1.0f));
+    V r, lg;
+    rcp_lg2(p, r, lg);
+    lacc = vfma(a, lg, lacc);
+    lacc = vfma(vadd(a, vneg(h)), vadd(re, vneg(ce)), lacc);
+    const V t = vfma(r, vsplat<V>(2.0f), vsplat<V>(-1.0f));
+    const V v = vfma(a, t, vneg(h));
+    racc = vadd(racc, v);
+    cacc = vadd(cacc, vneg(v));
+  }
+}
+
+// Per-document factors of the factored form in pair_fact's conventions.  w = weight basis of the
+// document (normalised gain G, float(rel), or the ordered-pair weight of TW_TWO); (k_hi, k_lo) =
+// sigma log2(e) split into two floats, so that e = (s - mid) k is exact to ~2^-48 relative.
+template <int TW>
+__device__ __forceinline__ void doc_factors(float s, float mid, float k_hi, float k_lo, float w, float& fa,
+                                            float& fb, float& fe, float& fg) {
+  const float c = s - mid;
+  const float eh = c * k_hi;
+  const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
+  fa = ex2_approx(-eh) * (1.0f - el);
+  fb = ex2_approx(eh) * (1.0f + el);
+  constexpr float half = tw_winner(TW) ? 0.5f : 1.0f;
+  fe = half * eh;
+  fg = half * w;
+}
+
+// Accumulators of one lane over a run of ring steps: packed halves (even / odd column of a pair)
+// plus scalar ones for the odd last column of a 1- or 3-rank chunk.
+template <int R>
+struct RowAcc {
+  float2 l2;
+  float l1;
+  float2 r2[R];
+  float r1[R];
+  __device__ __forceinline__ void clear() {
+    l2 = make_float2(0.0f, 0.0f);
+    l1 = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { r2[r] = make_float2(0.0f, 0.0f); r1[r] = 0.0f; }
+  }
+  __device__ __forceinline__ float loss() const { return l2.x + l2.y + l1; }
+  __device__ __forceinline__ float row(int r) const { return r2[r].x + r2[r].y + r1[r]; }
+  __device__ __forceinline__ void add(const RowAcc& o) {
+    l2 = vadd(l2, o.l2);
+    l1 += o.l1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { r2[r] = vadd(r2[r], o.r2[r]); r1[r] += o.r1[r]; }
+  }
+};
+
+// The R x R pairs of one row chunk against one column chunk (factored form), columns two at a time.
+//   dwin : halved delta window of this chunk distance, dwin[k - r + R - 1] for row r and column k (TW_DELTA)
+//   tc   : column gradients of this step, tc[k] += ...
+template <int TW, int R>
+__device__ __forceinline__ void chunk_pairs(const float (&ra)[R], const float (&re)[R], const float (&rg)[R],
+                                            const float (&rv)[R], const float (&cx)[4], const float (&ce)[4],
+                                            const float (&cg)[4], const float (&dwin)[8], RowAcc<R>& acc,
+                                            float (&tc)[4]) {
+  constexpr int CP = R / 2;
+#pragma unroll
+  for (int cp = 0; cp < CP; ++cp) {
+    const int k = 2 * cp;
+    const float2 cx2 = make_float2(cx[k], cx[k + 1]), ce2 = make_float2(ce[k], ce[k + 1]);
+    const float2 cg2 = make_float2(cg[k], cg[k + 1]);
+    float2 tc2 = make_float2(tc[k], tc[k + 1]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 dw2 = make_float2(0.0f, 0.0f);
+      if constexpr (TW == TW_DELTA) dw2 = make_float2(dwin[k - r + R - 1], dwin[k - r + R]);
+      pair_fact<TW, float2>(vsplat<float2>(ra[r]), vsplat<float2>(re[r]), vsplat<float2>(rg[r]),
+                            vsplat<float2>(rv[r]), cx2, ce2, cg2, dw2, acc.l2, acc.r2[r], tc2);
+    }
+    tc[k] = tc2.x;
+    tc[k + 1] = tc2.y;
+  }
+  if constexpr ((R & 1) != 0) {
+    constexpr int k = R - 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float dw = 0.0f;
+      if constexpr (TW == TW_DELTA) dw = dwin[k - r + R - 1];
+      pair_fact<TW, float>(ra[r], re[r], rg[r], rv[r], cx[k], ce[k], cg[k], dw, acc.l1, acc.r1[r], tc[k]);
+    }
+  }
+}
+
+// The triangle inside a chunk (rank distance k - r > 0), scalar.
+template <int TW, int R>
+__device__ __forceinline__ void chunk_triangle(const float (&ra)[R], const float (&re)[R], const float (&rg)[R],
+                                               const float (&rv)[R], const float (&cx)[4], const float (&ce)[4],
+                                               const float (&cg)[4], const float (&dwin)[8], float& tl,
+                                               float (&tr)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int k = r + 1; k < R; ++k) {
+      float dw = 0.0f;
+      if constexpr (TW == TW_DELTA) dw = dwin[k - r + R - 1];
+      pair_fact<TW, float>(ra[r], re[r], rg[r], rv[r], cx[k], ce[k], cg[k], dw, tl, tr[r], tr[k]);
+    }
+  }
+}
+
 // R consecutive floats starting at p[first] (first is a multiple of R; p is 16-byte aligned)
 template <int R>
 __device__ __forceinline__ void load_chunk(const float* __restrict__ p, int first, float (&v)[R]) {
@@ -198,6 +371,112 @@ __device__ __forceinline__ void load_chunk_s(const float* __restrict__ p, int ch
   }
 }
 
+// R column values of chunk `chunk` into a 4-slot array (the unused slots of a contiguous layout
+// are never read by chunk_pairs)
+template <int R, int S>
+__device__ __forceinline__ void load_cols(const float* __restrict__ p, int chunk, float (&v)[4]) {
+  if constexpr (S == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + chunk * 4);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    float u[R];
+    load_chunk<R>(p, chunk * S, u);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = r < R ? u[r < R ? r : 0] : 0.0f;
+  }
+}
+
+// Factored form of ring_pass (below): packed pair math (chunk_pairs), same schedule.
+template <int TW, int R, int S>
+__device__ __forceinline__ float ring_pass_fact(const PairSoA& it, float* __restrict__ gcol,
+                                                const float* __restrict__ wtab, int C, int n, int lane,
+                                                float (&racc)[R]) {
+  constexpr bool kFast = S == 4;
+  constexpr float kLossScale = TW == TW_TWO ? 1.0f : 2.0f;   // halved weights and exponents (pair_fact)
+  const bool active = lane < C;
+  const int me = active ? lane : 0;
+  float ra[R], re[R], rg[R], rv[R];
+  load_chunk_s<R, S>(it.a, me, ra);
+  load_chunk_s<R, S>(it.g, me, rg);
+  load_chunk_s<R, S>(it.e, me, re);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool valid = active && (me * R + r < n);
+    ra[r] = valid ? ra[r] : 0.0f;
+    rg[r] = valid ? rg[r] : (TW == TW_TWO ? 0.0f : kBigGain);
+    rv[r] = valid ? 1.0f : 0.0f;
+  }
+  RowAcc<R> acc;
+  acc.clear();
+  float tl = 0.0f, tr[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) tr[r] = 0.0f;
+
+  // within-chunk triangle (rank distance c - r > 0)
+  if constexpr (R > 1) {
+    float dwin[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if constexpr (TW == TW_DELTA) load_window(reinterpret_cast<const float4*>(wtab) + kMaxChunks * 2, dwin);
+    float cx[4], ce[4], cg[4];
+    load_cols<R, S>(it.b, me, cx);
+    load_cols<R, S>(it.g, me, cg);
+    load_cols<R, S>(it.e, me, ce);
+    chunk_triangle<TW, R>(ra, re, rg, rv, cx, ce, cg, dwin, tl, tr);
+  }
+
+  const int steps = C >> 1;
+  // even ring: the last step pairs chunk l with l + C/2 from both ends; only the lower half commits
+  const bool even = (C & 1) == 0;
+  const bool dup_last = even && lane >= steps;
+  int pc = me;
+  int m = 1;
+  if constexpr (kFast) {
+    // a lane without rows carries a = 0 and the padding gain: its pairs contribute exact zeros and only
+    // the address of its column update is predicated (chunk 32 + lane is a dump)
+    const int nfast = even ? steps - 1 : steps;
+    for (; m <= nfast; ++m) {
+      pc = pc + 1 == C ? 0 : pc + 1;
+      float dwin[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      if constexpr (TW == TW_DELTA)
+        load_window(reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2, dwin);
+      float4* g4 = reinterpret_cast<float4*>(gcol) + (active ? pc : 32 + lane);
+      const float4 gold = *g4;
+      float cx[4], ce[4], cg[4];
+      load_cols<R, S>(it.b, pc, cx);
+      load_cols<R, S>(it.g, pc, cg);
+      load_cols<R, S>(it.e, pc, ce);
+      float tc[4] = {gold.x, gold.y, gold.z, gold.w};
+      chunk_pairs<TW, R>(ra, re, rg, rv, cx, ce, cg, dwin, acc, tc);
+      *g4 = make_float4(tc[0], tc[1], tc[2], tc[3]);
+      __syncwarp();
+    }
+  }
+  for (; m <= steps; ++m) {
+    pc = pc + 1 == C ? 0 : pc + 1;
+    const bool commit = active && !(dup_last && m == steps);
+    float dwin[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if constexpr (TW == TW_DELTA)
+      load_window(reinterpret_cast<const float4*>(wtab) + (pc - me + kMaxChunks) * 2, dwin);
+    float cx[4], ce[4], cg[4];
+    load_cols<R, S>(it.b, pc, cx);
+    load_cols<R, S>(it.g, pc, cg);
+    load_cols<R, S>(it.e, pc, ce);
+    RowAcc<R> tmp;
+    tmp.clear();
+    float tc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    chunk_pairs<TW, R>(ra, re, rg, rv, cx, ce, cg, dwin, tmp, tc);
+    if (commit) {
+      acc.add(tmp);
+      // column gradients: chunk pc owns gcol[4 pc .. 4 pc + 3]
+#pragma unroll
+      for (int c = 0; c < R; ++c) gcol[pc * 4 + c] += tc[c];
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) racc[r] = active ? acc.row(r) + tr[r] : 0.0f;
+  return active ? kLossScale * (acc.loss() + tl) : 0.0f;
+}
+
 // All-pairs pass over one "ring" of C <= 32 chunks of R ranks held by one warp (C*R >= n).
 //   it    : rank-ordered factors of this block in shared memory, chunk c at [S c, S c + R)
 //   gcol  : warp-private column-gradient accumulators, chunk c at gcol[4c .. 4c+R), zero on entry;
@@ -212,6 +491,7 @@ template <int TW, bool FACTORED, int R, int S = R>
 __device__ __forceinline__ float ring_pass(const PairSoA& it, float* __restrict__ gcol,
                                            const float* __restrict__ wtab, int C, int n, int lane,
                                            float (&racc)[R]) {
+  if constexpr (FACTORED) return ring_pass_fact<TW, R, S>(it, gcol, wtab, C, n, lane, racc);
   constexpr bool kFast = FACTORED && S == 4;
   const bool active = lane < C;
   const int me = active ? lane : 0;
@@ -348,52 +628,83 @@ __device__ __forceinline__ float tile_pass(const PairSoA& it, int row_base, int 
                                            const float* __restrict__ delta, float* __restrict__ gcol,
                                            int lane, float (&racc)[4]) {
   constexpr int R = 4;
-  const float* colx = FACTORED ? it.b : it.a;
-  float ra[R], re[R], rg[R];
-  load_chunk<R>(it.a, row_base + lane * R, ra);
-  load_chunk<R>(it.g, row_base + lane * R, rg);
-  if constexpr (FACTORED) load_chunk<R>(it.e, row_base + lane * R, re);
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if constexpr (!FACTORED) re[r] = 0.0f;
-    racc[r] = 0.0f;
-  }
-  float lacc = 0.0f;
-  const int dist0 = (col_base - row_base) >> 2;   // chunk distance of column chunk 0 from row chunk 0
-  for (int m = 0; m < 32; ++m) {
-    const int pc = (lane + m) & 31;
-    float dwin[8];
-    if constexpr (TW == TW_DELTA) {
-      // delta[4d - 4 .. 4d + 3]: slot e + 4, so the window (e = -3..3) starts one float in
-      const float4* w4 = reinterpret_cast<const float4*>(delta) + (dist0 + pc - lane - 1);
-      const float4 w0 = *w4, w1 = *(w4 + 1);
-      dwin[0] = w0.y; dwin[1] = w0.z; dwin[2] = w0.w;
-      dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w; dwin[7] = 0.0f;
+  if constexpr (FACTORED) {
+    float ra[R], re[R], rg[R];
+    const float rv[R] = {1.0f, 1.0f, 1.0f, 1.0f};
+    load_chunk<R>(it.a, row_base + lane * R, ra);
+    load_chunk<R>(it.g, row_base + lane * R, rg);
+    load_chunk<R>(it.e, row_base + lane * R, re);
+    RowAcc<R> acc;
+    acc.clear();
+    const int dist0 = (col_base - row_base) >> 2;   // chunk distance of column chunk 0 from row chunk 0
+    for (int m = 0; m < 32; ++m) {
+      const int pc = (lane + m) & 31;
+      float dwin[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      if constexpr (TW == TW_DELTA) {
+        // delta[4d - 4 .. 4d + 3]: slot e + 4, so the window (e = -3..3) starts one float in
+        const float4* w4 = reinterpret_cast<const float4*>(delta) + (dist0 + pc - lane - 1);
+        const float4 w0 = *w4, w1 = *(w4 + 1);
+        dwin[0] = w0.y; dwin[1] = w0.z; dwin[2] = w0.w;
+        dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w;
+      }
+      float cx[4], ce[4], cg[4];
+      load_cols<R, 4>(it.b + col_base, pc, cx);
+      load_cols<R, 4>(it.g + col_base, pc, cg);
+      load_cols<R, 4>(it.e + col_base, pc, ce);
+      float4* g4 = reinterpret_cast<float4*>(gcol) + pc;
+      const float4 gold = *g4;
+      float tc[4] = {gold.x, gold.y, gold.z, gold.w};
+      chunk_pairs<TW, R>(ra, re, rg, rv, cx, ce, cg, dwin, acc, tc);
+      *g4 = make_float4(tc[0], tc[1], tc[2], tc[3]);
+      __syncwarp();
     }
-    float cx[R], ce[R], cg[R];
-    load_chunk<R>(colx, col_base + pc * R, cx);
-    load_chunk<R>(it.g, col_base + pc * R, cg);
-    if constexpr (FACTORED) load_chunk<R>(it.e, col_base + pc * R, ce);
-    float tc[R];
 #pragma unroll
-    for (int c = 0; c < R; ++c) tc[c] = 0.0f;
+    for (int r = 0; r < R; ++r) racc[r] = acc.row(r);
+    return (tw_winner(TW) ? 2.0f : 1.0f) * acc.loss();
+  } else {
+    const float* colx = it.a;
+    float ra[R], re[R], rg[R];
+    load_chunk<R>(it.a, row_base + lane * R, ra);
+    load_chunk<R>(it.g, row_base + lane * R, rg);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int c = 0; c < R; ++c) {
-        float dw = 1.0f;
-        if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
-        pair_once<TW, FACTORED>(ra[r], re[r], rg[r], cx[c], FACTORED ? ce[c] : 0.0f, cg[c], dw, lacc,
-                                racc[r], tc[c]);
-      }
+      re[r] = 0.0f;
+      racc[r] = 0.0f;
     }
-    float4* g4 = reinterpret_cast<float4*>(gcol) + pc;
-    float4 g = *g4;
-    g.x += tc[0]; g.y += tc[1]; g.z += tc[2]; g.w += tc[3];
-    *g4 = g;
-    __syncwarp();
+    float lacc = 0.0f;
+    const int dist0 = (col_base - row_base) >> 2;
+    for (int m = 0; m < 32; ++m) {
+      const int pc = (lane + m) & 31;
+      float dwin[8];
+      if constexpr (TW == TW_DELTA) {
+        const float4* w4 = reinterpret_cast<const float4*>(delta) + (dist0 + pc - lane - 1);
+        const float4 w0 = *w4, w1 = *(w4 + 1);
+        dwin[0] = w0.y; dwin[1] = w0.z; dwin[2] = w0.w;
+        dwin[3] = w1.x; dwin[4] = w1.y; dwin[5] = w1.z; dwin[6] = w1.w; dwin[7] = 0.0f;
+      }
+      float cx[R], cg[R];
+      load_chunk<R>(colx, col_base + pc * R, cx);
+      load_chunk<R>(it.g, col_base + pc * R, cg);
+      float tc[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) tc[c] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int c = 0; c < R; ++c) {
+          float dw = 1.0f;
+          if constexpr (TW == TW_DELTA) dw = dwin[c - r + R - 1];
+          pair_once<TW, false>(ra[r], re[r], rg[r], cx[c], 0.0f, cg[c], dw, lacc, racc[r], tc[c]);
+        }
+      }
+      float4* g4 = reinterpret_cast<float4*>(gcol) + pc;
+      float4 g = *g4;
+      g.x += tc[0]; g.y += tc[1]; g.z += tc[2]; g.w += tc[3];
+      *g4 = g;
+      __syncwarp();
+    }
+    return lacc;
   }
-  return lacc;
 }
 
 }  // namespace ltr

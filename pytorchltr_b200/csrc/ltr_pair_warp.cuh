@@ -387,6 +387,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     float diag = 0.0f;   // ARP1 / NDCG1 also count the pairs (i, i): w_i * log2(1 + e^0) = w_i
     {
       float fa[kWarpE], fb[kWarpE], fe[kWarpE], fg[kWarpE];
+      float gmin = INFINITY;   // factored winner-by-relevance losses: padded columns carry the smallest valid gain
 #pragma unroll
       for (int j = 0; j < kWarpE; ++j) {
         const int p = lane * Rq + j;
@@ -396,22 +397,29 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
           const int d = rank2doc[p];
           const float sd = ws.raw_s[d];
           const int yd = ws.raw_y[d];
-          if constexpr (TW == TW_DELTA) fg[j] = gain_of_grade(yd) * inv_max_dcg;
-          else if (TW == TW_TWO && variant != 0) fg[j] = gain_of_grade(yd) * inv_max_dcg / tb.disc[p];
-          else fg[j] = static_cast<float>(yd);
-          if constexpr (TW == TW_TWO) diag += fg[j];
+          float w;
+          if constexpr (TW == TW_DELTA) w = gain_of_grade(yd) * inv_max_dcg;
+          else if (TW == TW_TWO && variant != 0) w = gain_of_grade(yd) * inv_max_dcg / tb.disc[p];
+          else w = static_cast<float>(yd);
+          if constexpr (TW == TW_TWO) diag += w;
+          fg[j] = w;
           if constexpr (TW == TW_HINGE) {
             fa[j] = sd;                          // raw score: the hinge works on s_i - s_j itself
           } else if (factored) {
-            const float c = sd - mid;
-            const float eh = c * k_hi;
-            const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
-            fe[j] = eh;
-            fa[j] = ex2_approx(-eh) * (1.0f - el);
-            fb[j] = ex2_approx(eh) * (1.0f + el);
+            doc_factors<TW>(sd, mid, k_hi, k_lo, w, fa[j], fb[j], fe[j], fg[j]);
+            gmin = fminf(gmin, fg[j]);
           } else {
             fa[j] = sigma * sd;
           }
+        }
+      }
+      if constexpr (tw_winner(TW)) {
+        if (factored) {
+          gmin = -warp_max(-gmin);
+          if (!(gmin < INFINITY)) gmin = 0.0f;
+#pragma unroll
+          for (int j = 0; j < kWarpE; ++j)
+            if (!(j < Rq && lane * Rq + j < nb)) fg[j] = gmin;
         }
       }
       __syncwarp();   // raw_s / raw_y / rank2doc fully consumed: they are reused below
