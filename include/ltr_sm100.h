@@ -10,14 +10,20 @@
  *
  * Common contract
  *   - Padded batches, row-major and contiguous: scores float32 [B*L] (ld = L),
- *     relevance int64 or int32 [B*L] (`rel_bytes` = 8 or 4), n int64 or int32 [B]
- *     (`n_bytes` = 8 or 4).  Documents j >= n[b] are padding.  n is clamped to [0, L].
+ *     relevance int64 (the reference's dtype), int32, int16 or uint8 [B*L] (`rel_bytes` = 8, 4, 2
+ *     or 1), n int64 or int32 [B] (`n_bytes` = 8 or 4).  Documents j >= n[b] are padding.  n is
+ *     clamped to [0, L].
  *   - Device entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t,
  *     NULL = legacy default stream), never synchronise, never allocate and keep no
  *     pointer after returning: they are CUDA-graph capturable and re-entrant.
  *   - `*_host` entry points take HOST pointers (pinned memory makes the copies
  *     asynchronous) plus a caller-owned device workspace; they enqueue
- *     H2D copies -> kernel -> D2H copies on `stream` and return without synchronising.
+ *     H2D copies -> kernel -> D2H copies and return without synchronising: everything has
+ *     completed once `stream` has.  Large batches are cut into chunks of queries whose copies run
+ *     on two library-owned streams (created once per device on first use) so that H2D, kernel and
+ *     D2H overlap; these entry points are not meant for CUDA-graph capture.
+ *   - The first launch on a device fills ~70 KB of score-independent tables on the caller's stream
+ *     and creates one event; no call ever synchronises.
  *   - The caller owns every buffer.  Inputs are read-only.
  *   - Return value: 0 on success, a negative LTR_E* code otherwise; nothing is thrown
  *     and the process is never terminated.  ltr_strerror() names the code,
@@ -39,12 +45,12 @@
 extern "C" {
 #endif
 
-#define LTR_VERSION 105            /* major*100 + minor */
+#define LTR_VERSION 200            /* major*100 + minor */
 #define LTR_MAX_LIST_SIZE 4096
 
 /* error codes */
 #define LTR_OK 0
-#define LTR_EINVAL (-1)            /* bad argument (NULL pointer, bad mode, bad dtype width, k < 1) */
+#define LTR_EINVAL (-1)            /* bad argument (NULL pointer, bad mode, bad dtype width, k < 0) */
 #define LTR_EUNSUPPORTED (-2)      /* L > LTR_MAX_LIST_SIZE or not an sm_100 device */
 #define LTR_ECUDA (-3)             /* a CUDA runtime call failed: see ltr_last_cuda_error() */
 
@@ -211,19 +217,35 @@ int ltr_collate(const float *features, const int64_t *relevance, const int64_t *
 
 /*
  * Host-buffer form of the three loss families (the call the reference's CPU path is
- * compared with end to end): copies scores / relevance (int64) / n (int64) from host
- * memory into `workspace`, runs the fused loss + gradient kernel and copies loss_out
- * [B] and dscores_out [B*L] (if not NULL) back to host memory, all on `stream`.
- * `workspace` is a device buffer of at least ltr_host_workspace_bytes(B, L) bytes.
+ * compared with end to end): copies scores / relevance / n from host memory into `workspace`,
+ * runs the fused loss + gradient kernel and copies loss_out [B] and dscores_out [B*L] (if not
+ * NULL) back to host memory.  `workspace` is a device buffer of at least
+ * ltr_host_workspace_bytes(B, L) bytes (sized for int64 inputs; enough for every width).
+ *   ltr_loss_host      int64 relevance and n (the reference's dtypes).
+ *   ltr_loss_host_ex   relevance / n of any accepted width; keep_dscores != 0 computes the gradient
+ *                      into the workspace even when h_dscores_out is NULL (the usual training step:
+ *                      the backward pass scales it by the upstream gradient first, see
+ *                      ltr_scale_rows_host).
  */
 size_t ltr_host_workspace_bytes(int B, int L);
-/* Byte offset, inside that workspace, of the DEVICE copy of dscores_out [B*L] left behind by
- * ltr_loss_host (valid once the stream has reached it): a caller whose upstream gradient is not
- * all ones runs ltr_scale_rows on it without copying the gradient back to the device. */
+/* Byte offset, inside that workspace, of the DEVICE copy of dscores [B*L] left behind by
+ * ltr_loss_host / ltr_loss_host_ex (valid once the stream has reached it). */
 size_t ltr_host_workspace_dscores_offset(int B, int L);
 int ltr_loss_host(int family, int mode, const float *h_scores, const int64_t *h_rel,
                   const int64_t *h_n, int B, int L, float sigma, float *h_loss_out,
                   float *h_dscores_out, void *workspace, size_t workspace_bytes, void *stream);
+int ltr_loss_host_ex(int family, int mode, const float *h_scores, const void *h_rel, int rel_bytes,
+                     const void *h_n, int n_bytes, int B, int L, float sigma, float *h_loss_out,
+                     float *h_dscores_out, int keep_dscores, void *workspace,
+                     size_t workspace_bytes, void *stream);
+/*
+ * Backward pass of a host caller whose upstream gradient is one scalar for every query (what
+ * `loss.sum().backward()` / `loss.mean().backward()` produce): h_out[b, j] = g * d_dscores[b, j],
+ * scaled on the device (into d_scratch [B*L], which may be NULL when g == 1) and copied to host
+ * memory chunk by chunk, the copy of one chunk overlapping the scaling of the next.
+ */
+int ltr_scale_rows_host(float g, const float *d_dscores, float *h_out, int B, int L,
+                        float *d_scratch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,8 @@ SYMBOLS = (
     "ltr_listnet", "ltr_rank_metrics", "ltr_rank_by_score", "ltr_scale_rows",
     "ltr_host_workspace_bytes", "ltr_loss_host", "ltr_schedule_workspace_bytes",
     "ltr_pairwise_additive_ws", "ltr_lambda_ws", "ltr_host_workspace_dscores_offset",
-    "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate", "ltr_pbm_probabilities",
+    "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate",
+    "ltr_pbm_probabilities", "ltr_loss_host_ex", "ltr_scale_rows_host",
 )
 
 ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
@@ -89,6 +90,11 @@ def _declare(lib):
     lib.ltr_loss_host.restype = c_int
     lib.ltr_loss_host.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.ltr_loss_host_ex.restype = c_int
+    lib.ltr_loss_host_ex.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+    lib.ltr_scale_rows_host.restype = c_int
+    lib.ltr_scale_rows_host.argtypes = [c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
 
 
 def lib():

@@ -23,9 +23,24 @@ def _device_for(t: torch.Tensor) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_REL_DTYPES = (torch.int64, torch.int32, torch.int16, torch.uint8)
+
+
+def _integer_labels(relevance: torch.Tensor) -> torch.Tensor:
+    """Relevance in a dtype the kernels read directly (int64 / int32 / int16 / uint8).  Other integer
+    dtypes are widened to int64; floating-point labels must be integer valued (the kernels work on
+    integer grades: a fractional label would be truncated silently otherwise)."""
+    if relevance.dtype in _REL_DTYPES:
+        return relevance
+    if relevance.dtype.is_floating_point:
+        if not bool((relevance == relevance.round()).all()):
+            raise ValueError("relevance labels must be integers (got fractional floating-point labels)")
+    return relevance.to(torch.int64)
+
+
 def normalise(scores: torch.Tensor, relevance: Optional[torch.Tensor], n: torch.Tensor,
               device: torch.device):
-    """Returns contiguous device tensors ``scores (B, L) f32``, ``relevance (B, L) i64|i32``
+    """Returns contiguous device tensors ``scores (B, L) f32``, ``relevance (B, L) i64|i32|i16|u8``
     and ``n (B,) i64|i32``.  Accepts ``(B, L)`` or ``(B, L, 1)`` like the reference
     (loss/pairwise_additive.py:60-65)."""
     if scores.dim() == 3:
@@ -48,10 +63,7 @@ def normalise(scores: torch.Tensor, relevance: Optional[torch.Tensor], n: torch.
         if tuple(relevance.shape) != (B, L):
             raise ValueError(
                 f"relevance {tuple(relevance.shape)} does not match scores {(B, L)}")
-        y = relevance.detach()
-        if y.dtype not in (torch.int64, torch.int32):
-            y = y.to(torch.int64)
-        y = y.to(device, non_blocking=True).contiguous()
+        y = _integer_labels(relevance.detach()).to(device, non_blocking=True).contiguous()
     if n.dim() != 1 or n.shape[0] != B:
         raise ValueError(f"n must have shape ({B},), got {tuple(n.shape)}")
     nn = n.detach()
@@ -63,11 +75,11 @@ def normalise(scores: torch.Tensor, relevance: Optional[torch.Tensor], n: torch.
 
 def host_loss(scores: torch.Tensor, relevance: torch.Tensor, n: torch.Tensor, family: int, mode: int,
               sigma: float, want_grad: bool, dev: torch.device):
-    """CPU caller: ONE call of the host-buffer entry point (ltr_loss_host: H2D of scores /
-    relevance / n -> ordering + fused kernel -> D2H of the loss and of d loss / d scores on the
-    current stream) and one stream synchronisation.  Returns the loss and the gradient as pinned
-    host tensors plus a device view of the gradient (kept for a backward pass whose upstream
-    gradient is not all ones)."""
+    """CPU caller: ONE call of the host-buffer entry point (ltr_loss_host_ex: H2D of scores /
+    relevance / n -> ordering + fused kernel -> D2H of the loss, chunked and overlapped for large
+    batches) and one stream synchronisation.  Returns the loss as a pinned host tensor and a device
+    view of d loss / d scores inside the call's workspace (the backward pass scales it by the upstream
+    gradient on the device and copies it to the host once)."""
     if scores.dim() == 3:
         scores = scores.reshape(scores.shape[0], scores.shape[1])
     if scores.dim() != 2:
@@ -84,24 +96,46 @@ def host_loss(scores: torch.Tensor, relevance: torch.Tensor, n: torch.Tensor, fa
     if n.dim() != 1 or n.shape[0] != B:
         raise ValueError(f"n must have shape ({B},), got {tuple(n.shape)}")
     s = scores.detach().to(torch.float32).contiguous()
-    y = relevance.detach().to(torch.int64).contiguous()
-    nn = n.detach().to(torch.int64).contiguous()
+    y = _integer_labels(relevance.detach()).contiguous()
+    nn = n.detach()
+    if nn.dtype not in (torch.int64, torch.int32):
+        nn = nn.to(torch.int64)
+    nn = nn.contiguous()
     loss_h = torch.empty(B, dtype=torch.float32, device="cpu", pin_memory=True)
-    grad_h = torch.empty((B, L), dtype=torch.float32, device="cpu", pin_memory=True) if want_grad else None
     grad_d = None
     if B > 0:
         lib = _lib.lib()
         ws_bytes = lib.ltr_host_workspace_bytes(B, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            rc = lib.ltr_loss_host(family, mode, s.data_ptr(), y.data_ptr(), nn.data_ptr(), B, L, float(sigma),
-                                   loss_h.data_ptr(), _ptr(grad_h), ws.data_ptr(), ws_bytes, _stream(dev))
+            rc = lib.ltr_loss_host_ex(family, mode, s.data_ptr(), y.data_ptr(), y.element_size(), nn.data_ptr(),
+                                      nn.element_size(), B, L, float(sigma), loss_h.data_ptr(), None,
+                                      1 if want_grad else 0, ws.data_ptr(), ws_bytes, _stream(dev))
             _lib.check(rc)
             torch.cuda.current_stream(dev).synchronize()
         if want_grad:
             off = lib.ltr_host_workspace_dscores_offset(B, L)
             grad_d = ws[off:off + 4 * B * L].view(torch.float32).view(B, L)
-    return loss_h, grad_h, grad_d
+    elif want_grad:
+        grad_d = torch.empty((0, L), dtype=torch.float32, device=dev)
+    return loss_h, grad_d
+
+
+def host_scaled_grad(g_scalar: float, grad_d: torch.Tensor) -> torch.Tensor:
+    """``g_scalar * grad_d`` as a pinned HOST tensor: scaled on the device, copied once
+    (ltr_scale_rows_host, chunked so that the copy overlaps the scaling), one synchronisation."""
+    B, L = grad_d.shape
+    out = torch.empty((B, L), dtype=torch.float32, device="cpu", pin_memory=True)
+    if B == 0:
+        return out
+    dev = grad_d.device
+    scratch = torch.empty_like(grad_d) if g_scalar != 1.0 else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ltr_scale_rows_host(float(g_scalar), grad_d.data_ptr(), out.data_ptr(), B, L,
+                                            _ptr(scratch), _stream(dev))
+        _lib.check(rc)
+        torch.cuda.current_stream(dev).synchronize()
+    return out
 
 
 def to_host(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
@@ -202,13 +236,15 @@ class _FusedLoss(torch.autograd.Function):
         ctx.scores_shape = scores.shape
         ctx.scores_dtype = scores.dtype
         ctx.scores_device = scores.device
-        ctx.host_grad = None
+        ctx.host_caller = False
         if not scores.is_cuda and not relevance.is_cuda and not n.is_cuda:
             # CPU caller: host-buffer entry point, results come back as (pinned) CPU tensors
-            loss_h, grad_h, grad_d = host_loss(scores, relevance, n, family, mode, sigma, want_grad, dev)
+            if loss_sum is not None:
+                raise ValueError("loss_sum needs CUDA inputs")
+            loss_h, grad_d = host_loss(scores, relevance, n, family, mode, sigma, want_grad, dev)
             if want_grad:
-                ctx.host_grad = grad_h
-                ctx.save_for_backward(grad_d if grad_d is not None else grad_h)
+                ctx.host_caller = True
+                ctx.save_for_backward(grad_d)
             if loss_h.dtype != scores.dtype and scores.dtype.is_floating_point:
                 loss_h = loss_h.to(scores.dtype)
             return loss_h
@@ -231,19 +267,16 @@ class _FusedLoss(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         (saved,) = ctx.saved_tensors
-        if ctx.host_grad is not None:
-            B = ctx.host_grad.shape[0]
-            # `loss.sum().backward()` of a CPU caller: the upstream gradient is a broadcast 1.0 and
-            # the gradient is already on the host (copied back by the forward call)
-            if B == 0 or (not g.is_cuda and (B == 1 or g.stride(0) == 0) and float(g.reshape(-1)[0]) == 1.0):
-                # hand over the only reference, so that autograd can adopt the tensor as `.grad`
-                # instead of cloning it
-                out, ctx.host_grad = ctx.host_grad, None
+        if ctx.host_caller and not g.is_cuda:
+            B = saved.shape[0]
+            # `loss.sum().backward()` / `loss.mean().backward()` of a CPU caller: the upstream gradient is
+            # one broadcast scalar -- it travels as a kernel argument, the product comes back in one copy
+            if B <= 1 or g.stride(0) == 0:
+                g0 = float(g.reshape(-1)[0]) if B > 0 else 1.0
+                out = host_scaled_grad(g0, saved)
                 if out.dtype != ctx.scores_dtype:
                     out = out.to(ctx.scores_dtype)
-                if out.shape != ctx.scores_shape:
-                    out = out.reshape(ctx.scores_shape)
-                return out, None, None, None, None, None, None
+                return out.reshape(ctx.scores_shape), None, None, None, None, None, None
         out = scale_rows(g, saved)
         if out.dtype != ctx.scores_dtype:
             out = out.to(ctx.scores_dtype)

@@ -40,14 +40,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Builds the shared library if it is missing or older than its sources."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Builds the shared library if it is missing or older than its sources.  `defines` / `out`
+    build an A-B variant (e.g. defines=["LTR_RING_MIN_CTAS=4"], out="build/ltr_variant.so"; select it
+    at run time with LTR_SM100_LIB)."""
+    target = out or LIB
+    if not force and not out and not _stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += ["-D" + d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     # g++ from PATH: the image's CC/CXX wrappers are not needed for nvcc's host pass
     env = dict(os.environ)
     res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -55,8 +59,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=_defs, out=_out))

@@ -23,9 +23,7 @@ def pbm_probabilities(rankings, ys, n, relevance_probs, cutoff: Optional[int] = 
         y = y.reshape(B, L)
     if tuple(y.shape) != (B, L):
         raise ValueError(f"ys {tuple(y.shape)} does not match rankings {(B, L)}")
-    if y.dtype not in (torch.int64, torch.int32):
-        y = y.to(torch.int64)
-    y = y.to(dev).contiguous()
+    y = _ops._integer_labels(y).to(dev).contiguous()
     nn_ = n.detach()
     if nn_.dtype not in (torch.int64, torch.int32):
         nn_ = nn_.to(torch.int64)
@@ -35,8 +33,10 @@ def pbm_probabilities(rankings, ys, n, relevance_probs, cutoff: Optional[int] = 
     rp = relevance_probs.detach().to(dev, torch.float32).reshape(-1).contiguous()
     if cutoff is not None and cutoff < 1:
         raise ValueError("cutoff must be at least 1")
-    cp = torch.empty((B, L), dtype=torch.float32, device=dev)
-    pr = torch.empty((B, L), dtype=torch.float32, device=dev)
+    # zero-filled: a row of `rankings` that is not a full permutation (a top-k list, duplicates) leaves
+    # the documents it does not name at probability 0 instead of uninitialised memory
+    cp = torch.zeros((B, L), dtype=torch.float32, device=dev)
+    pr = torch.zeros((B, L), dtype=torch.float32, device=dev)
     if B > 0:
         with torch.cuda.device(dev):
             rc = _lib.lib().ltr_pbm_probabilities(rk.data_ptr(), y.data_ptr(), y.element_size(), nn_.data_ptr(),

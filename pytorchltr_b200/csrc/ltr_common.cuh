@@ -67,14 +67,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// ---- integer inputs of either width (the reference passes int64; int32 is accepted) ----
+// ---- integer inputs of any width: int64 (what the reference passes), int32, int16, uint8 ----
 __device__ __forceinline__ int load_int_clamped(const void* p, int bytes, size_t i) {
   if (bytes == 8) {
     long long v = reinterpret_cast<const long long*>(p)[i];
     v = v < -2147483647LL ? -2147483647LL : (v > 2147483647LL ? 2147483647LL : v);
     return static_cast<int>(v);
   }
-  return reinterpret_cast<const int*>(p)[i];
+  if (bytes == 4) return reinterpret_cast<const int*>(p)[i];
+  if (bytes == 2) return reinterpret_cast<const short*>(p)[i];
+  return reinterpret_cast<const unsigned char*>(p)[i];
 }
 
 __device__ __forceinline__ int load_n(const void* n, int n_bytes, int b, int L) {

@@ -355,12 +355,18 @@ listnet_reg_kernel(const float* __restrict__ scores, const void* __restrict__ re
         const int j = lane + 32 * k;
         y[k] = j < nb ? static_cast<float>(r8[j]) : -INFINITY;
       }
-    } else {
+    } else if (rel_bytes == 4) {
       const int* r4 = reinterpret_cast<const int*>(rel) + base;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int j = lane + 32 * k;
         y[k] = j < nb ? static_cast<float>(r4[j]) : -INFINITY;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        y[k] = j < nb ? static_cast<float>(load_int_clamped(rel, rel_bytes, base + j)) : -INFINITY;
       }
     }
     float ms = -INFINITY, my = -INFINITY;
@@ -514,11 +520,28 @@ rank_by_score_kernel(const float* __restrict__ scores, const void* __restrict__ 
 
 // out[b, j] = g[b] * d[b, j]: the backward of every loss (HBM-bound streaming pass).
 __global__ void __launch_bounds__(256)
-scale_rows_kernel(const float* __restrict__ g, int g_stride, const float* __restrict__ d,
-                  float* __restrict__ out, int B, int L) {
+scale_rows_kernel(const float* __restrict__ g, int g_stride, float g_scalar, const float* __restrict__ d,
+                  float* __restrict__ out, int B, int L, int vec_ok) {
   const size_t total = static_cast<size_t>(B) * L;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  if ((L & 3) == 0) {
+  if (g == nullptr) {
+    // one scalar for every row, passed by value (host callers: the broadcast gradient of .sum() / .mean())
+    if (vec_ok) {
+      const size_t total4 = total >> 2;
+      const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
+      float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+      for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4; i += stride) {
+        float4 v = d4[i];
+        v.x *= g_scalar; v.y *= g_scalar; v.z *= g_scalar; v.w *= g_scalar;
+        o4[i] = v;
+      }
+    } else {
+      for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += stride)
+        out[i] = g_scalar * d[i];
+    }
+    return;
+  }
+  if (vec_ok) {
     const size_t total4 = total >> 2;
     const int L4 = L >> 2;
     const float4* __restrict__ d4 = reinterpret_cast<const float4*>(d);
@@ -568,6 +591,8 @@ inline int device_info(DeviceInfo* out) {
   return out->major == 10 ? LTR_OK : LTR_EUNSUPPORTED;
 }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 inline int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -580,6 +605,14 @@ inline int check_common(const void* scores, const void* n, int n_bytes, int B, i
   if (B > 0 && (!scores || !n)) return LTR_EINVAL;
   if (n_bytes != 4 && n_bytes != 8) return LTR_EINVAL;
   return LTR_OK;
+}
+
+// relevance element widths: int64 (the reference's dtype), int32, int16, uint8
+inline bool rel_width_ok(int bytes) { return bytes == 8 || bytes == 4 || bytes == 2 || bytes == 1; }
+
+// TMA bulk row staging: 16-byte aligned rows of a multiple of 16 bytes, for scores and relevance alike
+inline bool rows_tma_ok(const void* scores, const void* rel, int rel_bytes, int L) {
+  return (L % 4 == 0) && ((static_cast<size_t>(rel_bytes) * L) % 16 == 0) && aligned16(scores) && aligned16(rel);
 }
 
 inline int cta_threads_for(int L) {
@@ -618,8 +651,6 @@ int launch_pair(const float* scores, const void* rel, int rel_bytes, const void*
   return LTR_OK;
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 // LTR_KERNEL=generic forces the generic one-CTA-per-query kernel (debugging / A-B timing).
 inline bool force_generic() {
   const char* v = getenv("LTR_KERNEL");
@@ -632,39 +663,75 @@ inline bool force_generic() {
 constexpr int kQueueSlots = 1024;
 __device__ unsigned int g_work_queues[2 * kQueueSlots];
 
-inline int next_queue(unsigned int** out) {
+inline int next_queue(cudaStream_t st, unsigned int** out) {
   static std::atomic<unsigned int> counter{0};
+  // A launch that is being captured would bake its slot into the graph, and two graphs replayed
+  // concurrently could then share a counter: captured launches without a caller-owned workspace take
+  // the queries in a static stride instead (queue == nullptr).
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  LTR_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) {
+    *out = nullptr;
+    return LTR_OK;
+  }
   unsigned int* base = nullptr;
   LTR_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_work_queues));
   *out = base + 2 * (counter.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
   return LTR_OK;
 }
 
-// Score-independent tables (delta windows, discounts, ideal-DCG prefix sums): filled on first
-// use per device by a kernel on the caller's stream.  If that first use is being captured into
-// a CUDA graph the fill becomes a node of that graph and is repeated by the next eager call
-// (it is idempotent), so the tables are always written before any kernel that reads them runs.
+// Score-independent tables (delta windows, discounts, ideal-DCG prefix sums): filled on first use per
+// device by a kernel on the caller's stream, followed by an event.  Nothing synchronises: until the
+// event has completed, launches on any stream are made to wait for it (cudaStreamWaitEvent); a first
+// use that is being captured into a CUDA graph puts the (idempotent) fill into that graph instead.
 __device__ PairTables g_pair_tables;
 
+struct TableState {
+  std::atomic<int> state{0};   // 0: not filled, 1: fill enqueued and `ev` recorded behind it, 2: fill complete
+  cudaEvent_t ev = nullptr;
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;
+};
+
 inline int pair_tables(cudaStream_t st, const PairTables** out) {
-  static std::atomic<bool> ready[64];
+  static TableState states[64];
   int dev = 0;
   LTR_CUDA(cudaGetDevice(&dev));
   PairTables* t = nullptr;
   LTR_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&t), g_pair_tables));
-  if (dev < 0 || dev >= 64 || !ready[dev].load(std::memory_order_acquire)) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    LTR_CUDA(cudaStreamIsCapturing(st, &cap));
+  *out = t;
+  if (dev < 0 || dev >= 64) {
     init_pair_tables_kernel<<<1, 1024, 0, st>>>(t);
     LTR_CUDA(cudaGetLastError());
-    if (cap == cudaStreamCaptureStatusNone && dev >= 0 && dev < 64) {
-      // later launches may be on other streams: make the fill visible to all of them
-      LTR_CUDA(cudaStreamSynchronize(st));
-      ready[dev].store(true, std::memory_order_release);
-    }
+    return LTR_OK;
   }
-  *out = t;
-  return LTR_OK;
+  TableState& ts = states[dev];
+  if (ts.state.load(std::memory_order_acquire) == 2) return LTR_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  LTR_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) {
+    init_pair_tables_kernel<<<1, 1024, 0, st>>>(t);
+    LTR_CUDA(cudaGetLastError());
+    return LTR_OK;
+  }
+  while (ts.busy.test_and_set(std::memory_order_acquire)) {}
+  int rc = LTR_OK;
+  const int state = ts.state.load(std::memory_order_acquire);
+  cudaError_t e = cudaSuccess;
+  if (state == 0) {
+    init_pair_tables_kernel<<<1, 1024, 0, st>>>(t);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ts.ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ts.ev, st);
+    if (e == cudaSuccess) ts.state.store(1, std::memory_order_release);
+  } else if (state == 1) {
+    const cudaError_t q = cudaEventQuery(ts.ev);
+    if (q == cudaSuccess) ts.state.store(2, std::memory_order_release);
+    else if (q == cudaErrorNotReady) e = cudaStreamWaitEvent(st, ts.ev, 0);
+    else e = q;
+  }
+  ts.busy.clear(std::memory_order_release);
+  if (e != cudaSuccess) rc = cuda_fail(e);
+  return rc;
 }
 
 // ---- longest-first query schedule ------------------------------------------------------------------
@@ -767,7 +834,7 @@ inline int make_schedule(const void* n, int n_bytes, int B, int L, long long slo
     out->order = q + 4;
     return LTR_OK;
   }
-  return next_queue(&out->queue);
+  return next_queue(st, &out->queue);
 }
 
 inline int env_int(const char* name, int dflt) {
@@ -814,7 +881,7 @@ int launch_pair_cta(const float* scores, const void* rel, int rel_bytes, const v
   const int threads = kCtaWarps * 32;
   // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes, and room for the
   // double buffer next to everything else
-  int tma = (L % 4 == 0) && aligned16(scores) && aligned16(rel) && cta_smem_bytes(L, P, rel_bytes) <= 200u * 1024u;
+  int tma = rows_tma_ok(scores, rel, rel_bytes, L) && cta_smem_bytes(L, P, rel_bytes) <= 200u * 1024u;
   if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
   const size_t smem = cta_smem_bytes(L, P, tma ? rel_bytes : 0);
   int grid = 0;
@@ -842,7 +909,7 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
   const int P = next_pow2(L);
   const int threads = kRingWarps * 32;
   // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes
-  int tma = (L % 4 == 0) && aligned16(scores) && aligned16(rel);
+  int tma = rows_tma_ok(scores, rel, rel_bytes, L);
   if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
   const size_t smem = ring_smem_bytes(L, tma ? rel_bytes : 0);
   int grid = 0;
@@ -900,7 +967,7 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
                   int64_t* ranking_out, float* loss_sum, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_common(scores, n, n_bytes, B, L);
   if (rc != LTR_OK) return rc;
-  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (!rel_width_ok(rel_bytes)) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!rel || !loss_out) return LTR_EINVAL;
   DeviceInfo di;
@@ -1011,7 +1078,7 @@ int ltr_listnet(const float* scores, const void* rel, int rel_bytes, const void*
                 int B, int L, float* loss_out, float* dscores_out, float* loss_sum, void* stream) {
   int rc = check_common(scores, n, n_bytes, B, L);
   if (rc != LTR_OK) return rc;
-  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (!rel_width_ok(rel_bytes)) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!rel || !loss_out) return LTR_EINVAL;
   DeviceInfo di;
@@ -1045,7 +1112,7 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
   if (metric < LTR_METRIC_DCG || metric > LTR_METRIC_ARP) return LTR_EINVAL;
   int rc = check_common(scores, n, n_bytes, B, L);
   if (rc != LTR_OK) return rc;
-  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (!rel_width_ok(rel_bytes)) return LTR_EINVAL;
   if (k < 0) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!rel || !out) return LTR_EINVAL;
@@ -1066,7 +1133,7 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
     if (rc != LTR_OK) return rc;
     const long long want = (static_cast<long long>(B) + kTopkWarps - 1) / kTopkWarps;
     // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes
-    int tma = (L % 4 == 0) && aligned16(scores) && aligned16(rel);
+    int tma = rows_tma_ok(scores, rel, rel_bytes, L);
     if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
 #define LTR_TOPK_LAUNCH(E)                                                                                  \
   do {                                                                                                      \
@@ -1160,22 +1227,29 @@ int ltr_rank_by_score(const float* scores, const void* n, int n_bytes, int B, in
   return LTR_OK;
 }
 
+static int launch_scale_rows(const float* g, int g_stride, float g_scalar, const float* dscores, float* out, int B,
+                             int L, cudaStream_t st) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const size_t total = static_cast<size_t>(B) * L;
+  // 128-bit path: rows of a multiple of 4 floats in 16-byte aligned buffers
+  const int vec_ok = (L & 3) == 0 && aligned16(dscores) && aligned16(out);
+  const size_t work = vec_ok ? total / 4 : total;
+  long long want = static_cast<long long>((work + 255) / 256);
+  long long cap = static_cast<long long>(di.sms) * 8;
+  const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+  scale_rows_kernel<<<grid, 256, 0, st>>>(g, g_stride, g_scalar, dscores, out, B, L, vec_ok);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 int ltr_scale_rows(const float* g, int g_stride, const float* dscores, float* out, int B, int L,
                    void* stream) {
   if (B < 0 || L < 1 || (g_stride != 0 && g_stride != 1)) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!g || !dscores || !out) return LTR_EINVAL;
-  DeviceInfo di;
-  int rc = device_info(&di);
-  if (rc != LTR_OK) return rc;
-  const size_t total = static_cast<size_t>(B) * L;
-  const size_t work = (L & 3) == 0 ? total / 4 : total;
-  long long want = static_cast<long long>((work + 255) / 256);
-  long long cap = static_cast<long long>(di.sms) * 8;
-  const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
-  scale_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, g_stride, dscores, out, B, L);
-  LTR_CUDA(cudaGetLastError());
-  return LTR_OK;
+  return launch_scale_rows(g, g_stride, 0.0f, dscores, out, B, L, static_cast<cudaStream_t>(stream));
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -1209,9 +1283,11 @@ pbm_probabilities_kernel(const int64_t* __restrict__ rankings, const void* __res
 int ltr_pbm_probabilities(const int64_t* rankings, const void* ys, int ys_bytes, const void* n, int n_bytes,
                           const float* relevance_probs, int n_probs, int cutoff, float eta, int B, int L,
                           float* click_prob_out, float* propensity_out, void* stream) {
-  int rc = check_common(reinterpret_cast<const float*>(rankings), n, n_bytes, B, L);
-  if (rc != LTR_OK) return rc;
-  if ((ys_bytes != 4 && ys_bytes != 8) || n_probs < 1 || cutoff < 0) return LTR_EINVAL;
+  // elementwise kernel: any list size (no LTR_MAX_LIST_SIZE limit here)
+  if (B < 0 || L < 1 || (n_bytes != 4 && n_bytes != 8)) return LTR_EINVAL;
+  if (B > 0 && (!rankings || !n)) return LTR_EINVAL;
+  int rc = LTR_OK;
+  if (!rel_width_ok(ys_bytes) || n_probs < 1 || cutoff < 0) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!ys || !relevance_probs || !click_prob_out || !propensity_out) return LTR_EINVAL;
   DeviceInfo di;
@@ -1258,7 +1334,7 @@ int ltr_linear_listnet(const float* features, const float* weight, const float* 
                        float* loss_out, float* dscores_out, float* qgrad_out, float* loss_sum, void* stream) {
   int rc = check_common(features, n, n_bytes, B, L);
   if (rc != LTR_OK) return rc;
-  if (rel_bytes != 4 && rel_bytes != 8) return LTR_EINVAL;
+  if (!rel_width_ok(rel_bytes)) return LTR_EINVAL;
   if (F < 1) return LTR_EINVAL;
   if (B > 0 && (!weight || !rel || !loss_out || !qgrad_out)) return LTR_EINVAL;
   // the fused kernel keeps a whole L x F block in shared memory and moves it by TMA bulk copies
@@ -1312,7 +1388,7 @@ int ltr_linear_listnet_backward(const float* qgrad, const float* g, int g_stride
 size_t ltr_host_workspace_bytes(int B, int L) {
   if (B < 0 || L < 1) return 0;
   const size_t bl = static_cast<size_t>(B) * L;
-  // scores f32 | relevance i64 | n i64 | loss f32 | dscores f32
+  // scores f32 | relevance (sized for int64) | n (sized for int64) | loss f32 | dscores f32 | schedule
   return align256(bl * 4) + align256(bl * 8) + align256(static_cast<size_t>(B) * 8) +
          align256(static_cast<size_t>(B) * 4) + align256(bl * 4) + align256(schedule_bytes(B));
 }
@@ -1324,11 +1400,93 @@ size_t ltr_host_workspace_dscores_offset(int B, int L) {
          align256(static_cast<size_t>(B) * 4);
 }
 
-int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_rel,
-                  const int64_t* h_n, int B, int L, float sigma, float* h_loss_out,
-                  float* h_dscores_out, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace ltr {
+
+// ---- host-buffer pipeline ------------------------------------------------------------------------------
+// Large batches are cut into chunks of queries: the H2D copy of chunk c + 1 (copy-in stream), the kernel
+// of chunk c (caller's stream) and the D2H copy of chunk c - 1 (copy-out stream) overlap, so the call is
+// bound by the slower PCIe direction instead of the sum of the three.  The two internal streams and the
+// events are created once per device on first use; the caller's stream waits for everything at the end.
+constexpr int kPipeMaxChunks = 16;
+constexpr size_t kPipeChunkBytes = 16u << 20;
+
+struct HostPipe {
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;
+  bool ready = false;
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t start = nullptr, done = nullptr, ev_in[kPipeMaxChunks], ev_k[kPipeMaxChunks];
+};
+
+struct PipeLock {
+  HostPipe* p;
+  explicit PipeLock(HostPipe* pipe) : p(pipe) { while (p->busy.test_and_set(std::memory_order_acquire)) {} }
+  ~PipeLock() { p->busy.clear(std::memory_order_release); }
+};
+
+inline int host_pipe(HostPipe** out) {
+  static HostPipe pipes[64];
+  int dev = 0;
+  LTR_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return LTR_EUNSUPPORTED;
+  HostPipe* p = &pipes[dev];
+  PipeLock lock(p);
+  if (!p->ready) {
+    LTR_CUDA(cudaStreamCreateWithFlags(&p->in, cudaStreamNonBlocking));
+    LTR_CUDA(cudaStreamCreateWithFlags(&p->out, cudaStreamNonBlocking));
+    LTR_CUDA(cudaEventCreateWithFlags(&p->start, cudaEventDisableTiming));
+    LTR_CUDA(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+    for (int i = 0; i < kPipeMaxChunks; ++i) {
+      LTR_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+      LTR_CUDA(cudaEventCreateWithFlags(&p->ev_k[i], cudaEventDisableTiming));
+    }
+    p->ready = true;
+  }
+  *out = p;
+  return LTR_OK;
+}
+
+// queries per chunk (a multiple of 64), 0 = do not pipeline
+inline int pipe_chunk_queries(int B, size_t bytes_per_query) {
+  const size_t total = static_cast<size_t>(B) * bytes_per_query;
+  if (total < 2 * kPipeChunkBytes) return 0;
+  size_t chunks = (total + kPipeChunkBytes - 1) / kPipeChunkBytes;
+  if (chunks > static_cast<size_t>(kPipeMaxChunks)) chunks = kPipeMaxChunks;
+  size_t bc = (static_cast<size_t>(B) + chunks - 1) / chunks;
+  bc = (bc + 63) / 64 * 64;
+  return static_cast<int>(bc);
+}
+
+inline int launch_family(int family, int mode, const float* d_scores, const void* d_rel, int rel_bytes,
+                         const void* d_n, int n_bytes, int B, int L, float sigma, float* d_loss, float* d_grad,
+                         void* d_sched, size_t sched_bytes, void* stream) {
+  switch (family) {
+    case LTR_FAMILY_ADDITIVE:
+      return ltr_pairwise_additive_ws(mode, d_scores, d_rel, rel_bytes, d_n, n_bytes, B, L, sigma, d_loss, d_grad,
+                                      nullptr, d_sched, sched_bytes, stream);
+    case LTR_FAMILY_LAMBDA:
+      return ltr_lambda_ws(mode, d_scores, d_rel, rel_bytes, d_n, n_bytes, B, L, sigma, d_loss, d_grad, nullptr,
+                           nullptr, d_sched, sched_bytes, stream);
+    case LTR_FAMILY_LISTNET:
+      return ltr_listnet(d_scores, d_rel, rel_bytes, d_n, n_bytes, B, L, d_loss, d_grad, nullptr, stream);
+    default:
+      return LTR_EINVAL;
+  }
+}
+
+}  // namespace ltr
+
+extern "C" {
+
+int ltr_loss_host_ex(int family, int mode, const float* h_scores, const void* h_rel, int rel_bytes,
+                     const void* h_n, int n_bytes, int B, int L, float sigma, float* h_loss_out,
+                     float* h_dscores_out, int keep_dscores, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   if (B < 0 || L < 1) return LTR_EINVAL;
   if (L > LTR_MAX_LIST_SIZE) return LTR_EUNSUPPORTED;
+  if (!rel_width_ok(rel_bytes) || (n_bytes != 4 && n_bytes != 8)) return LTR_EINVAL;
+  if (family < LTR_FAMILY_ADDITIVE || family > LTR_FAMILY_LISTNET) return LTR_EINVAL;
   if (B == 0) return LTR_OK;
   if (!h_scores || !h_rel || !h_n || !h_loss_out || !workspace) return LTR_EINVAL;
   if (workspace_bytes < ltr_host_workspace_bytes(B, L)) return LTR_EINVAL;
@@ -1336,36 +1494,110 @@ int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_
   const size_t bl = static_cast<size_t>(B) * L;
   unsigned char* p = static_cast<unsigned char*>(workspace);
   float* d_scores = reinterpret_cast<float*>(p);            p += align256(bl * 4);
-  int64_t* d_rel = reinterpret_cast<int64_t*>(p);           p += align256(bl * 8);
-  int64_t* d_n = reinterpret_cast<int64_t*>(p);             p += align256(static_cast<size_t>(B) * 8);
+  unsigned char* d_rel = p;                                 p += align256(bl * 8);
+  unsigned char* d_n = p;                                   p += align256(static_cast<size_t>(B) * 8);
   float* d_loss = reinterpret_cast<float*>(p);              p += align256(static_cast<size_t>(B) * 4);
   float* d_grad = reinterpret_cast<float*>(p);              p += align256(bl * 4);
   void* d_sched = p;
-  const size_t sched_bytes = schedule_bytes(B);
-  LTR_CUDA(cudaMemcpyAsync(d_scores, h_scores, bl * 4, cudaMemcpyHostToDevice, st));
-  LTR_CUDA(cudaMemcpyAsync(d_rel, h_rel, bl * 8, cudaMemcpyHostToDevice, st));
-  LTR_CUDA(cudaMemcpyAsync(d_n, h_n, static_cast<size_t>(B) * 8, cudaMemcpyHostToDevice, st));
-  float* gptr = h_dscores_out ? d_grad : nullptr;
-  int rc;
-  switch (family) {
-    case LTR_FAMILY_ADDITIVE:
-      rc = ltr_pairwise_additive_ws(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, d_sched,
-                                    sched_bytes, stream);
-      break;
-    case LTR_FAMILY_LAMBDA:
-      rc = ltr_lambda_ws(mode, d_scores, d_rel, 8, d_n, 8, B, L, sigma, d_loss, gptr, nullptr, nullptr, d_sched,
-                         sched_bytes, stream);
-      break;
-    case LTR_FAMILY_LISTNET:
-      rc = ltr_listnet(d_scores, d_rel, 8, d_n, 8, B, L, d_loss, gptr, nullptr, stream);
-      break;
-    default:
-      rc = LTR_EINVAL;
+  const bool want_grad = h_dscores_out != nullptr || keep_dscores != 0;
+  const unsigned char* hr = static_cast<const unsigned char*>(h_rel);
+  const unsigned char* hn = static_cast<const unsigned char*>(h_n);
+  const size_t row_in = static_cast<size_t>(L) * (4 + rel_bytes) + n_bytes;
+
+  // chunk rows must keep every chunk's device pointers 16-byte aligned (vector / TMA paths): 64 queries do
+  const int bc = pipe_chunk_queries(B, row_in + (h_dscores_out ? 4u * L : 0u));
+  if (bc <= 0 || bc >= B) {
+    LTR_CUDA(cudaMemcpyAsync(d_scores, h_scores, bl * 4, cudaMemcpyHostToDevice, st));
+    LTR_CUDA(cudaMemcpyAsync(d_rel, h_rel, bl * rel_bytes, cudaMemcpyHostToDevice, st));
+    LTR_CUDA(cudaMemcpyAsync(d_n, h_n, static_cast<size_t>(B) * n_bytes, cudaMemcpyHostToDevice, st));
+    int rc = launch_family(family, mode, d_scores, d_rel, rel_bytes, d_n, n_bytes, B, L, sigma, d_loss,
+                           want_grad ? d_grad : nullptr, d_sched, schedule_bytes(B), stream);
+    if (rc != LTR_OK) return rc;
+    LTR_CUDA(cudaMemcpyAsync(h_loss_out, d_loss, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
+    if (h_dscores_out) LTR_CUDA(cudaMemcpyAsync(h_dscores_out, d_grad, bl * 4, cudaMemcpyDeviceToHost, st));
+    return LTR_OK;
   }
+
+  HostPipe* pipe = nullptr;
+  int rc = host_pipe(&pipe);
   if (rc != LTR_OK) return rc;
-  LTR_CUDA(cudaMemcpyAsync(h_loss_out, d_loss, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
-  if (h_dscores_out)
-    LTR_CUDA(cudaMemcpyAsync(h_dscores_out, d_grad, bl * 4, cudaMemcpyDeviceToHost, st));
+  PipeLock lock(pipe);
+  LTR_CUDA(cudaEventRecord(pipe->start, st));
+  LTR_CUDA(cudaStreamWaitEvent(pipe->in, pipe->start, 0));
+  LTR_CUDA(cudaStreamWaitEvent(pipe->out, pipe->start, 0));
+  int c = 0;
+  for (int b0 = 0; b0 < B; b0 += bc, ++c) {
+    const int nb = B - b0 < bc ? B - b0 : bc;
+    const size_t e0 = static_cast<size_t>(b0) * L, en = static_cast<size_t>(nb) * L;
+    LTR_CUDA(cudaMemcpyAsync(d_scores + e0, h_scores + e0, en * 4, cudaMemcpyHostToDevice, pipe->in));
+    LTR_CUDA(cudaMemcpyAsync(d_rel + e0 * rel_bytes, hr + e0 * rel_bytes, en * rel_bytes, cudaMemcpyHostToDevice,
+                             pipe->in));
+    LTR_CUDA(cudaMemcpyAsync(d_n + static_cast<size_t>(b0) * n_bytes, hn + static_cast<size_t>(b0) * n_bytes,
+                             static_cast<size_t>(nb) * n_bytes, cudaMemcpyHostToDevice, pipe->in));
+    LTR_CUDA(cudaEventRecord(pipe->ev_in[c], pipe->in));
+    LTR_CUDA(cudaStreamWaitEvent(st, pipe->ev_in[c], 0));
+    rc = launch_family(family, mode, d_scores + e0, d_rel + e0 * rel_bytes, rel_bytes,
+                       d_n + static_cast<size_t>(b0) * n_bytes, n_bytes, nb, L, sigma, d_loss + b0,
+                       want_grad ? d_grad + e0 : nullptr, d_sched, schedule_bytes(nb), stream);
+    if (rc != LTR_OK) return rc;
+    LTR_CUDA(cudaEventRecord(pipe->ev_k[c], st));
+    LTR_CUDA(cudaStreamWaitEvent(pipe->out, pipe->ev_k[c], 0));
+    LTR_CUDA(cudaMemcpyAsync(h_loss_out + b0, d_loss + b0, static_cast<size_t>(nb) * 4, cudaMemcpyDeviceToHost,
+                             pipe->out));
+    if (h_dscores_out)
+      LTR_CUDA(cudaMemcpyAsync(h_dscores_out + e0, d_grad + e0, en * 4, cudaMemcpyDeviceToHost, pipe->out));
+  }
+  LTR_CUDA(cudaEventRecord(pipe->done, pipe->out));
+  LTR_CUDA(cudaStreamWaitEvent(st, pipe->done, 0));
+  return LTR_OK;
+}
+
+int ltr_loss_host(int family, int mode, const float* h_scores, const int64_t* h_rel,
+                  const int64_t* h_n, int B, int L, float sigma, float* h_loss_out,
+                  float* h_dscores_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return ltr_loss_host_ex(family, mode, h_scores, h_rel, 8, h_n, 8, B, L, sigma, h_loss_out, h_dscores_out,
+                          h_dscores_out != nullptr, workspace, workspace_bytes, stream);
+}
+
+int ltr_scale_rows_host(float g, const float* d_dscores, float* h_out, int B, int L, float* d_scratch,
+                        void* stream) {
+  if (B < 0 || L < 1) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!d_dscores || !h_out) return LTR_EINVAL;
+  const bool scale = g != 1.0f;
+  if (scale && !d_scratch) return LTR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bl = static_cast<size_t>(B) * L;
+  const float* src = scale ? d_scratch : d_dscores;
+  const int bc = pipe_chunk_queries(B, 4u * static_cast<size_t>(L));
+  if (bc <= 0 || bc >= B) {
+    if (scale) {
+      int rc = launch_scale_rows(nullptr, 0, g, d_dscores, d_scratch, B, L, st);
+      if (rc != LTR_OK) return rc;
+    }
+    LTR_CUDA(cudaMemcpyAsync(h_out, src, bl * 4, cudaMemcpyDeviceToHost, st));
+    return LTR_OK;
+  }
+  HostPipe* pipe = nullptr;
+  int rc = host_pipe(&pipe);
+  if (rc != LTR_OK) return rc;
+  PipeLock lock(pipe);
+  LTR_CUDA(cudaEventRecord(pipe->start, st));
+  LTR_CUDA(cudaStreamWaitEvent(pipe->out, pipe->start, 0));
+  int c = 0;
+  for (int b0 = 0; b0 < B; b0 += bc, ++c) {
+    const int nb = B - b0 < bc ? B - b0 : bc;
+    const size_t e0 = static_cast<size_t>(b0) * L, en = static_cast<size_t>(nb) * L;
+    if (scale) {
+      rc = launch_scale_rows(nullptr, 0, g, d_dscores + e0, d_scratch + e0, nb, L, st);
+      if (rc != LTR_OK) return rc;
+      LTR_CUDA(cudaEventRecord(pipe->ev_k[c], st));
+      LTR_CUDA(cudaStreamWaitEvent(pipe->out, pipe->ev_k[c], 0));
+    }
+    LTR_CUDA(cudaMemcpyAsync(h_out + e0, src + e0, en * 4, cudaMemcpyDeviceToHost, pipe->out));
+  }
+  LTR_CUDA(cudaEventRecord(pipe->done, pipe->out));
+  LTR_CUDA(cudaStreamWaitEvent(st, pipe->done, 0));
   return LTR_OK;
 }
 

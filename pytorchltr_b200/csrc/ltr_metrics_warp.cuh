@@ -91,7 +91,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
         ws.raw_s[j] = scores[base + j];
         ws.raw_y[j] = rel_bytes == 8
                           ? clamp_i64_to_i32(reinterpret_cast<const long long*>(rel)[base + j])
-                          : reinterpret_cast<const int*>(rel)[base + j];
+                          : load_int_clamped(rel, rel_bytes, base + j);
       }
     }
     __syncwarp();
@@ -364,7 +364,6 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
           count_grade(q, j, y);
         }
       } else {
-        const int* sy1 = reinterpret_cast<const int*>(sy);
 #pragma unroll
         for (int q = 0; q < E; ++q) {
           const int j = q * 32 + lane;
@@ -372,7 +371,7 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
           int y = 0;
           if (j < L) {
             s = ss[j];
-            y = sy1[j];
+            y = load_int_clamped(sy, rel_bytes, j);
           }
           key[q] = j < nb ? desc_key_f32(s) : kPadKey;
           raw_y[j] = y;
@@ -393,7 +392,7 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
         if (j < L) {
           s = scores[base + j];
           y = rel_bytes == 8 ? clamp_i64_to_i32(reinterpret_cast<const long long*>(rel)[base + j])
-                             : reinterpret_cast<const int*>(rel)[base + j];
+                             : load_int_clamped(rel, rel_bytes, base + j);
         }
         key[q] = j < nb ? desc_key_f32(s) : kPadKey;
         raw_y[j] = y;   // grades wait in shared memory (keeps the registers for loads in flight)

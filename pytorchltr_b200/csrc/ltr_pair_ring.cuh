@@ -30,6 +30,9 @@
 
 namespace ltr {
 
+#ifndef LTR_RING_MIN_CTAS
+#define LTR_RING_MIN_CTAS 3   // resident CTAs per SM the register allocation aims at (A-B timing: -DLTR_RING_MIN_CTAS=4)
+#endif
 constexpr int kRingWarps = 8;
 constexpr int kRingMaxL = 1024;
 
@@ -462,7 +465,7 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
         __syncwarp();
       }
     }
-    lacc += (FACTORED && tw_winner(TW) ? 2.0f : 1.0f) * (run_l + acc.loss());
+    lacc += run_l + acc.loss();
   }
   return lacc;
 }
@@ -501,7 +504,7 @@ __device__ __forceinline__ float ring_pairs(const RingSmem& m, const PairTables&
 }
 
 template <int TW>
-__global__ void __launch_bounds__(kRingWarps * 32, 3)
+__global__ void __launch_bounds__(kRingWarps * 32, LTR_RING_MIN_CTAS)
 pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                  int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,
@@ -544,7 +547,8 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
   // ---- query schedule: the first query of every CTA is static, the following ones come from a
   // device-wide queue.  `order` (optional) lists the queries by decreasing size: the long ones
   // start first and the tail of the launch is made of short ones -----------------------------------
-  const bool dynamic = gridDim.x < static_cast<unsigned int>(B);
+  // queue == nullptr (launch captured into a CUDA graph without a caller-owned workspace): static stride
+  const bool dynamic = queue != nullptr && gridDim.x < static_cast<unsigned int>(B);
   int b = static_cast<int>(blockIdx.x) < B ? static_cast<int>(order ? order[blockIdx.x] : blockIdx.x) : -1;
   if (tma && threadIdx.x == 0 && b >= 0) issue_row(b);
 
@@ -554,6 +558,9 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       int b_next = -1;
       if (dynamic) {
         const unsigned int qn = gridDim.x + atomicAdd(queue, 1u);
+        if (qn < static_cast<unsigned int>(B)) b_next = static_cast<int>(order ? order[qn] : qn);
+      } else {
+        const unsigned int qn = blockIdx.x + (iter + 1) * gridDim.x;
         if (qn < static_cast<unsigned int>(B)) b_next = static_cast<int>(order ? order[qn] : qn);
       }
       m.hist[38] = b_next;
@@ -661,7 +668,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
     const float mid = 0.5f * (smax + smin);
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
-    // factored winner-by-relevance losses: padded columns carry the smallest valid (halved) weight, so that
+    // factored winner-by-relevance losses: padded columns carry the smallest valid weight, so that
     // they lose every pair (pair_fact).  Grades 0..31 give gains >= 0: the padding value 0 is small enough.
     float gpad = 0.0f;
     if constexpr (tw_winner(TW)) {
@@ -669,7 +676,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         float lmin = INFINITY;
         for (int j = threadIdx.x; j < nb; j += blockDim.x) {
           const int y = m.raw_y[j];
-          lmin = fminf(lmin, 0.5f * (TW == TW_DELTA ? gain_of_grade(y) * inv_max_dcg : static_cast<float>(y)));
+          lmin = fminf(lmin, TW == TW_DELTA ? gain_of_grade(y) * inv_max_dcg : static_cast<float>(y));
         }
         gpad = cta_min(lmin, m.red);
         if (!(gpad < INFINITY)) gpad = 0.0f;

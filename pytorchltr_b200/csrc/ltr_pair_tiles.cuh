@@ -15,10 +15,11 @@
 // are added to a warp-private shared array with one vector read-modify-write (every lane
 // touches a different chunk, so there are no conflicts and no atomics).
 //
-// Pair math of the factored form (pair_fact): per unordered pair 1.5 MUFU + 11 FP32 lane-operations,
-// issued as packed f32x2 instructions on TWO adjacent columns at a time (FFMA2 / FADD2 / FMUL2: abs,
-// negation and the broadcast of a row value are operand modifiers, so the 11 operations cost 5.5
-// issue slots per pair), branch-free in the winner.
+// Pair math of the factored form (pair_fact): per unordered pair 1.5 MUFU + 10.5 FP32 lane-operations
+// + 2 max on the alu pipe, issued as packed f32x2 instructions on TWO adjacent columns at a time
+// (FFMA2 / FADD2 / FMUL2: abs, negation, the broadcast of a row value and the swap of the two halves
+// are operand modifiers), branch-free in the winner: 178 SASS instructions per 16 pairs per lane
+// (measured ceilings of the pipes: tools/issue_peak.cu, profiles/issue_peaks.json).
 // exp(-sigma (s_i - s_j)) is FACTORED as a_i * b_j with a_i = exp(-sigma (s_i - mid)), b_j = exp(+sigma (s_j - mid)) computed once per
 // document (double-precision exponent, so the product is good to a few float32 ulps); the pair
 // then needs only rcp and lg2 on the MUFU pipe, and the two pairs of a packed instruction share ONE
@@ -28,16 +29,17 @@
 // (e = sigma (s - mid) log2 e, so e_i - e_j = -lg2 q).  The factored form needs
 // sigma * (max - min) * log2 e <= kFactoredRange so that p_0 p_1 stays finite; queries outside that
 // range take the stable form exp(-|x|) (3 MUFU, scalar) instead.
-// The winner-by-relevance losses work on HALVED weights and exponents (h = ws / 2, e' = e / 2; the
-// tables and factors are stored halved, the loss is doubled at the end -- all exact in binary):
-//     a = |h|:   loss / 2 += a lg2(p) + (a - h)(e'_i - e'_j),   row += a (2 r - 1) - h,   column -= the same.
+// Winner-by-relevance losses, ws = signed pair weight (> 0 when the row wins), w = |ws|:
+//     loss += w lg2(p) + max(-ws, 0) (e_i - e_j),   row += w r - max(ws, 0),   column -= the same
+// (9 packed FP32 operations; the two max run on the alu pipe, beside the FP32 datapath).
 //
 // Padding: a padded ROW carries a = 0 (so p = 1, lg2 = 0, r = 1 exactly: both pairs of its packed
-// instruction have p = 1) and the gain +BIG (it "wins" everything: a - h = 0); a padded COLUMN carries
-// b = 0 and the smallest gain of the query, min(0, min_valid G) (it loses everything: a - h = 0 and
-// a lg2(1) = 0).  Every pair that involves padding contributes an exact zero to the loss; a padded
-// column that shares its reciprocal with a valid one sees r = 1 +- 1 ulp instead of 1 and leaves
-// a (2 r - 2) ~ 1e-7 of ONE pair weight in that row's gradient (once per row at most).
+// instruction have p = 1) and the gain +BIG (it "wins" everything: max(-ws, 0) = 0, w r - max(ws, 0) = 0);
+// a padded COLUMN carries b = 0 and the smallest gain of the query's valid documents (it loses
+// everything: max(-ws, 0) = 0 and w lg2(1) = 0).  Every pair that involves padding contributes an exact
+// zero to the loss; a padded column that shares its reciprocal with a valid one sees r = 1 +- 1 ulp
+// instead of 1 and leaves w (r - 1) ~ 1e-7 of ONE pair weight in that row's gradient (once per row at
+// most: only the last chunk of a query mixes valid and padded columns).
 // (Stable form: padding is a document of gain 0 scored -1e30, whose pairs evaluate to exp(-1e30) = 0.)
 //
 // delta_|i-j| (LambdaNDCGLoss2, pairwise_lambda.py:206-211) only depends on the rank distance:
@@ -53,7 +55,7 @@ namespace ltr {
 constexpr float kFactoredRange = 60.0f;    // max |sigma| * (max - min) * log2(e): p_0 * p_1 <= 2^121 stays finite
 constexpr float kBigGain = 1.0e30f;
 
-// winner decided by relevance (halved weights / exponents in the factored form, see pair_fact)
+// winner decided by relevance (pair_fact)
 __host__ __device__ constexpr bool tw_winner(int tw) { return tw == 0 || tw == 1 || tw == 2; }   // UNIT, DIFF, DELTA
 
 // Per-document factors of one query in shared memory, RANK order, structure of arrays so that
@@ -185,8 +187,10 @@ __device__ __forceinline__ float vmul(float a, float b) { return a * b; }
 __device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float vclamp_half(float a) { return fminf(fmaxf(a, -0.5f), 0.5f); }
-__device__ __forceinline__ float2 vclamp_half(float2 a) { return make_float2(vclamp_half(a.x), vclamp_half(a.y)); }
+__device__ __forceinline__ float vclamp_one(float a) { return fminf(fmaxf(a, -1.0f), 1.0f); }
+__device__ __forceinline__ float2 vclamp_one(float2 a) { return make_float2(vclamp_one(a.x), vclamp_one(a.y)); }
+__device__ __forceinline__ float vrelu(float a) { return fmaxf(a, 0.0f); }
+__device__ __forceinline__ float2 vrelu(float2 a) { return make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)); }
 __device__ __forceinline__ float vhsum(float a) { return a; }
 __device__ __forceinline__ float vhsum(float2 a) { return a.x + a.y; }
 // p -> (1 / p, lg2 p); the two pairs of the packed form share one reciprocal
@@ -196,14 +200,12 @@ __device__ __forceinline__ void rcp_lg2(float p, float& r, float& lg) {
 }
 __device__ __forceinline__ void rcp_lg2(float2 p, float2& r, float2& lg) {
   const float R = rcp_approx(p.x * p.y);
-  r = make_float2(R * p.y, R * p.x);
+  r = __fmul2_rn(make_float2(R, R), make_float2(p.y, p.x));   // one FMUL2: broadcast R, swapped halves of p
   lg = make_float2(lg2_approx(p.x), lg2_approx(p.y));
 }
 
-// Factored pair(s): row (ra, re, rg, rv) against column(s) (cx = b_j, ce, cg); dwh = halved delta
-// window value(s) (TW_DELTA).  Winner-by-relevance losses: re / ce hold e / 2, rg / cg half weights
-// (TW_DELTA: G; TW_DIFF / TW_UNIT: rel / 2) and lacc accumulates loss / 2.  TW_TWO: plain weights and
-// exponents, rv = validity of the row (1 or 0).  racc / cacc receive -lambda' / +lambda'.
+// Factored pair(s): row (ra, re, rg, rv) against column(s) (cx = b_j, ce, cg); dwh = delta window
+// value(s) (TW_DELTA).  TW_TWO: rv = validity of the row (1 or 0).  racc / cacc receive -lambda' / +lambda'.
 template <int TW, typename V>
 __device__ __forceinline__ void pair_fact(V ra, V re, V rg, V rv, V cx, V ce, V cg, V dwh, V& lacc, V& racc,
                                           V& cacc) {
@@ -220,19 +222,20 @@ __device__ __forceinline__ void pair_fact(V ra, V re, V rg, V rv, V cx, V ce, V 
     racc = vadd(racc, gc);
     cacc = vadd(cacc, vneg(gc));
   } else {
+    // ws = signed weight (> 0: the row wins), w = |ws|, K = max(ws, 0), D = max(-ws, 0) = K - ws:
+    //   loss += w lg2(p) + D (e_i - e_j),   row += w r - K,   column -= the same.
+    // K and D are max operations: they run on the alu pipe beside the packed FP32 datapath.
     const V gd = vadd(rg, vneg(cg));
-    V h;
-    if constexpr (TW == TW_DELTA) h = vmul(dwh, gd);
-    else if constexpr (TW == TW_DIFF) h = gd;
-    else h = vclamp_half(gd);                   // integer grades, halved: sign(gd) / 2
-    const V a = vabs(h);
+    V ws;
+    if constexpr (TW == TW_DELTA) ws = vmul(dwh, gd);
+    else if constexpr (TW == TW_DIFF) ws = gd;
+    else ws = vclamp_one(gd);                   // integer grades: sign(gd)
     const V p = vfma(ra, cx, vsplat<V>(1.0f));
     V r, lg;
     rcp_lg2(p, r, lg);
-    lacc = vfma(a, lg, lacc);
-    lacc = vfma(vadd(a, vneg(h)), vadd(re, vneg(ce)), lacc);
-    const V t = vfma(r, vsplat<V>(2.0f), vsplat<V>(-1.0f));
-    const V v = vfma(a, t, vneg(h));
+    lacc = vfma(vabs(ws), lg, lacc);
+    lacc = vfma(vrelu(vneg(ws)), vadd(re, vneg(ce)), lacc);
+    const V v = vfma(vabs(ws), r, vneg(vrelu(ws)));
     racc = vadd(racc, v);
     cacc = vadd(cacc, vneg(v));
   }
@@ -249,9 +252,8 @@ __device__ __forceinline__ void doc_factors(float s, float mid, float k_hi, floa
   const float el = fmaf(c, k_lo, fmaf(c, k_hi, -eh)) * kLn2;   // (c k - eh) ln 2
   fa = ex2_approx(-eh) * (1.0f - el);
   fb = ex2_approx(eh) * (1.0f + el);
-  constexpr float half = tw_winner(TW) ? 0.5f : 1.0f;
-  fe = half * eh;
-  fg = half * w;
+  fe = eh;
+  fg = w;
 }
 
 // Accumulators of one lane over a run of ring steps: packed halves (even / odd column of a pair)
@@ -279,7 +281,7 @@ struct RowAcc {
 };
 
 // The R x R pairs of one row chunk against one column chunk (factored form), columns two at a time.
-//   dwin : halved delta window of this chunk distance, dwin[k - r + R - 1] for row r and column k (TW_DELTA)
+//   dwin : delta window of this chunk distance, dwin[k - r + R - 1] for row r and column k (TW_DELTA)
 //   tc   : column gradients of this step, tc[k] += ...
 template <int TW, int R>
 __device__ __forceinline__ void chunk_pairs(const float (&ra)[R], const float (&re)[R], const float (&rg)[R],
@@ -392,7 +394,6 @@ __device__ __forceinline__ float ring_pass_fact(const PairSoA& it, float* __rest
                                                 const float* __restrict__ wtab, int C, int n, int lane,
                                                 float (&racc)[R]) {
   constexpr bool kFast = S == 4;
-  constexpr float kLossScale = TW == TW_TWO ? 1.0f : 2.0f;   // halved weights and exponents (pair_fact)
   const bool active = lane < C;
   const int me = active ? lane : 0;
   float ra[R], re[R], rg[R], rv[R];
@@ -474,7 +475,7 @@ __device__ __forceinline__ float ring_pass_fact(const PairSoA& it, float* __rest
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) racc[r] = active ? acc.row(r) + tr[r] : 0.0f;
-  return active ? kLossScale * (acc.loss() + tl) : 0.0f;
+  return active ? acc.loss() + tl : 0.0f;
 }
 
 // All-pairs pass over one "ring" of C <= 32 chunks of R ranks held by one warp (C*R >= n).
@@ -660,7 +661,7 @@ __device__ __forceinline__ float tile_pass(const PairSoA& it, int row_base, int 
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) racc[r] = acc.row(r);
-    return (tw_winner(TW) ? 2.0f : 1.0f) * acc.loss();
+    return acc.loss();
   } else {
     const float* colx = it.a;
     float ra[R], re[R], rg[R];

@@ -134,12 +134,32 @@ __global__ void __launch_bounds__(1024) init_pair_tables_kernel(PairTables* __re
     k = k < 0 ? -k : k;
     t->wtab[R - 1][rem] = t->delta[k];
   }
-  if (threadIdx.x == 0) {
-    double acc = 0.0;
-    for (int r = 0; r <= LTR_MAX_LIST_SIZE; ++r) {
-      t->inv_disc_prefix[r] = acc;
-      acc += 1.0 / static_cast<double>(t->disc[r]);
-    }
+  // S[p] = sum_{r<p} 1 / D(r) in double: every thread owns kPer consecutive entries, the thread totals are
+  // scanned through shared memory
+  constexpr int kPer = (LTR_MAX_LIST_SIZE + 1 + 1023) / 1024;
+  __shared__ double tot[1024];
+  const int first = threadIdx.x * kPer;
+  double local[kPer];
+  double run = 0.0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    local[j] = run;                                   // exclusive within the thread
+    const int r = first + j;
+    if (r <= LTR_MAX_LIST_SIZE) run += 1.0 / static_cast<double>(t->disc[r]);
+  }
+  tot[threadIdx.x] = run;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const double add = threadIdx.x >= off ? tot[threadIdx.x - off] : 0.0;
+    __syncthreads();
+    tot[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const double base = threadIdx.x > 0 ? tot[threadIdx.x - 1] : 0.0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int r = first + j;
+    if (r <= LTR_MAX_LIST_SIZE) t->inv_disc_prefix[r] = base + local[j];
   }
 }
 
@@ -194,7 +214,8 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
   // (optional) lists the queries by decreasing size, so the long ones start first and the tail of
   // the launch is made of short ones (longest-processing-time-first list scheduling) --------------
   const unsigned int total_warps = gridDim.x * kWarpsPerCta;
-  const bool dynamic = total_warps < static_cast<unsigned int>(B);   // else: one query per warp, no queue traffic
+  // queue == nullptr (launch captured into a CUDA graph without a caller-owned workspace): static stride
+  const bool dynamic = queue != nullptr && total_warps < static_cast<unsigned int>(B);   // else no queue traffic
   unsigned int q = blockIdx.x * kWarpsPerCta + warp;
 
   while (q < static_cast<unsigned int>(B)) {
@@ -217,8 +238,15 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         const longlong2 r0 = rp[0], r1 = rp[1];
         yv[0] = clamp_i64_to_i32(r0.x); yv[1] = clamp_i64_to_i32(r0.y);
         yv[2] = clamp_i64_to_i32(r1.x); yv[3] = clamp_i64_to_i32(r1.y);
-      } else {
+      } else if (rel_bytes == 4) {
         const int4 r4 = *reinterpret_cast<const int4*>(reinterpret_cast<const int*>(rel) + base + lane * kWarpE);
+        yv[0] = r4.x; yv[1] = r4.y; yv[2] = r4.z; yv[3] = r4.w;
+      } else if (rel_bytes == 2) {
+        const short4 r4 = *reinterpret_cast<const short4*>(reinterpret_cast<const short*>(rel) + base + lane * kWarpE);
+        yv[0] = r4.x; yv[1] = r4.y; yv[2] = r4.z; yv[3] = r4.w;
+      } else {
+        const uchar4 r4 =
+            *reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(rel) + base + lane * kWarpE);
         yv[0] = r4.x; yv[1] = r4.y; yv[2] = r4.z; yv[3] = r4.w;
       }
     } else {
@@ -487,7 +515,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       }
     }
     __syncwarp();
-    if (!dynamic) break;
+    if (!dynamic) { q += total_warps; continue; }
     q = __shfl_sync(0xffffffffu, b_next, 0);
   }
 

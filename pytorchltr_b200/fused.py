@@ -20,6 +20,12 @@ from pytorchltr_b200 import _lib, _ops
 class _LinearListNet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, weight, bias, relevance, n):
+        if ctx.needs_input_grad[0]:
+            # the fused kernel never forms d loss / d features (B x L x F): returning None would silently
+            # starve an upstream encoder of its gradient
+            raise NotImplementedError(
+                "linear_listnet is differentiable with respect to weight and bias only; `features` requires "
+                "grad (it comes from a trainable module): use torch.nn.Linear + ListNetLoss for that model")
         if not features.is_cuda:
             raise RuntimeError("linear_listnet computes on CUDA only (sm_100a kernels, no CPU fallback)")
         if features.dim() != 3:
@@ -38,10 +44,7 @@ class _LinearListNet(torch.autograd.Function):
             relevance = relevance.reshape(B, L)
         if tuple(relevance.shape) != (B, L):
             raise ValueError(f"relevance {tuple(relevance.shape)} does not match features {(B, L, F)}")
-        y = relevance.detach()
-        if y.dtype not in (torch.int64, torch.int32):
-            y = y.to(torch.int64)
-        y = y.to(dev).contiguous()
+        y = _ops._integer_labels(relevance.detach()).to(dev).contiguous()
         if n.dim() != 1 or n.shape[0] != B:
             raise ValueError(f"n must have shape ({B},), got {tuple(n.shape)}")
         nn_ = n.detach()

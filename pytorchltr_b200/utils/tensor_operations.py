@@ -43,12 +43,21 @@ def rank_by_score(scores: _torch.FloatTensor, n: _torch.LongTensor,
                   generator: Optional[_torch.Generator] = None) -> _torch.LongTensor:
     """Ranks documents by descending score with padded documents last (reference :48-64).
 
-    Runs ``ltr_rank_by_score``.  Ties are broken lowest-index-first and padded documents
-    keep index order; ``generator`` is accepted for signature compatibility and ignored
-    (the reference draws a random tie-breaking permutation from it).
+    Runs ``ltr_rank_by_score``.  By default ties are broken lowest-index-first and padded documents
+    keep index order (deterministic, no RNG state consumed).  Passing a ``generator`` opts into the
+    reference's random tie-break (one random column permutation per call drawn from it, :43-45):
+    the columns are permuted before the kernel and the indices mapped back, so that a constant or
+    degenerate scorer is neither rewarded nor penalised by the document order of the file.
     """
-    del generator
-    return _ops.rank_by_score(scores, n)
+    if generator is None:
+        return _ops.rank_by_score(scores, n)
+    if scores.dim() == 3:
+        scores = scores.reshape(scores.shape[0], scores.shape[1])
+    L = scores.shape[1]
+    perm = _torch.randperm(L, device=scores.device, generator=generator)
+    masked = mask_padded_values(scores.to(_torch.float32), n, mask_value=float("-inf"))
+    full = _torch.full_like(n, L)
+    return perm[_ops.rank_by_score(masked.index_select(1, perm), full)]
 
 
 def rank_by_plackettluce(scores: _torch.FloatTensor, n: _torch.LongTensor,

@@ -56,7 +56,10 @@ def test_public_surface_mirrors_reference():
                  "LambdaARPLoss2", "LambdaNDCGLoss1", "LambdaNDCGLoss2", "ListNetLoss"):
         cls = getattr(p.loss, name)
         assert issubclass(cls, torch.nn.Module)
-        assert list(inspect.signature(cls.forward).parameters) == ["self", "scores", "relevance", "n"]
+        params = inspect.signature(cls.forward).parameters
+        assert list(params)[:4] == ["self", "scores", "relevance", "n"]
+        # extensions beyond the reference's signature must be optional (loss_sum: distributed epilogue)
+        assert all(q.default is not inspect.Parameter.empty for q in list(params.values())[4:])
     assert p.loss.PairwiseLogisticLoss(sigma=2.0).sigma == 2.0
     assert p.loss.LambdaNDCGLoss2().sigma == 1.0
     assert issubclass(p.loss.PairwiseDCGHingeLoss, p.loss.PairwiseHingeLoss)

@@ -286,7 +286,7 @@ def test_cabi_error_codes_and_host_entry():
     st = torch.cuda.current_stream().cuda_stream
     args = (ds.data_ptr(), dy.data_ptr(), 8, dn.data_ptr(), 8, B, L, 1.0, loss.data_ptr(), None, None, None, st)
     assert lib.ltr_lambda(9, *args) == -1                                   # bad mode
-    assert lib.ltr_lambda(3, ds.data_ptr(), dy.data_ptr(), 2, *args[3:]) == -1   # bad dtype width
+    assert lib.ltr_lambda(3, ds.data_ptr(), dy.data_ptr(), 3, *args[3:]) == -1   # bad dtype width (8, 4, 2, 1 are valid)
     big = (ds.data_ptr(), dy.data_ptr(), 8, dn.data_ptr(), 8, B, _lib.MAX_LIST_SIZE + 1, 1.0,
            loss.data_ptr(), None, None, None, st)
     assert lib.ltr_lambda(3, *big) == -2                                    # unsupported L
