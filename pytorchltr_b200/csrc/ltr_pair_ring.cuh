@@ -668,15 +668,15 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
     const float mid = 0.5f * (smax + smin);
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
-    // factored winner-by-relevance losses: padded columns carry the smallest valid weight, so that
-    // they lose every pair (pair_fact).  Grades 0..31 give gains >= 0: the padding value 0 is small enough.
+    // winner-by-relevance losses: padded columns carry the smallest valid weight, so that they lose (or tie)
+    // every pair, in the factored and in the stable form.  Grades 0..31 give gains >= 0: the padding value 0 is small enough.
     float gpad = 0.0f;
     if constexpr (tw_winner(TW)) {
-      if (factored && !(TW == TW_DELTA && m.hist[32] == 0)) {
+      if (!(TW == TW_DELTA && m.hist[32] == 0)) {
         float lmin = INFINITY;
         for (int j = threadIdx.x; j < nb; j += blockDim.x) {
           const int y = m.raw_y[j];
-          lmin = fminf(lmin, TW == TW_DELTA ? gain_of_grade(y) * inv_max_dcg : static_cast<float>(y));
+          lmin = fminf(lmin, TW == TW_DELTA ? gain_of_grade(y) * fabsf(inv_max_dcg) : static_cast<float>(y));
         }
         gpad = cta_min(lmin, m.red);
         if (!(gpad < INFINITY)) gpad = 0.0f;
@@ -695,7 +695,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
         const float s = m.raw_s[d];
         const int y = m.raw_y[d];
         float w;
-        if constexpr (TW == TW_DELTA) w = gain_of_grade(y) * inv_max_dcg;
+        if constexpr (TW == TW_DELTA) w = gain_of_grade(y) * fabsf(inv_max_dcg);   // |G_i - G_j|: :214-216
         else if (TW == TW_TWO && variant != 0) w = gain_of_grade(y) * inv_max_dcg / tb.disc[p];
         else w = static_cast<float>(y);
         if constexpr (TW == TW_TWO) diag += w;   // the pairs (i, i): w_i * log2(1 + e^0)

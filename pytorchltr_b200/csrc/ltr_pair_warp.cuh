@@ -415,7 +415,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     float diag = 0.0f;   // ARP1 / NDCG1 also count the pairs (i, i): w_i * log2(1 + e^0) = w_i
     {
       float fa[kWarpE], fb[kWarpE], fe[kWarpE], fg[kWarpE];
-      float gmin = INFINITY;   // factored winner-by-relevance losses: padded columns carry the smallest valid gain
+      float gmin = INFINITY;   // winner-by-relevance losses: padded columns carry the smallest valid weight
 #pragma unroll
       for (int j = 0; j < kWarpE; ++j) {
         const int p = lane * Rq + j;
@@ -426,7 +426,7 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
           const float sd = ws.raw_s[d];
           const int yd = ws.raw_y[d];
           float w;
-          if constexpr (TW == TW_DELTA) w = gain_of_grade(yd) * inv_max_dcg;
+          if constexpr (TW == TW_DELTA) w = gain_of_grade(yd) * fabsf(inv_max_dcg);   // |G_i - G_j|: :214-216
           else if (TW == TW_TWO && variant != 0) w = gain_of_grade(yd) * inv_max_dcg / tb.disc[p];
           else w = static_cast<float>(yd);
           if constexpr (TW == TW_TWO) diag += w;
@@ -435,20 +435,20 @@ pair_warp_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
             fa[j] = sd;                          // raw score: the hinge works on s_i - s_j itself
           } else if (factored) {
             doc_factors<TW>(sd, mid, k_hi, k_lo, w, fa[j], fb[j], fe[j], fg[j]);
-            gmin = fminf(gmin, fg[j]);
+            gmin = fminf(gmin, w);
           } else {
             fa[j] = sigma * sd;
+            gmin = fminf(gmin, w);
           }
         }
       }
       if constexpr (tw_winner(TW)) {
-        if (factored) {
-          gmin = -warp_max(-gmin);
-          if (!(gmin < INFINITY)) gmin = 0.0f;
+        // padded columns carry the smallest valid weight: they lose (or tie) every pair, in both forms
+        gmin = -warp_max(-gmin);
+        if (!(gmin < INFINITY)) gmin = 0.0f;
 #pragma unroll
-          for (int j = 0; j < kWarpE; ++j)
-            if (!(j < Rq && lane * Rq + j < nb)) fg[j] = gmin;
-        }
+        for (int j = 0; j < kWarpE; ++j)
+          if (!(j < Rq && lane * Rq + j < nb)) fg[j] = gmin;
       }
       __syncwarp();   // raw_s / raw_y / rank2doc fully consumed: they are reused below
       const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);

@@ -36,7 +36,12 @@ def test_narrow_relevance_is_bit_identical_to_int64(mode, L, dtype):
     s, y, n = make_batch(11 + L, 9, L)
     ref = _cuda_loss_grad(mode, s, torch.as_tensor(y), n)
     got = _cuda_loss_grad(mode, s, torch.as_tensor(y).to(dtype), n)
-    assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1])
+    if L > 1024 and mode in ("ndcg2", "arp1", "logistic"):
+        # the 128 x 128 tile kernel merges its tiles with shared float atomics: not bit-reproducible
+        _assert_parity(got[0].astype(np.float64), got[1].astype(np.float64), ref[0].astype(np.float64),
+                       ref[1].astype(np.float64))
+    else:
+        assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1])
 
 
 @pytest.mark.parametrize("L", (37, 200, 700))
@@ -63,7 +68,10 @@ def test_negative_grades_with_padding():
         for mode in ("arp2", "logistic", "ndcg2"):
             loss, grad = _run_cuda(mode, s, y, n)
             rl, rg = _oracle_loss(mode, s, y, n)
-            _assert_parity(loss, grad, rl, rg, loss_rel=2e-5)
+            try:
+                _assert_parity(loss, grad, rl, rg, loss_rel=2e-5)
+            except AssertionError as e:
+                raise AssertionError(f"L={L} mode={mode} n={n.tolist()}: {e}") from None
 
 
 def test_fractional_labels_are_rejected():
