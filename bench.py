@@ -722,7 +722,8 @@ def measure_config(args, name, cfg, rank, world, dev, steps, warmup, windows, sa
             for i in range(pool_n):
                 g = torch.cuda.CUDAGraph()
                 pool[i][0].grad = None
-                with torch.cuda.graph(g):
+                # thread_local: NCCL's watchdog thread may touch the device while a collective is captured
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     step(i)
                 graphs.append(g)
             launch = "cuda_graph (collective captured)" if world > 1 else "cuda_graph"

@@ -1142,7 +1142,9 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
                                                            kTopkWarps * 32, 0));                            \
     if (per_sm < 1) return LTR_EUNSUPPORTED;                                                                \
     const long long cap = static_cast<long long>(per_sm) * di.sms;                                          \
-    const int grid = static_cast<int>(want < cap ? want : cap);                                             \
+    /* every warp the same number of queries: no second partial wave */                                     \
+    const long long rounds = (want + cap - 1) / cap;                                                        \
+    const int grid = static_cast<int>((want + rounds - 1) / rounds);                                        \
     topk_metrics_warp_kernel<E><<<grid, kTopkWarps * 32, 0, st>>>(metric, scores, rel, rel_bytes, n, n_bytes, B, \
                                                                   L, k, exp_gain, tma, out, out_ld, tabs);  \
   } while (0)
@@ -1165,20 +1167,32 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
     return LTR_OK;
   }
   if (L <= 256 && !force_generic()) {
-    // short lists: one warp per query, in-register ranking
+    // short lists: one warp per query, in-register ranking, double-buffered TMA row staging
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const PairTables* tabs = nullptr;
     rc = pair_tables(st, &tabs);
     if (rc != LTR_OK) return rc;
+    int tma = rows_tma_ok(scores, rel, rel_bytes, L);
+    if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
     const long long want = (static_cast<long long>(B) + kMetricWarps - 1) / kMetricWarps;
-    const long long cap = static_cast<long long>(di.sms) * 12;
-    const int grid = static_cast<int>(want < cap ? want : cap);
-    if (L <= 128)
-      rank_metrics_warp_kernel<4><<<grid, kMetricWarps * 32, 0, st>>>(
-          metric, scores, rel, rel_bytes, n, n_bytes, B, L, k, exp_gain, out, out_ld, tabs);
-    else
-      rank_metrics_warp_kernel<8><<<grid, kMetricWarps * 32, 0, st>>>(
-          metric, scores, rel, rel_bytes, n, n_bytes, B, L, k, exp_gain, out, out_ld, tabs);
+#define LTR_RANKM_LAUNCH(E)                                                                                    \
+  do {                                                                                                        \
+    int per_sm = 0;                                                                                           \
+    LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_metrics_warp_kernel<E>,              \
+                                                           kMetricWarps * 32, 0));                            \
+    if (per_sm < 1) return LTR_EUNSUPPORTED;                                                                  \
+    const long long cap = static_cast<long long>(per_sm) * di.sms;                                            \
+    /* every warp the same number of queries: no second partial wave */                                       \
+    const long long rounds = (want + cap - 1) / cap;                                                          \
+    const int grid = static_cast<int>((want + rounds - 1) / rounds);                                          \
+    rank_metrics_warp_kernel<E><<<grid, kMetricWarps * 32, 0, st>>>(metric, scores, rel, rel_bytes, n, n_bytes, B, L, \
+                                                                    k, exp_gain, tma, out, out_ld, tabs);     \
+  } while (0)
+    if (L <= 32) LTR_RANKM_LAUNCH(1);
+    else if (L <= 64) LTR_RANKM_LAUNCH(2);
+    else if (L <= 128) LTR_RANKM_LAUNCH(4);
+    else LTR_RANKM_LAUNCH(8);
+#undef LTR_RANKM_LAUNCH
     LTR_CUDA(cudaGetLastError());
     return LTR_OK;
   }

@@ -17,40 +17,96 @@ struct MetricScratch {
   int raw_y[32 * E];
 };
 
+// Exact (32-bit key, document) order of two neighbouring ranks: true when (ka, da) must come after (kb, db).
+__device__ __forceinline__ bool key_doc_after(uint32_t ka, int da, uint32_t kb, int db) {
+  return ka > kb || (ka == kb && da > db);
+}
+
 // Ranks the valid documents of one row by descending score (ties: lowest index first).
 // On return position p = lane * E + r < nb holds document doc[r]; positions >= nb are the padded
 // documents in index order, i.e. document p itself (not produced here).
+// The network sorts one 32-bit word per document: the top bits of the score key with the document index
+// in the low log2(32 E) bits.  That order is exact unless two neighbouring ranks share their key bits;
+// only then the exact keys are fetched again (raw_s) and the neighbours are put right by odd-even
+// transposition rounds (runs of equal key bits are short: scores closer than 2^-15 relative), with the
+// exact 64-bit network as the last resort for pathological inputs.
 template <int E>
 __device__ __forceinline__ void warp_rank_by_score(const float (&sv)[E], int nb, int lane,
                                                    const float* __restrict__ raw_s, int (&doc)[E]) {
   constexpr uint32_t kIdxMask = 32u * E - 1u;
-  uint32_t ekey[E], pk[E];
+  uint32_t pk[E];
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const int j = lane * E + r;
-    ekey[r] = j < nb ? desc_key_f32(sv[r]) : kPadKey;
-    pk[r] = (ekey[r] & ~kIdxMask) | static_cast<uint32_t>(j);
+    const uint32_t ekey = j < nb ? desc_key_f32(sv[r]) : kPadKey;
+    pk[r] = (ekey & ~kIdxMask) | static_cast<uint32_t>(j);
   }
   warp_bitonic_sort32<E>(pk, lane);
-  uint64_t xk[E];
+  const uint32_t pk_next = __shfl_down_sync(0xffffffffu, pk[0], 1);
+  bool ambiguous = false;
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     doc[r] = static_cast<int>(pk[r] & kIdxMask);
-    const int p = lane * E + r;
-    xk[r] = pack_key(p < nb ? desc_key_f32(raw_s[doc[r]]) : kPadKey, doc[r]);
+    const uint32_t nxt = r + 1 < E ? pk[(r + 1) % E] : pk_next;
+    ambiguous = ambiguous || (((pk[r] ^ nxt) <= kIdxMask) && (lane * E + r + 1 < nb));
   }
-  const uint64_t next0 = __shfl_down_sync(0xffffffffu, xk[0], 1);
-  bool bad = lane < 31 && xk[E - 1] > next0;
+  if (!__any_sync(0xffffffffu, ambiguous)) return;
+
+  uint32_t ek[E];
 #pragma unroll
-  for (int r = 0; r + 1 < E; ++r) bad = bad || (xk[r] > xk[r + 1]);
-  if (__any_sync(0xffffffffu, bad)) {
-    // two scores closer than the packed key can resolve: exact 64-bit network
+  for (int r = 0; r < E; ++r) ek[r] = lane * E + r < nb ? desc_key_f32(raw_s[doc[r]]) : kPadKey;
+  for (int round = 0; round < 8; ++round) {
+    bool swapped = false;
+    // even phase: (0,1), (2,3), ... inside the lane
 #pragma unroll
-    for (int r = 0; r < E; ++r) xk[r] = pack_key(ekey[r], lane * E + r);
-    warp_bitonic_sort64<E>(xk, lane);
+    for (int r = 0; r + 1 < E; r += 2) {
+      if (key_doc_after(ek[r], doc[r], ek[r + 1], doc[r + 1])) {
+        const uint32_t tk = ek[r]; ek[r] = ek[r + 1]; ek[r + 1] = tk;
+        const int td = doc[r]; doc[r] = doc[r + 1]; doc[r + 1] = td;
+        swapped = true;
+      }
+    }
+    // odd phase: (1,2), (3,4), ... inside the lane and (E-1 of this lane, 0 of the next)
 #pragma unroll
-    for (int r = 0; r < E; ++r) doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
+    for (int r = 1; r + 1 < E; r += 2) {
+      if (key_doc_after(ek[r], doc[r], ek[r + 1], doc[r + 1])) {
+        const uint32_t tk = ek[r]; ek[r] = ek[r + 1]; ek[r + 1] = tk;
+        const int td = doc[r]; doc[r] = doc[r + 1]; doc[r + 1] = td;
+        swapped = true;
+      }
+    }
+    {
+      const uint32_t nk = __shfl_down_sync(0xffffffffu, ek[0], 1);
+      const int nd = __shfl_down_sync(0xffffffffu, doc[0], 1);
+      const uint32_t pk_ = __shfl_up_sync(0xffffffffu, ek[E - 1], 1);
+      const int pd = __shfl_up_sync(0xffffffffu, doc[E - 1], 1);
+      const bool up_swap = lane < 31 && key_doc_after(ek[E - 1], doc[E - 1], nk, nd);     // my last <-> next first
+      const bool dn_swap = lane > 0 && key_doc_after(pk_, pd, ek[0], doc[0]);             // previous last <-> my first
+      if (E == 1) {
+        // one element per lane: a lane may not take part in both exchanges of a round
+        const bool take_up = up_swap && (lane & 1) == (round & 1);
+        const bool take_dn = dn_swap && ((lane - 1) & 1) == (round & 1);
+        if (take_up) { ek[0] = nk; doc[0] = nd; }
+        else if (take_dn) { ek[0] = pk_; doc[0] = pd; }
+        swapped = swapped || take_up || take_dn;
+      } else {
+        if (up_swap) { ek[E - 1] = nk; doc[E - 1] = nd; }
+        if (dn_swap) { ek[0] = pk_; doc[0] = pd; }
+        swapped = swapped || up_swap || dn_swap;
+      }
+    }
+    if (!__any_sync(0xffffffffu, swapped)) return;
   }
+  // still moving after 8 rounds: exact 64-bit network over the original documents
+  uint64_t xk[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int j = lane * E + r;
+    xk[r] = pack_key(j < nb ? desc_key_f32(sv[r]) : kPadKey, j);
+  }
+  warp_bitonic_sort64<E>(xk, lane);
+#pragma unroll
+  for (int r = 0; r < E; ++r) doc[r] = static_cast<int>(xk[r] & 0xffffffffu);
 }
 
 // Inclusive scan over positions p = lane * E + r of per-position values.
@@ -69,37 +125,77 @@ __device__ __forceinline__ void warp_inclusive_scan(float (&v)[E], int lane) {
   for (int r = 0; r < E; ++r) v[r] += excl;
 }
 
+// Rows arrive by TMA bulk copies (cp.async.bulk + mbarrier) into one of TWO staging buffers per warp:
+// the row of the warp's next query is in flight while the current one is ranked (the kernel is
+// otherwise bound by the latency of its own row loads).  Rows that cannot be staged (not 16-byte
+// aligned) are read with coalesced loads into the same buffers.
 template <int E>
-__global__ void __launch_bounds__(kMetricWarps * 32)
+__global__ void __launch_bounds__(kMetricWarps * 32, 8)
 rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const void* __restrict__ rel,
                          int rel_bytes, const void* __restrict__ n, int n_bytes, int B, int L, int k,
-                         int exp_gain, float* __restrict__ out, int out_ld,
+                         int exp_gain, int tma, float* __restrict__ out, int out_ld,
                          const PairTables* __restrict__ tabs) {
-  __shared__ MetricScratch<E> scratch[kMetricWarps];
+  __shared__ __align__(16) unsigned char s_stage[kMetricWarps][2][32 * E * 12];
+  __shared__ int s_y[kMetricWarps][32 * E];
+  __shared__ uint64_t s_bar[kMetricWarps][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  MetricScratch<E>& ws = scratch[warp];
+  int* raw_y = s_y[warp];
   const float* __restrict__ inv_disc = tabs->inv_disc;
-  for (int b = blockIdx.x * kMetricWarps + warp; b < B; b += gridDim.x * kMetricWarps) {
+  const uint32_t row_s_bytes = 4u * L, row_y_bytes = static_cast<uint32_t>(rel_bytes) * L;
+  const int stride = gridDim.x * kMetricWarps;
+  int b = blockIdx.x * kMetricWarps + warp;
+  auto issue_row = [&](int q, int buf) {
+    uint64_t* bar = &s_bar[warp][buf];
+    unsigned char* stage = s_stage[warp][buf];
+    mbar_arrive_expect_tx(bar, row_s_bytes + row_y_bytes);
+    tma_load_1d(stage, scores + static_cast<size_t>(q) * L, row_s_bytes, bar);
+    tma_load_1d(stage + row_s_bytes, static_cast<const unsigned char*>(rel) + static_cast<size_t>(q) * row_y_bytes,
+                row_y_bytes, bar);
+  };
+  if (tma) {
+    if (lane == 0) {
+      mbar_init(&s_bar[warp][0], 1);
+      mbar_init(&s_bar[warp][1], 1);
+      fence_mbar_init();
+      if (b < B) issue_row(b, 0);
+    }
+    __syncwarp();
+  }
+
+  for (int iter = 0; b < B; b += stride, ++iter) {
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
-    // coalesced loads (document j = k * 32 + lane) staged through shared memory into the blocked
-    // layout of the sorting network (document j = lane * E + r)
+    const int buf = iter & 1;
+    unsigned char* stage = s_stage[warp][buf];
+    float* raw_s = reinterpret_cast<float*>(stage);
+    if (tma) {
+      if (lane == 0 && b + stride < B) {
+        fence_proxy_async();   // the other buffer was last read through the generic proxy
+        issue_row(b + stride, buf ^ 1);
+      }
+      mbar_wait(&s_bar[warp][buf], (iter >> 1) & 1);
+      const unsigned char* sy = stage + row_s_bytes;
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-      const int j = q * 32 + lane;
-      if (j < L) {
-        ws.raw_s[j] = scores[base + j];
-        ws.raw_y[j] = rel_bytes == 8
-                          ? clamp_i64_to_i32(reinterpret_cast<const long long*>(rel)[base + j])
-                          : load_int_clamped(rel, rel_bytes, base + j);
+      for (int q = 0; q < E; ++q) {
+        const int j = q * 32 + lane;
+        if (j < L) raw_y[j] = load_int_clamped(sy, rel_bytes, j);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int j = q * 32 + lane;
+        if (j < L) {
+          raw_s[j] = scores[base + j];
+          raw_y[j] = load_int_clamped(rel, rel_bytes, base + j);
+        }
       }
     }
     __syncwarp();
     float sv[E];
     int doc[E];
 #pragma unroll
-    for (int r = 0; r < E; ++r) sv[r] = lane * E + r < nb ? ws.raw_s[lane * E + r] : 0.0f;
-    warp_rank_by_score<E>(sv, nb, lane, ws.raw_s, doc);
+    for (int r = 0; r < E; ++r) sv[r] = lane * E + r < nb ? raw_s[lane * E + r] : 0.0f;
+    warp_rank_by_score<E>(sv, nb, lane, raw_s, doc);
 
     // relevance per rank; ranks >= nb are the padded documents in index order, whose relevance
     // the reference does not mask (dcg.py:85)
@@ -108,7 +204,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 #pragma unroll
     for (int r = 0; r < E; ++r) {
       const int p = lane * E + r;
-      iy[r] = p < L ? ws.raw_y[p < nb ? doc[r] : p] : 0;
+      iy[r] = p < L ? raw_y[p < nb ? doc[r] : p] : 0;
       ry[r] = static_cast<float>(iy[r]);
     }
 
@@ -143,7 +239,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         const int j = lane * E + r;
-        yk[r] = j < nb ? desc_key_i32(ws.raw_y[j]) : kPadKey;
+        yk[r] = j < nb ? desc_key_i32(raw_y[j]) : kPadKey;
       }
       warp_bitonic_sort32<E>(yk, lane);
 #pragma unroll
@@ -151,7 +247,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
         const int p = lane * E + r;
         int gy = 0;
         if (p < nb) gy = static_cast<int>(~yk[r] ^ 0x80000000u);
-        else if (p < L) gy = ws.raw_y[p];
+        else if (p < L) gy = raw_y[p];
         const float g = exp_gain ? gain_of_grade(gy) : static_cast<float>(gy);
         iterm[r] = p < L ? g * __ldg(inv_disc + p) : 0.0f;
       }
@@ -184,8 +280,8 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
           term[r] = term[r] / iv;
         }
       }
-      // stage through shared memory for coalesced stores
-      float* o = ws.raw_s;
+      // stage through shared memory (the grades are dead) for coalesced stores
+      float* o = reinterpret_cast<float*>(raw_y);
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < E; ++r) o[lane * E + r] = term[r];
@@ -471,11 +567,9 @@ topk_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
       if (kv > 0) {
         double acc = 0.0;
         if (!__any_sync(0xffffffffu, wide)) {
+          // 16-bit fields, at most 32 x 32 documents per field: one warp-wide integer add per word (REDUX)
 #pragma unroll
-          for (int f = 0; f < 4; ++f) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wcnt[f] += __shfl_xor_sync(0xffffffffu, wcnt[f], o);
-          }
+          for (int f = 0; f < 4; ++f) wcnt[f] = __reduce_add_sync(0xffffffffu, wcnt[f]);
           int start = 0;
 #pragma unroll
           for (int g = 7; g >= 1; --g) {

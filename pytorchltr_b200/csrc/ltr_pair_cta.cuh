@@ -29,7 +29,8 @@ struct CtaSmem {
   int* raw_y;         // [L]      relevance, document order
   int* doc;           // [Lp]     rank -> document
   float* gacc;        // [Lp]     rank-order gradient (unscaled)
-  float* gcol;        // [W*128]  per-warp column accumulators of the current tile
+  float* gcol;        // [W*256]  per-warp column accumulators of the current tile (128) + the dump of ring
+                      //          lanes that own no chunk (ring_pass_fact: chunk 32 + lane)
   float* red;         // [40]
   int* hist;          // [36]     grade histogram + flags + tile counter
   // TMA staging (tma != 0): two row buffers and their mbarriers; raw_s then aliases tma_s[cur]
@@ -44,7 +45,7 @@ __host__ __device__ inline size_t cta_align16(size_t v) { return (v + 15) & ~sta
 // rel_bytes = 0: no TMA staging buffers
 __host__ __device__ inline size_t cta_smem_bytes(int L, int P, int tma_rel_bytes) {
   const size_t Lp = (static_cast<size_t>(L) + 127) / 128 * 128;
-  size_t bytes = 8u * P + 16u * Lp + 4u * (Lp + 8) + 4u * kCtaWarps * 128 + 4u * Lp + 4u * Lp +
+  size_t bytes = 8u * P + 16u * Lp + 4u * (Lp + 8) + 4u * kCtaWarps * 256 + 4u * Lp + 4u * Lp +
                  cta_align16(4u * L) + cta_align16(4u * L) + 4u * 40 + 4u * 40;
   if (tma_rel_bytes) bytes += cta_align16(4u * L) + 2u * cta_align16(static_cast<size_t>(tma_rel_bytes) * L) + 16u;
   return bytes;
@@ -59,7 +60,7 @@ __device__ __forceinline__ CtaSmem cta_carve(unsigned char* base, int L, int P, 
   m.it.e = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.it.g = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.delta = reinterpret_cast<float*>(base);                   base += 4u * (Lp + 8);
-  m.gcol = reinterpret_cast<float*>(base);                    base += 4u * kCtaWarps * 128;
+  m.gcol = reinterpret_cast<float*>(base);                    base += 4u * kCtaWarps * 256;
   m.gacc = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.doc = reinterpret_cast<int*>(base);                       base += 4u * Lp;
   m.raw_s = reinterpret_cast<float*>(base);                   base += cta_align16(4u * L);
@@ -80,7 +81,7 @@ template <int TW, bool FACTORED>
 __device__ __forceinline__ float cta_tiles(const CtaSmem& m, const PairTables& tb, int nb, int lane, int warp) {
   const int S = (nb + 127) >> 7;
   const int T = S * (S + 1) / 2;
-  float* gcol = m.gcol + warp * 128;
+  float* gcol = m.gcol + warp * 256;
   float wl = 0.0f;
   for (;;) {
     int t = 0;

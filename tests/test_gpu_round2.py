@@ -222,6 +222,17 @@ def _free_port():
 
 
 def _nccl_worker(rank, world, port, B, L, out_dir):
+    import traceback
+    try:
+        _nccl_worker_body(rank, world, port, B, L, out_dir)
+    except BaseException:  # noqa: B902  (reported through a file: the parent kills a wedged peer)
+        with open(os.path.join(out_dir, f"error{rank}.txt"), "w") as f:
+            f.write(traceback.format_exc())
+        os._exit(1)
+    os._exit(0)
+
+
+def _nccl_worker_body(rank, world, port, B, L, out_dir):
     import torch.distributed as dist
     from pytorchltr_b200.distributed import global_mean, shard_batch, shard_bounds, sharded_mean_loss
     from pytorchltr_b200.evaluation import ndcg
@@ -230,43 +241,58 @@ def _nccl_worker(rank, world, port, B, L, out_dir):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    try:
-        s, y, n = make_batch(5, B, L)
-        st, yt, nt = shard_batch(torch.as_tensor(s), torch.as_tensor(y), torch.as_tensor(n))
-        st = st.to(dev).requires_grad_(True)
-        yt, nt = yt.to(dev), nt.to(dev)
-        mod = _loss_module("ndcg2")
-        mean = sharded_mean_loss(mod, st, yt, nt)
-        mean.backward()
-        # the same step captured into a CUDA graph (collective included), replayed twice
-        st2 = st.detach().clone().requires_grad_(True)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+    dist.all_reduce(torch.zeros(2, device=dev))          # communicator set-up before any capture
+    torch.cuda.synchronize()
+    s, y, n = make_batch(5, B, L)
+    st, yt, nt = shard_batch(torch.as_tensor(s), torch.as_tensor(y), torch.as_tensor(n))
+    st = st.to(dev).requires_grad_(True)
+    yt, nt = yt.to(dev), nt.to(dev)
+    mod = _loss_module("ndcg2")
+    mean = sharded_mean_loss(mod, st, yt, nt)
+    mean.backward()
+    gm = global_mean(ndcg(st.detach(), yt, nt, k=10))
+    torch.cuda.synchronize()
+    # the same step captured into a CUDA graph (collective included), replayed twice
+    st2 = st.detach().clone().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            st2.grad = None
             sharded_mean_loss(mod, st2, yt, nt).backward()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        st2.grad = None
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            gmean = sharded_mean_loss(mod, st2, yt, nt)
-            gmean.backward()
-        graph.replay()
-        graph.replay()
-        torch.cuda.synchronize()
-        gm = global_mean(ndcg(st.detach(), yt, nt, k=10))
-        lo, hi = shard_bounds(B, rank, world)
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), mean=mean.item(), grad=st.grad.cpu().numpy(),
-                 gmean=gmean.item(), ggrad=st2.grad.cpu().numpy(), lo=lo, hi=hi, gm=gm.item())
-    finally:
-        dist.destroy_process_group()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    st2.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        gmean = sharded_mean_loss(mod, st2, yt, nt)
+        gmean.backward()
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    lo, hi = shard_bounds(B, rank, world)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), mean=mean.item(), grad=st.grad.cpu().numpy(),
+             gmean=gmean.item(), ggrad=st2.grad.cpu().numpy(), lo=lo, hi=hi, gm=gm.item())
+    dist.barrier()
+    torch.cuda.synchronize()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_mean_loss_two_ranks_nccl(tmp_path):
+    import time
     import torch.multiprocessing as mp
     B, L, world = 1001, 256, 2
-    mp.spawn(_nccl_worker, args=(world, _free_port(), B, L, str(tmp_path)), nprocs=world, join=True)
+    ctx = mp.start_processes(_nccl_worker, args=(world, _free_port(), B, L, str(tmp_path)), nprocs=world,
+                             join=False, start_method="spawn")
+    deadline = time.time() + 150
+    while time.time() < deadline and any(p.is_alive() for p in ctx.processes):
+        time.sleep(0.5)
+    wedged = [p for p in ctx.processes if p.is_alive()]
+    for p in wedged:
+        p.kill()
+    errors = [open(tmp_path / f).read() for f in os.listdir(tmp_path) if f.startswith("error")]
+    assert not errors, errors[0]
+    assert not wedged, "a rank did not finish within 150 s"
     s, y, n = make_batch(5, B, L)
     loss, grad = oracle.lambda_loss("ndcg2", s, y, n)
     ndcg = oracle.ndcg(s, y, n, k=10)
@@ -353,3 +379,36 @@ def test_ours_vs_ref32_beside_ref32_vs_ref64():
             f.write("fixture mode max_rel|ours-ref64| max_rel|ref32-ref64| max_rel|ours-ref32|\n")
             for r in rows:
                 f.write("%s %s %.3e %.3e %.3e\n" % r)
+
+
+# ------------------------------------------------------------------ close scores: exactness of the packed sort
+@pytest.mark.parametrize("L", (20, 50, 100, 200, 256))
+@pytest.mark.parametrize("kind", ("bucket", "grid", "pairs"))
+def test_rank_by_score_with_scores_closer_than_the_packed_key(L, kind):
+    """Scores that share the key bits of the 32-bit packed sort: the ranking must still be the exact
+    (descending score, lowest index first) order, and arp / dcg must agree with the oracle."""
+    from pytorchltr_b200.evaluation import arp, dcg
+    from pytorchltr_b200.utils import rank_by_score
+    rng = np.random.default_rng(L)
+    B = 33
+    if kind == "bucket":       # every score inside one bucket, random order, with exact ties
+        s = (1.0 + rng.integers(0, 64, size=(B, L)) * 2.0 ** -22).astype(np.float32)
+    elif kind == "grid":       # normal scores on a coarse grid: many exact ties
+        s = (np.round(rng.standard_normal((B, L)) * 8) / 8).astype(np.float32)
+    else:                      # random scores, a few pairs one ulp apart in reversed index order
+        s = rng.standard_normal((B, L)).astype(np.float32)
+        for b in range(B):
+            i, j = sorted(rng.choice(L // 2, size=2, replace=False))
+            s[b, i] = np.nextafter(s[b, j], np.float32(-np.inf))
+    n = rng.integers(L // 2, L + 1, size=B)
+    y = rng.integers(0, 5, size=(B, L))
+    y[np.arange(L)[None, :] >= n[:, None]] = 0
+    st, yt, nt = (torch.as_tensor(a).to(DEV) for a in (s, y, n))
+    got = rank_by_score(st, nt).cpu().numpy()
+    for b in range(B):
+        nb = int(n[b])
+        want = np.lexsort((np.arange(nb), -s[b, :nb].astype(np.float64)))
+        assert np.array_equal(got[b, :nb], want), (kind, L, b)
+        assert np.array_equal(got[b, nb:], np.arange(nb, L))
+    assert arp(st, yt, nt).cpu().double().numpy() == pytest.approx(oracle.arp(s, y, n), rel=1e-5, abs=1e-6)
+    assert dcg(st, yt, nt).cpu().double().numpy() == pytest.approx(oracle.dcg(s, y, n), rel=1e-5, abs=1e-5)

@@ -2,6 +2,7 @@
 """Per-source-line executed instructions and stall samples from an .ncu-rep (needs -lineinfo)."""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+by_inst = len(sys.argv) > 3 and sys.argv[3] == "inst"   # sort by executed instructions instead of stall samples
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -28,6 +29,6 @@ tot_st = {}
 for a in agg:
     for k, v in a[5].items(): tot_st[k] = tot_st.get(k, 0) + v
 print("stall totals:", {k: v for k, v in sorted(tot_st.items(), key=lambda kv: -kv[1]) if v})
-for smp, n, f, ln, src, st in sorted(agg, key=lambda a: -a[0])[:top]:
+for smp, n, f, ln, src, st in sorted(agg, key=lambda a: -(a[1] if by_inst else a[0]))[:top]:
     main = max(st.items(), key=lambda kv: kv[1])[0] if any(st.values()) else ""
     print(f"{smp:6d} {n:9d} {main:18s} {f}:{ln}: {src}")
