@@ -216,6 +216,31 @@ int ltr_collate(const float *features, const int64_t *relevance, const int64_t *
                 int64_t *n_out, int64_t *count_out, void *stream);
 
 /*
+ * Sampled collation (list samplers, datasets/list_sampler.py:19-61, consulted by collate_fn only for
+ * queries with more than `L` documents, svmrank.py:159-190): such a query takes the documents
+ * sel[b * sel_ld + l], l < L (indices inside the query: a permutation prefix produced on the device,
+ * e.g. ltr_rank_by_score over random keys for the UniformSampler); shorter queries are copied in order.
+ * sel == NULL: every query in order (== ltr_collate).
+ */
+int ltr_collate_sampled(const float *features, const int64_t *relevance, const int64_t *offsets,
+                        const int64_t *qidx, const int64_t *sel, int sel_ld, int B, int L, int F,
+                        float *feat_out, int64_t *rel_out, int64_t *n_out, int64_t *count_out,
+                        void *stream);
+
+/*
+ * Sparse collation (svmrank.py:163-177, 198-203): features in CSR form over the documents (indptr
+ * [N+1], indices, values); returns the COO triplets (batch row, list position, feature) as coo_out
+ * [3 * nnz_out] (three planes) + val_out [nnz_out] of a sparse (B, L, F) tensor, and rel_out / n_out as
+ * above.  out_ptr [B * L + 1]: exclusive scan of the non-zero counts of the selected documents (the
+ * caller computes it from indptr; out_ptr[B * L] == nnz_out).
+ */
+int ltr_collate_sparse(const int64_t *indptr, const int64_t *indices, const float *values,
+                       const int64_t *relevance, const int64_t *offsets, const int64_t *qidx,
+                       const int64_t *sel, int sel_ld, const int64_t *out_ptr, int B, int L,
+                       int64_t nnz_out, int64_t *coo_out, float *val_out, int64_t *rel_out,
+                       int64_t *n_out, void *stream);
+
+/*
  * Host-buffer form of the three loss families (the call the reference's CPU path is
  * compared with end to end): copies scores / relevance / n from host memory into `workspace`,
  * runs the fused loss + gradient kernel and copies loss_out [B] and dscores_out [B*L] (if not

@@ -18,7 +18,7 @@ SYMBOLS = (
     "ltr_host_workspace_bytes", "ltr_loss_host", "ltr_schedule_workspace_bytes",
     "ltr_pairwise_additive_ws", "ltr_lambda_ws", "ltr_host_workspace_dscores_offset",
     "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate",
-    "ltr_pbm_probabilities", "ltr_loss_host_ex", "ltr_scale_rows_host",
+    "ltr_pbm_probabilities", "ltr_loss_host_ex", "ltr_scale_rows_host", "ltr_collate_sampled", "ltr_collate_sparse",
 )
 
 ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
@@ -87,6 +87,13 @@ def _declare(lib):
     lib.ltr_collate.restype = c_int
     lib.ltr_collate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]
+    lib.ltr_collate_sampled.restype = c_int
+    lib.ltr_collate_sampled.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ltr_collate_sparse.restype = c_int
+    lib.ltr_collate_sparse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_void_p, c_int, c_int, ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]
     lib.ltr_loss_host.restype = c_int
     lib.ltr_loss_host.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]

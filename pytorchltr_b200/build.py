@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libltr_sm100.so")
+PARSER_LIB = os.path.join(CSRC, "libltr_svmrank.so")
+PARSER_SRC = os.path.join(CSRC, "svmrank_parser.cpp")
 SOURCES = ["ltr_kernels.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -40,11 +42,26 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_parser(force: bool = False) -> str:
+    """The SVMrank text parser (host C++, no CUDA): csrc/libltr_svmrank.so."""
+    if not force and os.path.exists(PARSER_LIB) and os.path.getmtime(PARSER_LIB) >= os.path.getmtime(PARSER_SRC):
+        return PARSER_LIB
+    cxx = shutil.which("g++") or "/usr/bin/g++"
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-o", PARSER_LIB, PARSER_SRC]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd))
+    return PARSER_LIB
+
+
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
     """Builds the shared library if it is missing or older than its sources.  `defines` / `out`
     build an A-B variant (e.g. defines=["LTR_RING_MIN_CTAS=4"], out="build/ltr_variant.so"; select it
     at run time with LTR_SM100_LIB)."""
     target = out or LIB
+    if not out:
+        build_parser(force)
     if not force and not out and not _stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]

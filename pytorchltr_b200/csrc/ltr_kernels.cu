@@ -1339,6 +1339,48 @@ int ltr_collate(const float* features, const int64_t* relevance, const int64_t* 
   return LTR_OK;
 }
 
+int ltr_collate_sampled(const float* features, const int64_t* relevance, const int64_t* offsets,
+                        const int64_t* qidx, const int64_t* sel, int sel_ld, int B, int L, int F, float* feat_out,
+                        int64_t* rel_out, int64_t* n_out, int64_t* count_out, void* stream) {
+  if (B < 0 || L < 1 || F < 1 || sel_ld < 0) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!features || !relevance || !offsets || !qidx || !feat_out || !rel_out || !n_out) return LTR_EINVAL;
+  if (!sel && sel_ld != 0) return LTR_EINVAL;
+  if (sel && sel_ld < L) return LTR_EINVAL;
+  const long long groups = (L + kGatherRowsPerCta - 1) / kGatherRowsPerCta;
+  const long long grid = groups * B;
+  if (grid > 2147483647LL) return LTR_EUNSUPPORTED;
+  const int vec_ok = (F % 4 == 0) && aligned16(features) && aligned16(feat_out);
+  collate_gather_kernel<<<static_cast<unsigned int>(grid), kCollateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      features, relevance, offsets, qidx, sel, sel_ld, B, L, F, static_cast<int>(groups), vec_ok, feat_out, rel_out,
+      n_out, count_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_collate_sparse(const int64_t* indptr, const int64_t* indices, const float* values, const int64_t* relevance,
+                       const int64_t* offsets, const int64_t* qidx, const int64_t* sel, int sel_ld,
+                       const int64_t* out_ptr, int B, int L, int64_t nnz_out, int64_t* coo_out, float* val_out,
+                       int64_t* rel_out, int64_t* n_out, void* stream) {
+  if (B < 0 || L < 1 || nnz_out < 0 || sel_ld < 0) return LTR_EINVAL;
+  if (B == 0) return LTR_OK;
+  if (!indptr || !relevance || !offsets || !qidx || !out_ptr || !rel_out || !n_out) return LTR_EINVAL;
+  if (nnz_out > 0 && (!indices || !values || !coo_out || !val_out)) return LTR_EINVAL;
+  if (sel && sel_ld < L) return LTR_EINVAL;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  const long long rows = static_cast<long long>(B) * L;
+  const long long want = (rows + kCollateThreads / 32 - 1) / (kCollateThreads / 32);
+  const long long cap = static_cast<long long>(di.sms) * 8;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  collate_sparse_kernel<<<grid, kCollateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      indptr, indices, values, relevance, offsets, qidx, sel, sel_ld, out_ptr, B, L, nnz_out, coo_out, val_out, rel_out,
+      n_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
 size_t ltr_linear_listnet_workspace_bytes(int F) {
   return F < 1 ? 0 : static_cast<size_t>(kFusedBwdCtas) * (static_cast<size_t>(F) + 1) * sizeof(float);
 }

@@ -1,0 +1,92 @@
+"""SVMrank text parser (csrc/svmrank_parser.cpp) against what the UNMODIFIED reference
+parser returned for the same files (tests/golden/svmrank/cases.npz, made by
+tests/golden/make_svmrank_golden.py from pytorchltr/datasets/svmrank/parser/svmrank_parser.{h,pyx}):
+values bit-identical (same decimal arithmetic), same shapes, same exceptions."""
+import os
+
+import numpy as np
+import pytest
+
+from pytorchltr_b200.datasets.svmrank import parse_svmrank_file, query_offsets
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "svmrank", "cases.npz"))
+NAMES = sorted({k.split("__")[0] for k in GOLDEN.files})
+
+
+def _write(tmp_path, name):
+    path = tmp_path / (name + ".txt")
+    path.write_bytes(GOLDEN[name + "__text"].tobytes())
+    return str(path)
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("threads", (1, 4))
+def test_parser_matches_reference_parser(tmp_path, name, threads):
+    path = _write(tmp_path, name)
+    if int(GOLDEN[name + "__error"]):
+        with pytest.raises(ValueError):
+            parse_svmrank_file(path, n_threads=threads)
+        return
+    xs, ys, qids = parse_svmrank_file(path, n_threads=threads)
+    assert xs.dtype == np.float64 and ys.dtype == np.int32 and qids.dtype == np.int64
+    assert np.array_equal(xs, GOLDEN[name + "__xs"])          # bit-identical doubles
+    assert np.array_equal(ys, GOLDEN[name + "__ys"])
+    assert np.array_equal(qids, GOLDEN[name + "__qids"])
+    x32, _, _ = parse_svmrank_file(path, dtype=np.float32, n_threads=threads)
+    assert np.array_equal(x32, GOLDEN[name + "__xs"].astype(np.float32))
+
+
+def test_missing_file_raises_oserror(tmp_path):
+    with pytest.raises(OSError):
+        parse_svmrank_file(str(tmp_path / "nope.txt"))
+
+
+def test_large_file_is_thread_count_invariant(tmp_path):
+    """~6 MB, cut into many slices: every thread count gives the same arrays; values agree with the
+    numbers that were printed."""
+    rng = np.random.default_rng(5)
+    rows, F = 20000, 40
+    X = np.round(rng.standard_normal((rows, F)), 5)
+    y = rng.integers(0, 5, size=rows)
+    q = np.sort(rng.integers(1, 900, size=rows))
+    with open(tmp_path / "big.txt", "w") as f:
+        for i in range(rows):
+            f.write("%d qid:%d %s\n" % (y[i], q[i], " ".join("%d:%.5f" % (c + 1, X[i, c]) for c in range(F))))
+    ref = parse_svmrank_file(str(tmp_path / "big.txt"), n_threads=1)
+    assert ref[0].shape == (rows, F)
+    assert np.allclose(ref[0], X, rtol=0, atol=1e-12)
+    assert np.array_equal(ref[1], y) and np.array_equal(ref[2], q)
+    for threads in (2, 3, 8, 0):
+        got = parse_svmrank_file(str(tmp_path / "big.txt"), n_threads=threads)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    offsets, unique = query_offsets(ref[2])
+    assert offsets[0] == 0 and offsets[-1] == rows and np.array_equal(unique, np.unique(q))
+
+
+@pytest.mark.gpu
+def test_load_svmrank_to_device_dataset(tmp_path):
+    """Text file -> DeviceRankingDataset (dense and CSR) -> collated batch, against the parsed arrays."""
+    import torch
+    from pytorchltr_b200.datasets.svmrank import load_svmrank
+    path = _write(tmp_path, "sparse_mixed")
+    xs, ys, qids = GOLDEN["sparse_mixed__xs"], GOLDEN["sparse_mixed__ys"], GOLDEN["sparse_mixed__qids"]
+    offsets, unique = query_offsets(qids)
+    dense = load_svmrank(path)
+    sp = load_svmrank(path, sparse=True)
+    assert len(dense) == len(unique) == len(sp)
+    idx = list(range(len(unique)))
+    a, b = dense.collate(idx), sp.collate(idx)
+    L = int(np.diff(offsets).max())
+    want = np.zeros((len(unique), L, xs.shape[1]), dtype=np.float32)
+    rel = np.zeros((len(unique), L), dtype=np.int64)
+    for i in range(len(unique)):
+        n = offsets[i + 1] - offsets[i]
+        want[i, :n] = xs[offsets[i]:offsets[i + 1]].astype(np.float32)
+        rel[i, :n] = ys[offsets[i]:offsets[i + 1]]
+    assert np.array_equal(a.features.cpu().numpy(), want)
+    assert np.array_equal(b.features.to_dense().cpu().numpy(), want)
+    assert np.array_equal(a.relevance.cpu().numpy(), rel) and torch.equal(a.relevance, b.relevance)
+    assert np.array_equal(a.qid.cpu().numpy(), unique)
+    filt = load_svmrank(path, filter_queries=True)
+    keep = [i for i in range(len(unique)) if ys[offsets[i]:offsets[i + 1]].sum() > 0]
+    assert len(filt) == len(keep) and np.array_equal(filt.qids.numpy(), unique[keep])
