@@ -11,8 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_functions():
-    text = open(os.path.join(ROOT, "include", "ltr_sm100.h")).read()
+def _header_functions(header="ltr_sm100.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ltr_[a-z_0-9]+)\s*\(", text)))
 
@@ -32,6 +32,17 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert lib.ltr_strerror(0) == b"success"
     assert b"invalid" in lib.ltr_strerror(-1)
     assert lib.ltr_host_workspace_bytes(4, 8) >= 4 * 8 * 16
+
+
+def test_parser_library_exports_header_symbols():
+    from pytorchltr_b200 import build
+    from pytorchltr_b200.datasets import svmrank
+    path = build.build_parser()
+    handle = ctypes.CDLL(path)
+    names = _header_functions("ltr_svmrank.h")
+    assert sorted(svmrank.SYMBOLS) == names
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/ltr_svmrank.h but not exported"
 
 
 def test_argument_validation_needs_no_gpu():
