@@ -81,7 +81,7 @@ collate_gather_kernel(const float* __restrict__ features, const int64_t* __restr
     float* __restrict__ dst = feat_out + (static_cast<size_t>(b) * L + l) * F;
     int64_t d = -1;
     if (l < n) {
-      d = sampled ? sel[static_cast<size_t>(b) * sel_ld + l] : l;
+      d = (sampled && sel) ? sel[static_cast<size_t>(b) * sel_ld + l] : l;
       d = d < 0 ? 0 : (d >= cnt ? cnt - 1 : d);
     }
     if (d >= 0) {
@@ -134,7 +134,7 @@ collate_sparse_kernel(const int64_t* __restrict__ indptr, const int64_t* __restr
     const int n = static_cast<int>(sampled ? L : cnt);
     int64_t rel = 0;
     if (l < n) {
-      int64_t d = sampled ? sel[static_cast<size_t>(b) * sel_ld + l] : l;
+      int64_t d = (sampled && sel) ? sel[static_cast<size_t>(b) * sel_ld + l] : l;
       d = d < 0 ? 0 : (d >= cnt ? cnt - 1 : d);
       const int64_t doc = off + d;
       rel = relevance[doc];

@@ -75,25 +75,30 @@ __device__ __forceinline__ void warp_rank_by_score(const float (&sv)[E], int nb,
         swapped = true;
       }
     }
-    {
+    if constexpr (E == 1) {
+      // one element per lane: the pairs (l, l + 1) with even l, then those with odd l
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const uint32_t nk = __shfl_down_sync(0xffffffffu, ek[0], 1);
+        const int nd = __shfl_down_sync(0xffffffffu, doc[0], 1);
+        const uint32_t pk_ = __shfl_up_sync(0xffffffffu, ek[0], 1);
+        const int pd = __shfl_up_sync(0xffffffffu, doc[0], 1);
+        const bool take_up = lane < 31 && (lane & 1) == par && key_doc_after(ek[0], doc[0], nk, nd);
+        const bool take_dn = lane > 0 && ((lane - 1) & 1) == par && key_doc_after(pk_, pd, ek[0], doc[0]);
+        if (take_up) { ek[0] = nk; doc[0] = nd; }
+        else if (take_dn) { ek[0] = pk_; doc[0] = pd; }
+        swapped = swapped || take_up || take_dn;
+      }
+    } else {
       const uint32_t nk = __shfl_down_sync(0xffffffffu, ek[0], 1);
       const int nd = __shfl_down_sync(0xffffffffu, doc[0], 1);
       const uint32_t pk_ = __shfl_up_sync(0xffffffffu, ek[E - 1], 1);
       const int pd = __shfl_up_sync(0xffffffffu, doc[E - 1], 1);
       const bool up_swap = lane < 31 && key_doc_after(ek[E - 1], doc[E - 1], nk, nd);     // my last <-> next first
       const bool dn_swap = lane > 0 && key_doc_after(pk_, pd, ek[0], doc[0]);             // previous last <-> my first
-      if (E == 1) {
-        // one element per lane: a lane may not take part in both exchanges of a round
-        const bool take_up = up_swap && (lane & 1) == (round & 1);
-        const bool take_dn = dn_swap && ((lane - 1) & 1) == (round & 1);
-        if (take_up) { ek[0] = nk; doc[0] = nd; }
-        else if (take_dn) { ek[0] = pk_; doc[0] = pd; }
-        swapped = swapped || take_up || take_dn;
-      } else {
-        if (up_swap) { ek[E - 1] = nk; doc[E - 1] = nd; }
-        if (dn_swap) { ek[0] = pk_; doc[0] = pd; }
-        swapped = swapped || up_swap || dn_swap;
-      }
+      if (up_swap) { ek[E - 1] = nk; doc[E - 1] = nd; }
+      if (dn_swap) { ek[0] = pk_; doc[0] = pd; }
+      swapped = swapped || up_swap || dn_swap;
     }
     if (!__any_sync(0xffffffffu, swapped)) return;
   }
