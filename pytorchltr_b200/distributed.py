@@ -60,22 +60,33 @@ def global_mean(per_query: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class _MeanOfShards(torch.autograd.Function):
-    """``buf[0] / max(buf[1], 1)`` as a function of the local per-query losses: ``buf`` already holds
-    the all-reduced ``[sum, count]``; the backward pass hands every local query the broadcast
-    gradient ``g / count`` (a stride-0 view, which the loss's backward reads in place)."""
+    """``total / count`` as a function of the local per-query losses: ``total`` already holds the
+    all-reduced sum; the backward pass hands every local query the broadcast gradient ``g / count`` (a
+    stride-0 view, which the loss's backward reads in place).  ``count`` is the all-reduced query count
+    (a device scalar) or, when the caller knows it, a Python number (no kernel for it)."""
 
     @staticmethod
-    def forward(ctx, per_query, buf):
-        count = buf[1].clamp(min=1.0)
-        ctx.save_for_backward(count)
+    def forward(ctx, per_query, total, count):
+        if isinstance(count, torch.Tensor):
+            count = count.clamp(min=1.0)
+            ctx.save_for_backward(count)
+            ctx.inv_count = None
+            out = total / count
+        else:
+            ctx.inv_count = 1.0 / max(float(count), 1.0)
+            out = total * ctx.inv_count
         ctx.num_queries = per_query.shape[0]
         ctx.out_dtype = per_query.dtype
-        return (buf[0] / count).to(per_query.dtype)
+        return out.reshape(()).to(per_query.dtype)
 
     @staticmethod
     def backward(ctx, g):
-        (count,) = ctx.saved_tensors
-        return (g / count.to(g.dtype)).to(ctx.out_dtype).reshape(1).expand(ctx.num_queries), None
+        if ctx.inv_count is None:
+            (count,) = ctx.saved_tensors
+            gq = g / count.to(g.dtype)
+        else:
+            gq = g * ctx.inv_count
+        return gq.to(ctx.out_dtype).reshape(1).expand(ctx.num_queries), None, None
 
 
 def _accepts_loss_sum(loss_fn) -> bool:
@@ -85,7 +96,7 @@ def _accepts_loss_sum(loss_fn) -> bool:
 
 
 def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.Tensor,
-                      n: torch.Tensor, group=None) -> torch.Tensor:
+                      n: torch.Tensor, group=None, global_count: Optional[int] = None) -> torch.Tensor:
     """Global mean loss over the query shards of all ranks.
 
     ``loss_fn(scores, relevance, n)`` runs on the local shard only.  The returned scalar
@@ -94,9 +105,11 @@ def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.
     on the local scores), so no gradient collective is needed for the scores.
 
     With CUDA inputs and a loss module of this package the local sum is produced by the loss
-    kernel's own epilogue (``loss_sum``: one atomic add per query), so the 2-element
-    ``[sum, count]`` all-reduce follows the kernel with no reduction launch in between; the whole
-    step (kernel, collective, backward) is CUDA-graph capturable.  The float32 atomics make the
+    kernel's own epilogue (``loss_sum``: one atomic add per query), so the ``[sum, count]``
+    all-reduce follows the kernel with no reduction launch in between; the whole step (kernel,
+    collective, backward) is CUDA-graph capturable.  ``global_count`` (the number of queries over
+    all ranks, when the caller knows it -- e.g. a fixed global batch size) shrinks the collective to
+    the sum alone and removes the count arithmetic from the step.  The float32 atomics make the
     last bits of the reported mean depend on the summation order; gradients do not depend on it.
 
     Parameter gradients of a model in front of the loss must be SUM-reduced across ranks
@@ -105,12 +118,16 @@ def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.
     returned loss by the world size to compensate.
     """
     if scores.is_cuda and _accepts_loss_sum(loss_fn):
-        buf = torch.zeros(2, dtype=torch.float32, device=scores.device)
-        buf[1:].fill_(float(scores.shape[0]))
+        if global_count is not None:
+            buf = torch.zeros(1, dtype=torch.float32, device=scores.device)
+        else:
+            buf = torch.zeros(2, dtype=torch.float32, device=scores.device)
+            buf[1:].fill_(float(scores.shape[0]))
         per_query = loss_fn(scores, relevance, n, loss_sum=buf[:1])
         if _world(group) > 1:
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     else:
         per_query = loss_fn(scores, relevance, n)
         buf = global_sum_count(per_query, group)
-    return _MeanOfShards.apply(per_query, buf)
+    count = buf[1] if global_count is None else int(global_count)
+    return _MeanOfShards.apply(per_query, buf[0], count)

@@ -213,6 +213,12 @@ def test_sharded_mean_loss_single_rank_uses_the_kernel_epilogue():
     m2.backward()
     assert m1.item() == pytest.approx(m2.item(), rel=2e-6)      # float32 atomics: summation order
     assert torch.equal(a.grad, b.grad)
+    # the caller knows the global query count: scalar-only exchange, same numbers
+    c = torch.as_tensor(s).to(DEV).requires_grad_(True)
+    m3 = sharded_mean_loss(mod, c, yd, nd, global_count=300)
+    m3.backward()
+    assert m3.item() == pytest.approx(m2.item(), rel=2e-6)
+    assert torch.allclose(c.grad, b.grad, rtol=1e-6, atol=0)
 
 
 def _free_port():
@@ -265,7 +271,7 @@ def _nccl_worker_body(rank, world, port, B, L, out_dir):
     st2.grad = None
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-        gmean = sharded_mean_loss(mod, st2, yt, nt)
+        gmean = sharded_mean_loss(mod, st2, yt, nt, global_count=B)
         gmean.backward()
     graph.replay()
     graph.replay()
@@ -305,7 +311,7 @@ def test_sharded_mean_loss_two_ranks_nccl(tmp_path):
         ref = grad[lo:hi] / B
         gmax = np.abs(ref).max(axis=1, keepdims=True)
         assert (np.abs(d["grad"] - ref) <= 1e-5 * gmax + 1e-9).all()
-        assert np.array_equal(d["grad"], d["ggrad"])
+        assert np.allclose(d["grad"], d["ggrad"], rtol=1e-6, atol=0)
 
 
 # ------------------------------------------------------------------ round-1 coverage holes
