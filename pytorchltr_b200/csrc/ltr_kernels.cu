@@ -902,18 +902,18 @@ inline bool force_tiles() {
   return v && strcmp(v, "tiles") == 0;
 }
 
-template <int TW>
-int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
-                     int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
-                     float* loss_sum, void* ws, size_t ws_bytes, cudaStream_t st, const DeviceInfo& di) {
+template <int TW, int W>
+int launch_pair_ring_w(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                       int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
+                       float* loss_sum, void* ws, size_t ws_bytes, cudaStream_t st, const DeviceInfo& di) {
   const int P = next_pow2(L);
-  const int threads = kRingWarps * 32;
+  const int threads = W * 32;
   // TMA bulk staging needs 16-byte aligned rows of a multiple of 16 bytes
   int tma = rows_tma_ok(scores, rel, rel_bytes, L);
   if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
-  const size_t smem = ring_smem_bytes(L, tma ? rel_bytes : 0);
+  const size_t smem = ring_smem_bytes(L, tma ? rel_bytes : 0, W);
   int grid = 0;
-  int rc = persistent_grid(pair_ring_kernel<TW>, threads, smem, B, di, &grid);
+  int rc = persistent_grid(pair_ring_kernel<TW, W>, threads, smem, B, di, &grid);
   if (rc != LTR_OK) return rc;
   Schedule sc;
   rc = make_schedule(n, n_bytes, B, L, grid, ws, ws_bytes, st, &sc);
@@ -921,11 +921,25 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
   const PairTables* tabs = nullptr;
   rc = pair_tables(st, &tabs);
   if (rc != LTR_OK) return rc;
-  pair_ring_kernel<TW><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma, dcg_mod,
-                                                    tma, loss_out, grad_out, ranking_out, loss_sum, sc.queue,
-                                                    sc.order, tabs);
+  pair_ring_kernel<TW, W><<<grid, threads, smem, st>>>(scores, rel, rel_bytes, n, n_bytes, B, L, P, sigma, dcg_mod,
+                                                       tma, loss_out, grad_out, ranking_out, loss_sum, sc.queue,
+                                                       sc.order, tabs);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
+}
+
+template <int TW>
+int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const void* n, int n_bytes,
+                     int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
+                     float* loss_sum, void* ws, size_t ws_bytes, cudaStream_t st, const DeviceInfo& di) {
+  // LTR_RING_WARPS=8 keeps eight warps per query for every list size (A-B timing)
+  static const int forced = env_int("LTR_RING_WARPS", 0);
+  const bool short_lists = forced ? forced == kRingWarpsShort : L <= kRingShortL;
+  if (short_lists)
+    return launch_pair_ring_w<TW, kRingWarpsShort>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, dcg_mod, loss_out,
+                                                   grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di);
+  return launch_pair_ring_w<TW, kRingWarpsLong>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, dcg_mod, loss_out,
+                                                grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di);
 }
 
 // PairwiseHingeLoss / PairwiseDCGHingeLoss for L > 128: O(n log n) by sorting

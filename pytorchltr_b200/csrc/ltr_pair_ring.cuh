@@ -33,8 +33,14 @@ namespace ltr {
 #ifndef LTR_RING_MIN_CTAS
 #define LTR_RING_MIN_CTAS 3   // resident CTAs per SM the register allocation aims at (A-B timing: -DLTR_RING_MIN_CTAS=4)
 #endif
-constexpr int kRingWarps = 8;
 constexpr int kRingMaxL = 1024;
+// Warps per CTA (= per query).  8 for lists up to 1024 documents; 4 for lists up to 512 (the (65536, 512)
+// configuration): half the private gradient arrays (28 KB of shared memory per CTA at L = 512), every
+// warp busy in the 128-key block sorts, and twice as many independent CTAs per SM, so that a CTA waiting
+// at one of its barriers costs the SM half as much.
+constexpr int kRingWarpsLong = 8;
+constexpr int kRingWarpsShort = 4;
+constexpr int kRingShortL = 512;
 
 // ---- 128-key blocks sorted in registers -------------------------------------------------------------
 // Element index inside the block = lane * 4 + r; `gbase` is the block's first index in the whole
@@ -148,7 +154,7 @@ __device__ __forceinline__ void cta_block_sort(uint64_t* keys, int P, int lane, 
 struct RingSmem {
   PairSoA it;          // 4 x [Lp]   rank order, Lp = L rounded up to 128; it.a is reused as the
                        //            document-order gradient once the pair phase is over
-  float* gw;           // [kRingWarps][Lp] private rank-order gradients.  Until the pair phase starts
+  float* gw;           // [warps][Lp] private rank-order gradients.  Until the pair phase starts
                        //            the same storage holds the sort keys and the unpacked row:
   uint64_t* keys;      // [P]        (inside gw)
   float* raw_s;        // [L]        scores, document order (inside gw)
@@ -164,22 +170,24 @@ struct RingSmem {
 __host__ __device__ inline size_t ring_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
 
 // tma_rel_bytes = 0: no staging buffer
-__host__ __device__ inline size_t ring_smem_bytes(int L, int tma_rel_bytes) {
+__host__ __device__ inline size_t ring_smem_bytes(int L, int tma_rel_bytes, int warps) {
   const size_t Lp = (static_cast<size_t>(L) + 127) / 128 * 128;
-  size_t bytes = 16u * Lp + 4u * kRingWarps * Lp + 4u * (2 * Lp + 8) + 2u * Lp + 4u * 80;
+  // the private arrays also hold the sort keys and the unpacked row before the pair phase: 8 P + 8 L <= 24 L
+  const size_t gw = 4u * static_cast<size_t>(warps) * Lp < 24u * Lp ? 24u * Lp : 4u * static_cast<size_t>(warps) * Lp;
+  size_t bytes = 16u * Lp + gw + 4u * (2 * Lp + 8) + 2u * Lp + 4u * 80;
   if (tma_rel_bytes) bytes += ring_align16(4u * L) + ring_align16(static_cast<size_t>(tma_rel_bytes) * L) + 16u;
   return bytes;
 }
 
-__device__ __forceinline__ RingSmem ring_carve(unsigned char* base, int L, int P, int tma_rel_bytes) {
+__device__ __forceinline__ RingSmem ring_carve(unsigned char* base, int L, int P, int tma_rel_bytes, int warps) {
   const int Lp = (L + 127) / 128 * 128;
   RingSmem m;
-  // 8 P + 8 L <= 24 L bytes of keys and row fit in the 32 Lp bytes of the private arrays
+  // 8 P + 8 L <= 24 L bytes of keys and row fit in the private arrays (at least 24 Lp bytes)
   m.gw = reinterpret_cast<float*>(base);
   m.keys = reinterpret_cast<uint64_t*>(base);
   m.raw_s = reinterpret_cast<float*>(base + 8u * P);
   m.raw_y = reinterpret_cast<int*>(base + 8u * P + ring_align16(4u * L));
-  base += 4u * kRingWarps * Lp;
+  base += (4u * warps * Lp < 24u * Lp) ? 24u * Lp : 4u * warps * Lp;
   m.it.a = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.it.b = reinterpret_cast<float*>(base);                    base += 4u * Lp;
   m.it.e = reinterpret_cast<float*>(base);                    base += 4u * Lp;
@@ -314,7 +322,7 @@ __device__ __forceinline__ void ring_step_fact(const PairSoA& it, float* __restr
 //   gw    : THIS warp's private rank-order gradient array, zero on entry
 //   symc  : centre of the signed-distance delta table in shared memory (TW_DELTA)
 // Requires C = ceil(nb / 4) >= 32.  Returns the lane's partial loss.
-template <int TW, bool FACTORED>
+template <int TW, bool FACTORED, int W>
 __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict__ gw,
                                             const float* __restrict__ symc, int nb, int lane, int warp) {
   constexpr int R = 4;
@@ -334,8 +342,8 @@ __device__ __forceinline__ float ring_split(const PairSoA& it, float* __restrict
   while (f > 1 && (T < cl_n || (f - 1) * T + cl_n > C)) { f >>= 1; T = (M + f) / f; }
   const int U_full = (G - 1) * (M + 1);
   const int U = U_full + T;             // f == 1: T == M + 1
-  int u = static_cast<int>((static_cast<long long>(U) * warp) / kRingWarps);
-  const int u_end = static_cast<int>((static_cast<long long>(U) * (warp + 1)) / kRingWarps);
+  int u = static_cast<int>((static_cast<long long>(U) * warp) / W);
+  const int u_end = static_cast<int>((static_cast<long long>(U) * (warp + 1)) / W);
   const bool even = (C & 1) == 0;
   const float* colx = FACTORED ? it.b : it.a;
   float lacc = 0.0f;
@@ -491,10 +499,10 @@ __device__ __forceinline__ float ring_small(const PairSoA& it, float* __restrict
   return l;
 }
 
-template <int TW, bool FACTORED>
+template <int TW, bool FACTORED, int W>
 __device__ __forceinline__ float ring_pairs(const RingSmem& m, const PairTables& tb, int Lp, int nb, int lane,
                                             int warp) {
-  if (nb > 124) return ring_split<TW, FACTORED>(m.it, m.gw + warp * Lp, m.sym + Lp, nb, lane, warp);
+  if (nb > 124) return ring_split<TW, FACTORED, W>(m.it, m.gw + warp * Lp, m.sym + Lp, nb, lane, warp);
   if (warp != 0) return 0.0f;
   const int R = (nb + 31) >> 5;
   if (R == 1) return ring_small<TW, FACTORED, 1>(m.it, m.gw, tb, nb, lane);
@@ -503,8 +511,8 @@ __device__ __forceinline__ float ring_pairs(const RingSmem& m, const PairTables&
   return ring_small<TW, FACTORED, 4>(m.it, m.gw, tb, nb, lane);
 }
 
-template <int TW>
-__global__ void __launch_bounds__(kRingWarps * 32, LTR_RING_MIN_CTAS)
+template <int TW, int W>
+__global__ void __launch_bounds__(W * 32, W == kRingWarpsLong ? LTR_RING_MIN_CTAS : 6)
 pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                  int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,
@@ -512,7 +520,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
                  unsigned int* __restrict__ queue, const unsigned int* __restrict__ order,
                  const PairTables* __restrict__ tabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const RingSmem m = ring_carve(smem_raw, L, P, tma ? rel_bytes : 0);
+  const RingSmem m = ring_carve(smem_raw, L, P, tma ? rel_bytes : 0, W);
   const PairTables& tb = *tabs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Lp = (L + 127) / 128 * 128;
@@ -590,7 +598,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     }
 
     // ---- rank_by_score ----------------------------------------------------------------------------------
-    if (sorted) cta_block_sort(m.keys, P, lane, warp, kRingWarps);
+    if (sorted) cta_block_sort(m.keys, P, lane, warp, W);
 
     // ---- ideal DCG ---------------------------------------------------------------------------------------
     float max_dcg = 1.0f;
@@ -634,7 +642,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
           if (j < nb) key = desc_key_i32(m.raw_y[j]);
           m.keys[j] = j < L ? pack_key(key, j) : ~0ull;
         }
-        cta_block_sort(m.keys, P, lane, warp, kRingWarps);
+        cta_block_sort(m.keys, P, lane, warp, W);
         float part = 0.0f;
         for (int r = threadIdx.x; r < nb; r += blockDim.x)
           part += exp_gain_f32(m.raw_y[static_cast<int>(m.keys[r] & 0xffffffffu)]) / tb.disc[r];
@@ -664,7 +672,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
       if (lane == 0) { m.red[warp] = lmax; m.red[8 + warp] = lmin; }
       __syncthreads();
       smax = m.red[0]; smin = m.red[8];
-      for (int w = 1; w < kRingWarps; ++w) { smax = fmaxf(smax, m.red[w]); smin = fminf(smin, m.red[8 + w]); }
+      for (int w = 1; w < W; ++w) { smax = fmaxf(smax, m.red[w]); smin = fminf(smin, m.red[8 + w]); }
     }
     const float mid = 0.5f * (smax + smin);
     const bool factored = TW != TW_HINGE && fabsf(sigma) * (smax - smin) * kLog2e <= kFactoredRange;
@@ -714,7 +722,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     __syncthreads();   // keys and row fully consumed: their storage becomes the private gradient arrays
     {
       float4* z = reinterpret_cast<float4*>(m.gw);
-      const int nz = (nb > 124 ? kRingWarps : 1) * (Lp >> 2);
+      const int nz = (nb > 124 ? W : 1) * (Lp >> 2);
       for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncthreads();
@@ -722,8 +730,8 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     // ---- all pairs, once ---------------------------------------------------------------------------------
     float wl = 0.0f;
     if (nb > 1) {
-      if constexpr (TW == TW_HINGE) wl = ring_pairs<TW, false>(m, tb, Lp, nb, lane, warp);
-      else wl = factored ? ring_pairs<TW, true>(m, tb, Lp, nb, lane, warp) : ring_pairs<TW, false>(m, tb, Lp, nb, lane, warp);
+      if constexpr (TW == TW_HINGE) wl = ring_pairs<TW, false, W>(m, tb, Lp, nb, lane, warp);
+      else wl = factored ? ring_pairs<TW, true, W>(m, tb, Lp, nb, lane, warp) : ring_pairs<TW, false, W>(m, tb, Lp, nb, lane, warp);
     }
     float loss = cta_sum(wl + diag, m.red);   // its barriers also publish the private arrays
     float gmul = gscale;
@@ -744,7 +752,7 @@ pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel,
     // ---- gradient: sum of the private arrays, back to document order -----------------------------------
     if (grad_out) {
       float* gdoc = m.it.a;   // the factors are dead
-      const int copies = nb > 124 ? kRingWarps : 1;
+      const int copies = nb > 124 ? W : 1;
       for (int p = threadIdx.x; p < L; p += blockDim.x) {
         float gsum = 0.0f;
         if (p < nb && nb > 1) {
