@@ -166,9 +166,10 @@ int ltr_scale_rows(const float *g, int g_stride, const float *dscores, float *ou
  *   qgrad_out   [B*(F+1)]  per-query parameter gradient: qgrad[b, f] = sum_l dscores[b, l] *
  *                          features[b, l, f] for f < F, qgrad[b, F] = sum_l dscores[b, l] (bias).
  * features float32 [B*L*F] row-major, weight float32 [F], bias float32 [1] or NULL.
- * LTR_EUNSUPPORTED unless F % 4 == 0, F <= 1024, (rel_bytes * L) % 16 == 0, 16-byte aligned
- * features / rel, and 4 L F + rel_bytes L bytes fit in shared memory (callers then fall back to
- * their scorer + ltr_listnet).
+ * When F % 4 == 0, F <= 1024, (rel_bytes * L) % 16 == 0, features / rel are 16-byte aligned and
+ * 4 L F + rel_bytes L bytes fit in shared memory, the block of a query is staged by TMA (double
+ * buffered) and read once; every other shape runs a tiled kernel that streams the block twice inside
+ * the same launch (the second pass is served by L2).
  *
  * ltr_linear_listnet_backward: the backward pass for an upstream gradient g [B] (g_stride 1) or a
  * broadcast one (g_stride 0): dweight_out[f] = sum_b g[b] qgrad[b, f], dbias_out[0] (NULL to skip)

@@ -805,12 +805,80 @@ order_queries_kernel(const void* __restrict__ n, int n_bytes, int B, int L, unsi
   if (tid == 0) { queue[0] = 0u; queue[1] = 0u; }
 }
 
+// Large batches: the same counting sort spread over many CTAs (the single-CTA form serialises 65536
+// shared-memory atomics on ~250 distinct list sizes: 63 us at (65536, 512)).
+//   order_hist_kernel    per-CTA shared histogram of its slice of n, added to the global histogram
+//   order_scatter_kernel every CTA scans the global histogram (decreasing n) into shared memory, then
+//                        places its queries: position = first slot of the size class + a global cursor
+// Workspace: queue[4] | order[B] | hist[LTR_MAX_LIST_SIZE + 1] | cursor[LTR_MAX_LIST_SIZE + 1]; queue, hist
+// and cursor are zeroed by one cudaMemsetAsync.  The order inside a size class depends on the atomics'
+// arrival order: the schedule changes from run to run, the results (per-query, independent) do not.
+constexpr int kOrderBins = LTR_MAX_LIST_SIZE + 1;
+constexpr int kOrderParThreads = 256;
+constexpr int kOrderParMinB = 16384;
+
+__global__ void __launch_bounds__(kOrderParThreads)
+order_hist_kernel(const void* __restrict__ n, int n_bytes, int B, int L, unsigned int* __restrict__ ghist) {
+  __shared__ unsigned int hist[kOrderBins];
+  for (int i = threadIdx.x; i <= L; i += kOrderParThreads) hist[i] = 0u;
+  __syncthreads();
+  for (int i = blockIdx.x * kOrderParThreads + threadIdx.x; i < B; i += gridDim.x * kOrderParThreads)
+    atomicAdd(&hist[load_n(n, n_bytes, i, L)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i <= L; i += kOrderParThreads)
+    if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+}
+
+__global__ void __launch_bounds__(kOrderParThreads)
+order_scatter_kernel(const void* __restrict__ n, int n_bytes, int B, int L, const unsigned int* __restrict__ ghist,
+                     unsigned int* __restrict__ cursor, unsigned int* __restrict__ order) {
+  __shared__ unsigned int first[kOrderBins];   // first[v] = number of queries with n > v
+  __shared__ unsigned int wsum[kOrderParThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // exclusive scan in order of decreasing n: entry e stands for n = L - e
+  const int K = (L + kOrderParThreads) / kOrderParThreads;
+  unsigned int local = 0u;
+  for (int e = tid * K; e < (tid + 1) * K && e <= L; ++e) local += ghist[L - e];
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int w = lane < kOrderParThreads / 32 ? wsum[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < kOrderParThreads / 32) wsum[lane] = w;
+  }
+  __syncthreads();
+  unsigned int run = incl - local + (warp > 0 ? wsum[warp - 1] : 0u);
+  for (int e = tid * K; e < (tid + 1) * K && e <= L; ++e) {
+    first[L - e] = run;
+    run += ghist[L - e];
+  }
+  __syncthreads();
+  for (int i = blockIdx.x * kOrderParThreads + tid; i < B; i += gridDim.x * kOrderParThreads) {
+    const int v = load_n(n, n_bytes, i, L);
+    order[first[v] + atomicAdd(&cursor[v], 1u)] = static_cast<unsigned int>(i);
+  }
+}
+
 struct Schedule {
   unsigned int* queue;          // {next query, finished CTAs / warps}
   const unsigned int* order;    // queries by decreasing n, or nullptr (natural order)
 };
 
-inline size_t schedule_bytes(int B) { return 16u + 4u * static_cast<size_t>(B > 0 ? B : 0); }
+inline size_t schedule_bytes(int B) {
+  const size_t b = static_cast<size_t>(B > 0 ? B : 0);
+  // queue | order [B] | (large batches) histogram + cursors of the multi-CTA counting sort
+  return 16u + 4u * b + (B >= kOrderParMinB ? 2u * 4u * kOrderBins : 0u);
+}
 
 // `slots` = queries that start at once (resident CTAs / warps): below that nothing queues and the
 // order is irrelevant.  LTR_SCHEDULE=natural disables the sort (A-B timing).
@@ -828,8 +896,24 @@ inline int make_schedule(const void* n, int n_bytes, int B, int L, long long slo
   if (ws && ws_bytes >= schedule_bytes(B) && (B > slots || always) && !natural &&
       (reinterpret_cast<uintptr_t>(ws) & 15u) == 0) {
     unsigned int* q = static_cast<unsigned int*>(ws);
-    order_queries_kernel<<<1, kOrderThreads, 0, st>>>(n, n_bytes, B, L, q, q + 4);
-    LTR_CUDA(cudaGetLastError());
+    if (B >= kOrderParMinB) {
+      unsigned int* hist = q + 4 + B;
+      unsigned int* cursor = hist + kOrderBins;
+      LTR_CUDA(cudaMemsetAsync(q, 0, 16, st));
+      LTR_CUDA(cudaMemsetAsync(hist, 0, 2u * 4u * kOrderBins, st));
+      DeviceInfo di;
+      int rc = device_info(&di);
+      if (rc != LTR_OK) return rc;
+      const int want = (B + kOrderParThreads * 4 - 1) / (kOrderParThreads * 4);
+      const int grid = want < di.sms ? want : di.sms;
+      order_hist_kernel<<<grid, kOrderParThreads, 0, st>>>(n, n_bytes, B, L, hist);
+      LTR_CUDA(cudaGetLastError());
+      order_scatter_kernel<<<grid, kOrderParThreads, 0, st>>>(n, n_bytes, B, L, hist, cursor, q + 4);
+      LTR_CUDA(cudaGetLastError());
+    } else {
+      order_queries_kernel<<<1, kOrderThreads, 0, st>>>(n, n_bytes, B, L, q, q + 4);
+      LTR_CUDA(cudaGetLastError());
+    }
     out->queue = q;
     out->order = q + 4;
     return LTR_OK;
@@ -1407,20 +1491,38 @@ int ltr_linear_listnet(const float* features, const float* weight, const float* 
   if (!rel_width_ok(rel_bytes)) return LTR_EINVAL;
   if (F < 1) return LTR_EINVAL;
   if (B > 0 && (!weight || !rel || !loss_out || !qgrad_out)) return LTR_EINVAL;
-  // the fused kernel keeps a whole L x F block in shared memory and moves it by TMA bulk copies
-  if (F % 4 != 0 || F > kFusedMaxF || (static_cast<size_t>(rel_bytes) * L) % 16 != 0 || !aligned16(features) ||
-      !aligned16(rel))
-    return LTR_EUNSUPPORTED;
   DeviceInfo di;
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
   if (B == 0) return LTR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t max_smem = 227u * 1024u;
+  // The fast kernel keeps a whole L x F block in shared memory and moves it by TMA bulk copies; every
+  // other shape (F % 4 != 0, unaligned buffers, blocks larger than shared memory) takes the tiled kernel.
+  const bool fast_ok = F % 4 == 0 && F <= kFusedMaxF && (static_cast<size_t>(rel_bytes) * L) % 16 == 0 &&
+                       aligned16(features) && aligned16(rel) && fused_smem_bytes(L, F, rel_bytes, 1) <= max_smem;
+  static const bool force_tiled = [] {
+    const char* v = getenv("LTR_FUSED");
+    return v && strcmp(v, "tiled") == 0;
+  }();
+  if (!fast_ok || force_tiled) {
+    const size_t smem = fused_tiled_smem_bytes(L, F);
+    if (smem > max_smem) return LTR_EUNSUPPORTED;
+    if (smem > 48 * 1024)
+      LTR_CUDA(cudaFuncSetAttribute(linear_listnet_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    const int vec_ok = F % 4 == 0 && aligned16(features);
+    const long long cap = 2LL * di.sms;
+    const int grid = static_cast<int>(B < cap ? B : cap);
+    linear_listnet_tiled_kernel<<<grid, kFusedThreads, smem, st>>>(features, weight, bias, rel, rel_bytes, n, n_bytes,
+                                                                   B, L, F, vec_ok, scores_out, loss_out, dscores_out,
+                                                                   qgrad_out, loss_sum);
+    LTR_CUDA(cudaGetLastError());
+    return LTR_OK;
+  }
   int nbuf = 2;
   if (fused_smem_bytes(L, F, rel_bytes, 2) > max_smem) nbuf = 1;
   const size_t smem = fused_smem_bytes(L, F, rel_bytes, nbuf);
-  if (smem > max_smem) return LTR_EUNSUPPORTED;
   const int grid = di.sms < B ? di.sms : B;
   if (nbuf == 2) {
     LTR_CUDA(cudaFuncSetAttribute(linear_listnet_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -257,6 +257,128 @@ linear_listnet_kernel(const float* __restrict__ feat, const float* __restrict__ 
   }
 }
 
+// ---- any shape: feature blocks larger than shared memory, F % 4 != 0, unaligned buffers ----------------
+// Same outputs, same arithmetic for the ListNet part; the L x F block of a query is streamed from global
+// memory twice inside ONE kernel -- scores (one warp per row, coalesced), then, after the loss, the weight
+// gradient (thread = (feature, row slice)) -- and the second pass finds the block in L2 (a query's block is
+// at most a few MB), so the HBM traffic stays one pass over the features.  One CTA per query, grid-stride.
+__host__ __device__ inline size_t fused_tiled_smem_bytes(int L, int F) {
+  const size_t fc = F < kFusedThreads ? F : kFusedThreads;
+  const size_t slices = kFusedThreads / fc;
+  return fused_align16(4u * static_cast<size_t>(F)) + 2u * fused_align16(4u * static_cast<size_t>(L)) +
+         fused_align16(4u * slices * fc) + 4u * 128;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 2)
+linear_listnet_tiled_kernel(const float* __restrict__ feat, const float* __restrict__ weight,
+                            const float* __restrict__ bias, const void* __restrict__ rel, int rel_bytes,
+                            const void* __restrict__ n, int n_bytes, int B, int L, int F, int vec_ok,
+                            float* __restrict__ scores_out, float* __restrict__ loss_out,
+                            float* __restrict__ dscores_out, float* __restrict__ qgrad,
+                            float* __restrict__ loss_sum) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int fc = F < kFusedThreads ? F : kFusedThreads;      // features handled per gradient pass
+  const int slices = kFusedThreads / fc;
+  unsigned char* p = smem_raw;
+  float* w_s = reinterpret_cast<float*>(p);            p += fused_align16(4u * static_cast<size_t>(F));
+  float* sc = reinterpret_cast<float*>(p);             p += fused_align16(4u * static_cast<size_t>(L));
+  float* dd = reinterpret_cast<float*>(p);             p += fused_align16(4u * static_cast<size_t>(L));
+  float* part = reinterpret_cast<float*>(p);           p += fused_align16(4u * static_cast<size_t>(slices) * fc);
+  float* red = reinterpret_cast<float*>(p);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int f = tid; f < F; f += kFusedThreads) w_s[f] = weight[f];
+  const float b0 = bias ? bias[0] : 0.0f;
+  __syncthreads();
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int nb = load_n(n, n_bytes, b, L);
+    const float* __restrict__ X = feat + static_cast<size_t>(b) * L * F;
+    const size_t base = static_cast<size_t>(b) * L;
+    const int rows = scores_out ? L : nb;
+    // ---- scores: one warp per row ----------------------------------------------------------------------
+    for (int l = warp; l < rows; l += kFusedWarps) {
+      const float* __restrict__ xr = X + static_cast<size_t>(l) * F;
+      float acc = 0.0f;
+      if (vec_ok) {
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        const float4* w4 = reinterpret_cast<const float4*>(w_s);
+        for (int g = lane; g < (F >> 2); g += 32) {
+          const float4 x = x4[g], w = w4[g];
+          acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc);
+          acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+        }
+      } else {
+        for (int f = lane; f < F; f += 32) acc = fmaf(xr[f], w_s[f], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) sc[l] = acc + b0;
+    }
+    __syncthreads();
+
+    // ---- ListNet (same arithmetic as linear_listnet_kernel) ------------------------------------------
+    float ms = -INFINITY, my = -INFINITY;
+    for (int l = tid; l < nb; l += kFusedThreads) {
+      const float y = static_cast<float>(load_int_clamped(rel, rel_bytes, base + l));
+      dd[l] = y;
+      ms = fmaxf(ms, sc[l]);
+      my = fmaxf(my, y);
+    }
+    cta_max2(ms, my, red);
+    float zs = 0.0f, zy = 0.0f, a = 0.0f;
+    for (int l = tid; l < nb; l += kFusedThreads) {
+      const float ds = sc[l] - ms;
+      const float es = ex2_approx(ds * kLog2e);
+      const float ey = ex2_approx((dd[l] - my) * kLog2e);
+      zs += es; zy += ey;
+      a = fmaf(ey, ds, a);
+    }
+    cta_sum3(zs, zy, a, red);
+    const float loss = nb > 0 ? logf(zs) - a / zy : 0.0f;
+    const float izs = nb > 0 ? 1.0f / zs : 0.0f, izy = nb > 0 ? 1.0f / zy : 0.0f;
+    float dsum = 0.0f, dummy1 = 0.0f, dummy2 = 0.0f;
+    for (int l = tid; l < L; l += kFusedThreads) {
+      float d = 0.0f;
+      const float s = l < rows ? sc[l] : 0.0f;
+      if (l < nb) {
+        const float es = ex2_approx((s - ms) * kLog2e);
+        const float ey = ex2_approx((dd[l] - my) * kLog2e);
+        d = es * izs - ey * izy;
+      }
+      dd[l] = d;
+      dsum += d;
+      if (scores_out) scores_out[base + l] = s;
+      if (dscores_out) dscores_out[base + l] = d;
+    }
+    __syncthreads();                    // cta_max2's slots may be rewritten: everyone is past cta_sum3
+    cta_max2(dummy1, dummy2, red);      // (a barrier with the reduction layout the next call expects)
+    cta_sum3(dsum, dummy1, dummy2, red);
+    if (tid == 0) {
+      loss_out[b] = loss;
+      if (loss_sum) atomicAdd(loss_sum, loss);
+      qgrad[static_cast<size_t>(b) * (F + 1) + F] = dsum;    // d loss_b / d bias
+    }
+
+    // ---- weight gradient G_b[f] = sum_l d_l x_l[f]: the block comes from L2 this time -------------------
+    for (int c0 = 0; c0 < F; c0 += fc) {
+      const int f = tid % fc, slice = tid / fc;
+      float acc = 0.0f;
+      if (slice < slices && c0 + f < F) {
+        const float* __restrict__ col = X + c0 + f;
+#pragma unroll 4
+        for (int l = slice; l < nb; l += slices) acc = fmaf(dd[l], col[static_cast<size_t>(l) * F], acc);
+      }
+      if (slice < slices) part[slice * fc + f] = acc;
+      __syncthreads();
+      if (tid < fc && c0 + tid < F) {
+        float s = 0.0f;
+        for (int sl = 0; sl < slices; ++sl) s += part[sl * fc + tid];     // fixed order: deterministic
+        qgrad[static_cast<size_t>(b) * (F + 1) + c0 + tid] = s;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // out[f] = sum_b g[b * g_stride] * qgrad[b, f] for a chunk of queries per CTA -> partials[cta, f]
 __global__ void __launch_bounds__(256)
 weighted_colsum_kernel(const float* __restrict__ qgrad, const float* __restrict__ g, int g_stride, int B,

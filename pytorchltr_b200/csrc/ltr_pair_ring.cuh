@@ -33,6 +33,9 @@ namespace ltr {
 #ifndef LTR_RING_MIN_CTAS
 #define LTR_RING_MIN_CTAS 3   // resident CTAs per SM the register allocation aims at (A-B timing: -DLTR_RING_MIN_CTAS=4)
 #endif
+#ifndef LTR_RING_SHORT_CTAS
+#define LTR_RING_SHORT_CTAS 6   // same for the 4-warp CTAs of short lists
+#endif
 constexpr int kRingMaxL = 1024;
 // Warps per CTA (= per query).  8 for lists up to 1024 documents; 4 for lists up to 512 (the (65536, 512)
 // configuration): half the private gradient arrays (28 KB of shared memory per CTA at L = 512), every
@@ -512,7 +515,7 @@ __device__ __forceinline__ float ring_pairs(const RingSmem& m, const PairTables&
 }
 
 template <int TW, int W>
-__global__ void __launch_bounds__(W * 32, W == kRingWarpsLong ? LTR_RING_MIN_CTAS : 6)
+__global__ void __launch_bounds__(W * 32, W == kRingWarpsLong ? LTR_RING_MIN_CTAS : LTR_RING_SHORT_CTAS)
 pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                  int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,

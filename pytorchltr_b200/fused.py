@@ -64,7 +64,7 @@ class _LinearListNet(torch.autograd.Function):
                                         None, st)
             fused = rc == 0
             if rc == -2:
-                # shape the fused kernel does not take (F % 4, block larger than shared memory):
+                # LTR_EUNSUPPORTED: not even the tiled kernel's O(L + F) shared memory fits (F beyond ~50k):
                 # scorer by the library GEMV, then the ListNet kernel
                 s = torch.mv(x.reshape(B * L, F), w)
                 if b is not None:

@@ -628,12 +628,14 @@ def _fused_batch(seed, B, L, F):
 
 
 @pytest.mark.parametrize("B,L,F", [(5, 8, 4), (37, 200, 136), (300, 40, 64), (3, 100, 256), (4, 50, 12),
-                                   (6, 30, 10), (2, 300, 136)])
+                                   (6, 30, 10), (2, 300, 136), (3, 1000, 136), (2, 700, 45), (2, 64, 700),
+                                   (300, 33, 7)])
 def test_cuda_fused_linear_listnet_vs_oracle(B, L, F):
     """ltr_linear_listnet (one pass over the features) against the float64 oracle: loss and dscores
     within 1e-5 (relative to the row maximum), dweight within 1e-5 of sum |dscores * x| (the scale
-    its float32 accumulation error grows with).  (6, 30, 10) and (2, 300, 136) do not fit the fused
-    kernel (F % 4 != 0; block larger than shared memory) and take the scorer + ltr_listnet path."""
+    its float32 accumulation error grows with).  Shapes the TMA-staged kernel does not take (F % 4 != 0,
+    a feature block larger than shared memory, more features than threads) run the tiled kernel
+    (linear_listnet_tiled_kernel): still one launch, no library GEMV."""
     from pytorchltr_b200.fused import linear_listnet
     X, w, b, y, n = _fused_batch(B * 1000 + L + F, B, L, F)
     n[0] = 0
