@@ -687,6 +687,17 @@ def measure_config(args, name, cfg, rank, world, dev, steps, warmup, windows, sa
     torch.cuda.synchronize()
     outs = [None] * pool_n
     global_queries = cfg["B"] if cfg.get("strong") else B * world
+    # the step's scalar exchange: NVLink peer-memory mailboxes (ltr_p2p_*), NCCL if the mapping fails
+    exchange, exchange_kind = None, "none"
+    if world > 1 and not is_metric:
+        exchange_kind = "nccl all_reduce"
+        if os.environ.get("LTR_EXCHANGE", "p2p") == "p2p":
+            try:
+                from pytorchltr_b200.distributed import PeerScalarExchange
+                exchange = PeerScalarExchange()
+                exchange_kind = "ltr_p2p_allreduce_sum (NVLink peer-memory mailboxes, one single-CTA kernel)"
+            except Exception as e:  # pragma: no cover
+                sys.stderr.write(f"[bench] peer-memory exchange unavailable ({e!r}); using NCCL\n")
 
     def step(i):
         s, y, n = pool[i % pool_n]
@@ -699,7 +710,7 @@ def measure_config(args, name, cfg, rank, world, dev, steps, warmup, windows, sa
             if world > 1:
                 # the path's only exchange: the loss kernel's epilogue leaves the local sum on the
                 # device, the 2-element all-reduce follows inside the same captured step
-                out = sharded_mean_loss(loss_fn, s, y, n, global_count=global_queries)
+                out = sharded_mean_loss(loss_fn, s, y, n, global_count=global_queries, exchange=exchange)
                 out.backward()
             else:
                 out = loss_fn(s, y, n)
@@ -918,7 +929,9 @@ def measure_config(args, name, cfg, rank, world, dev, steps, warmup, windows, sa
                      "note": "binding roofline of the O(L^2) losses (SURVEY.md F4): the kernel needs lg2 of every "
                              "pair and one rcp per two pairs on the 16-lane/clk/SM MUFU pipe"}
     launches_per_step = 1 if is_metric else (2 if family == "listnet" else 3)
-    return {"ms": ms, "B": B, "L": L, "launch": launch, "pool_n": pool_n, "pool_bytes": pool_bytes,
+    if exchange is not None and exchange.timed_out():
+        raise RuntimeError("a peer-memory exchange timed out")
+    return {"ms": ms, "B": B, "L": L, "launch": launch, "exchange": exchange_kind, "pool_n": pool_n, "pool_bytes": pool_bytes,
             "windows": win, "parity": parity, "roofline": roofline, "issue": issue, "loss_fn": loss_fn,
             "is_metric": is_metric, "family": family, "mode": mode, "metric_ld": metric_ld,
             "launches_per_step": launches_per_step, "clock_window": clock_window}
@@ -1091,10 +1104,11 @@ def run_ours(args, name, cfg, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(cfg, world),
             "details": {"B_per_gpu": B, "global_batch": total_queries, "launch": m["launch"],
-                        "step": "sharded_mean_loss(loss_fn, scores, relevance, n, global_count=B).backward() "
-                                "(scalar NCCL all-reduce, fed by the loss kernel's epilogue, inside the captured "
-                                "step; one untimed aligning step between the host barrier and the first timed "
-                                "step)" if world > 1 and not m["is_metric"]
+                        "exchange": m["exchange"],
+                        "step": "sharded_mean_loss(loss_fn, scores, relevance, n, global_count=B, exchange=...)"
+                                ".backward() (scalar all-reduce, fed by the loss kernel's epilogue, inside the "
+                                "captured step; one untimed aligning step between the host barrier and the first "
+                                "timed step)" if world > 1 and not m["is_metric"]
                         else "loss_fn(scores, relevance, n).mean().backward()" if not m["is_metric"]
                         else "metric(scores, relevance, n)",
                         "l2_policy": f"inputs larger than L2: {m['pool_n']} distinct resident batches "

@@ -242,6 +242,24 @@ int ltr_collate_sparse(const int64_t *indptr, const int64_t *indices, const floa
                        int64_t *n_out, void *stream);
 
 /*
+ * Scalar all-reduce over NVLink peer memory (the path's only exchange, the [sum, count]
+ * behind a global mean).  Every rank of ONE node creates a mailbox (device memory, exported by CUDA IPC),
+ * the 64-byte handles are exchanged by the caller (e.g. torch.distributed.all_gather_object) and
+ * connected; ltr_p2p_allreduce_sum then replaces values[0..k) (device, k <= 4) by the sum over all
+ * ranks with one single-CTA kernel on `stream`: remote 64-bit stores carrying {value, sequence number},
+ * a spin on the own mailbox, a sum in rank order (bit-identical on every rank).  CUDA-graph capturable
+ * (the sequence number lives on the device).  Every rank must call it the same number of times; a missing
+ * peer trips a ~2 s timeout and sets the error flag (ltr_p2p_error) instead of hanging.  The reference has
+ * no distributed code; this replaces the ncclAllReduce a torch.distributed caller would issue.
+ */
+typedef struct ltr_p2p ltr_p2p;
+int ltr_p2p_create(int rank, int world, ltr_p2p **out, unsigned char *handle_out /* 64 bytes */);
+int ltr_p2p_connect(ltr_p2p *p, const unsigned char *handles /* world x 64 bytes, rank order */);
+int ltr_p2p_allreduce_sum(ltr_p2p *p, float *values, int k, void *stream);
+int ltr_p2p_error(ltr_p2p *p);
+void ltr_p2p_destroy(ltr_p2p *p);
+
+/*
  * Host-buffer form of the three loss families (the call the reference's CPU path is
  * compared with end to end): copies scores / relevance / n from host memory into `workspace`,
  * runs the fused loss + gradient kernel and copies loss_out [B] and dscores_out [B*L] (if not

@@ -59,6 +59,59 @@ def global_mean(per_query: torch.Tensor, group=None) -> torch.Tensor:
     return (buf[0] / buf[1].clamp(min=1.0)).to(per_query.dtype)
 
 
+class PeerScalarExchange:
+    """Scalar all-reduce over NVLink peer memory for the ranks of ONE node (``ltr_p2p_*`` in
+    ``include/ltr_sm100.h``): every rank owns a mailbox in device memory, exported by CUDA IPC; a step's
+    exchange is one single-CTA kernel (remote 64-bit stores + a spin on the own mailbox) instead of a
+    library collective -- a few microseconds, CUDA-graph capturable.  Construct it once, collectively
+    (the IPC handles travel through ``torch.distributed.all_gather_object``), after the process group
+    exists and the CUDA device of the rank is current; pass it to :func:`sharded_mean_loss`.
+    """
+
+    def __init__(self, group=None):
+        import ctypes
+
+        from pytorchltr_b200 import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerScalarExchange needs an initialised process group")
+        self._lib = _lib.lib()
+        self._check = _lib.check
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._handle = ctypes.c_void_p()
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(self._lib.ltr_p2p_create(self.rank, self.world, ctypes.byref(self._handle), mine))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(mine), group=group)
+        blob = (ctypes.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(gathered))
+        rc = self._lib.ltr_p2p_connect(self._handle, blob)
+        # every rank learns whether every rank connected (a rank that failed must not leave the others
+        # spinning on a mailbox nobody writes)
+        ok = [None] * self.world
+        dist.all_gather_object(ok, rc == 0, group=group)
+        if not all(ok):
+            self.close()
+            raise RuntimeError("CUDA IPC peer mapping failed on rank(s) %s" % [i for i, v in enumerate(ok) if not v])
+
+    def all_reduce_(self, values: torch.Tensor) -> torch.Tensor:
+        """In place: ``values`` (float32 CUDA, 1..4 elements) becomes the sum over all ranks."""
+        if not (values.is_cuda and values.dtype == torch.float32 and values.is_contiguous() and 1 <= values.numel() <= 4):
+            raise ValueError("values must be a contiguous float32 CUDA tensor with 1 to 4 elements")
+        with torch.cuda.device(values.device):
+            self._check(self._lib.ltr_p2p_allreduce_sum(self._handle, values.data_ptr(), values.numel(),
+                                                        torch.cuda.current_stream(values.device).cuda_stream))
+        return values
+
+    def timed_out(self) -> bool:
+        """True if an exchange gave up waiting for a peer (synchronises the device)."""
+        return self._lib.ltr_p2p_error(self._handle) == 1
+
+    def close(self):
+        if self._handle:
+            self._lib.ltr_p2p_destroy(self._handle)
+            self._handle = None
+
+
 class _MeanOfShards(torch.autograd.Function):
     """``total / count`` as a function of the local per-query losses: ``total`` already holds the
     all-reduced sum; the backward pass hands every local query the broadcast gradient ``g / count`` (a
@@ -96,7 +149,8 @@ def _accepts_loss_sum(loss_fn) -> bool:
 
 
 def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.Tensor,
-                      n: torch.Tensor, group=None, global_count: Optional[int] = None) -> torch.Tensor:
+                      n: torch.Tensor, group=None, global_count: Optional[int] = None,
+                      exchange: Optional[PeerScalarExchange] = None) -> torch.Tensor:
     """Global mean loss over the query shards of all ranks.
 
     ``loss_fn(scores, relevance, n)`` runs on the local shard only.  The returned scalar
@@ -109,7 +163,9 @@ def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.
     all-reduce follows the kernel with no reduction launch in between; the whole step (kernel,
     collective, backward) is CUDA-graph capturable.  ``global_count`` (the number of queries over
     all ranks, when the caller knows it -- e.g. a fixed global batch size) shrinks the collective to
-    the sum alone and removes the count arithmetic from the step.  The float32 atomics make the
+    the sum alone and removes the count arithmetic from the step.  ``exchange`` (a
+    :class:`PeerScalarExchange`, ranks of one node) carries the scalars over NVLink peer memory instead
+    of the process group's all-reduce.  The float32 atomics make the
     last bits of the reported mean depend on the summation order; gradients do not depend on it.
 
     Parameter gradients of a model in front of the loss must be SUM-reduced across ranks
@@ -125,7 +181,10 @@ def sharded_mean_loss(loss_fn: Callable, scores: torch.Tensor, relevance: torch.
             buf[1:].fill_(float(scores.shape[0]))
         per_query = loss_fn(scores, relevance, n, loss_sum=buf[:1])
         if _world(group) > 1:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            if exchange is not None:
+                exchange.all_reduce_(buf)
+            else:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     else:
         per_query = loss_fn(scores, relevance, n)
         buf = global_sum_count(per_query, group)

@@ -276,9 +276,37 @@ def _nccl_worker_body(rank, world, port, B, L, out_dir):
     graph.replay()
     graph.replay()
     torch.cuda.synchronize()
+    # NVLink peer-memory exchange (ltr_p2p_*): same sums as NCCL, eager and captured, many steps in a row
+    from pytorchltr_b200.distributed import PeerScalarExchange
+    ex = PeerScalarExchange()
+    p2p_ok = True
+    for it in range(300):
+        k = 1 + it % 4
+        v = torch.arange(k, device=dev, dtype=torch.float32) * (rank + 1) + it * 0.5 + rank
+        ref = v.clone()
+        dist.all_reduce(ref)
+        ex.all_reduce_(v)
+        p2p_ok = p2p_ok and bool(torch.equal(v, ref))
+    st3 = st.detach().clone().requires_grad_(True)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            st3.grad = None
+            sharded_mean_loss(mod, st3, yt, nt, global_count=B, exchange=ex).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    st3.grad = None
+    graph3 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph3):
+        pmean = sharded_mean_loss(mod, st3, yt, nt, global_count=B, exchange=ex)
+        pmean.backward()
+    for _ in range(5):
+        graph3.replay()
+    torch.cuda.synchronize()
+    p2p_ok = p2p_ok and not ex.timed_out()
     lo, hi = shard_bounds(B, rank, world)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), mean=mean.item(), grad=st.grad.cpu().numpy(),
-             gmean=gmean.item(), ggrad=st2.grad.cpu().numpy(), lo=lo, hi=hi, gm=gm.item())
+             gmean=gmean.item(), ggrad=st2.grad.cpu().numpy(), lo=lo, hi=hi, gm=gm.item(),
+             p2p_ok=p2p_ok, pmean=pmean.item(), pgrad=st3.grad.cpu().numpy())
     dist.barrier()
     torch.cuda.synchronize()
 
@@ -312,6 +340,9 @@ def test_sharded_mean_loss_two_ranks_nccl(tmp_path):
         gmax = np.abs(ref).max(axis=1, keepdims=True)
         assert (np.abs(d["grad"] - ref) <= 1e-5 * gmax + 1e-9).all()
         assert np.allclose(d["grad"], d["ggrad"], rtol=1e-6, atol=0)
+        assert bool(d["p2p_ok"]), "peer-memory all-reduce disagrees with NCCL (or timed out)"
+        assert float(d["pmean"]) == pytest.approx(loss.mean(), rel=1e-5)
+        assert np.array_equal(d["pgrad"], d["ggrad"])
 
 
 # ------------------------------------------------------------------ round-1 coverage holes
