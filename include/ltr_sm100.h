@@ -186,6 +186,22 @@ int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride
                                 size_t workspace_bytes, void *stream);
 
 /*
+ * MLP scorer: the reference's documented ranker, docs/source/getting-started.rst:42-51
+ *   torch.nn.Sequential(Linear(F, H1), ReLU, Linear(H1, H2), ReLU, Linear(H2, 1))   (136 -> 50 -> 10 -> 1)
+ * applied to the flat feature block in front of any loss of this header:
+ *   scores_out[r] = w3 . relu(W2 relu(W1 features[r, :] + b1) + b2) + b3,  r < rows (= B*L).
+ * features float32 [rows*F] row-major; w1 [H1*F], w2 [H2*H1], w3 [H2] row-major as torch.nn.Linear.weight;
+ * b1 [H1], b2 [H2], b3 [1] or NULL.  Layer 1 runs on the tensor cores (tcgen05.mma kind::tf32 fed by TMA
+ * tensor copies, accumulators in tensor memory): TF32 operands, float32 accumulation -- the arithmetic of
+ * torch.backends.cuda.matmul.allow_tf32 = True; layers 2-3 are float32.  The features are read once, only
+ * the score leaves the SM.  Requires F % 4 == 0, 16-byte aligned features / w1, H1 <= 64, H2 <= 16
+ * (LTR_EUNSUPPORTED otherwise: the caller keeps its own modules for such a model).
+ */
+int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1, const float *b1,
+                   int H1, const float *w2, const float *b2, int H2, const float *w3,
+                   const float *b3, float *scores_out, void *stream);
+
+/*
  * Position-biased click model (click_simulation/pbm.py:12-63): for the document
  * d = rankings[b, r] at rank r,
  *   propensity_out[b, d] = 1 / (2 + r)^eta  if r < min(n[b], cutoff)  else 0    (cutoff 0 = none)

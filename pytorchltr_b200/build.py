@@ -16,12 +16,17 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libltr_sm100.so")
 PARSER_LIB = os.path.join(CSRC, "libltr_svmrank.so")
 PARSER_SRC = os.path.join(CSRC, "svmrank_parser.cpp")
-SOURCES = ["ltr_kernels.cu"]
+SOURCES = ["ltr_kernels.cu", "ltr_mlp.cu"]
+# headers a source does NOT include (so editing them does not recompile it)
+NOT_INCLUDED = {"ltr_kernels.cu": {"ltr_mlp_scorer.cuh"},
+                "ltr_mlp.cu": {f for f in os.listdir(CSRC) if f.endswith(".cuh")} -
+                              {"ltr_mlp_scorer.cuh", "ltr_common.cuh", "ltr_host.cuh"}}
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-cudart", "static",
 ]
 
@@ -64,18 +69,44 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = Non
         build_parser(force)
     if not force and not out and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
-    cmd += ["-D" + d for d in defines]
+    base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    base += ["-D" + d for d in defines]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
+        base += ["-Xptxas", "-v"]
     # g++ from PATH: the image's CC/CXX wrappers are not needed for nvcc's host pass
     env = dict(os.environ)
-    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
+
+    def run(cmd):
+        res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
+
+    # one object per source, recompiled only when the source or a header it includes is newer
+    tag = "" if not defines else "_" + "_".join(sorted(defines)).replace("=", "-")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", tag + ".o"))
+        deps = [os.path.join(CSRC, src), os.path.join(ROOT, "include", "ltr_sm100.h")]
+        deps += [os.path.join(CSRC, h) for h in headers if h not in NOT_INCLUDED.get(src, ())]
+        objs.append(obj)
+        if force or verbose or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
+            cmd = base + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                                text=True)))
+    failed = None
+    for cmd, pr in procs:
+        text, _ = pr.communicate()
+        if verbose or pr.returncode != 0:
+            sys.stderr.write(text)
+        if pr.returncode != 0:
+            failed = cmd
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + " ".join(failed))
+    run(base + ["-shared", "-o", target] + objs)
     return target
 
 

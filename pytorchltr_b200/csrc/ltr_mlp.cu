@@ -1,0 +1,139 @@
+// ltr_mlp.cu -- host side of the MLP scorer entry points of libltr_sm100.so (kernels: ltr_mlp_scorer.cuh).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "ltr_common.cuh"
+#include "ltr_host.cuh"
+#include "ltr_mlp_scorer.cuh"
+#include "ltr_sm100.h"
+
+using namespace ltr;
+
+// ---- MLP scorer (tcgen05 layer 1): tensor maps and launches -------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so the library
+// still links nothing but the static CUDA runtime.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_tiled_fn(EncodeTiledFn* out) {
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    LTR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) return LTR_EUNSUPPORTED;
+    cached.store(fn, std::memory_order_release);
+  }
+  *out = reinterpret_cast<EncodeTiledFn>(fn);
+  return LTR_OK;
+}
+
+// a row-major float32 matrix [nrows, ncols] seen as boxes of `box_cols` x `box_rows`, rows `pitch` bytes
+// apart in shared memory under the matching swizzle; out-of-range elements read as zero
+static int make_map_2d(CUtensorMap* map, const float* base, long long nrows, int ncols, int box_cols, int box_rows) {
+  EncodeTiledFn encode = nullptr;
+  int rc = encode_tiled_fn(&encode);
+  if (rc != LTR_OK) return rc;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ncols), static_cast<cuuint64_t>(nrows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ncols) * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const int pitch = box_cols * 4;
+  const CUtensorMapSwizzle sw = pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tls_cuda_error = static_cast<int>(r);
+    return LTR_ECUDA;
+  }
+  return LTR_OK;
+}
+
+static MlpGeom mlp_geometry(int F, int stages) {
+  MlpGeom g;
+  g.F = F;
+  g.nfull = F / 32;
+  const int w = F - 32 * g.nfull;
+  g.tail_pitch = w == 0 ? 0 : (w <= 8 ? 32 : (w <= 16 ? 64 : 128));
+  g.tail_ksteps = (w + 7) / 8;
+  g.stage_bytes = g.nfull * kMlpChunkX + kMlpTileDocs * g.tail_pitch;
+  g.w1_bytes = g.nfull * kMlpChunkW + kMlpN1 * g.tail_pitch;
+  g.stages = stages;
+  return g;
+}
+
+struct MlpMaps { CUtensorMap x, x_tail, w, w_tail; };
+
+static int mlp_make_maps(MlpMaps* m, const MlpGeom& g, const float* features, long long rows, const float* w1,
+                         int H1) {
+  int rc = LTR_OK;
+  const int tail_cols = g.tail_pitch ? g.tail_pitch / 4 : 32;
+  // a geometry without full chunks (F < 32) or without a tail still gets valid (unused) maps
+  rc = make_map_2d(&m->x, features, rows, g.F, g.F < 32 ? tail_cols : 32, kMlpTileDocs);
+  if (rc != LTR_OK) return rc;
+  rc = make_map_2d(&m->x_tail, features, rows, g.F, tail_cols, kMlpTileDocs);
+  if (rc != LTR_OK) return rc;
+  rc = make_map_2d(&m->w, w1, H1, g.F, g.F < 32 ? tail_cols : 32, kMlpN1);
+  if (rc != LTR_OK) return rc;
+  return make_map_2d(&m->w_tail, w1, H1, g.F, tail_cols, kMlpN1);
+}
+
+static int mlp_check(const float* features, long long rows, int F, const float* w1, int H1, const float* w2, int H2,
+                     const float* w3) {
+  if (rows < 0 || F < 1 || H1 < 1 || H2 < 1) return LTR_EINVAL;
+  if (rows > 0 && (!features || !w1 || !w2 || !w3)) return LTR_EINVAL;
+  // TMA tensor copies: rows of a multiple of 16 bytes on 16-byte boundaries; TMEM tile of 64 hidden units
+  if (F % 4 != 0 || !aligned16(features) || !aligned16(w1)) return LTR_EUNSUPPORTED;
+  if (H1 > kMlpMaxH1 || H2 > kMlpMaxH2 || rows > (1LL << 31) - kMlpTileDocs) return LTR_EUNSUPPORTED;
+  return LTR_OK;
+}
+
+template <int H1, int H2>
+static int launch_mlp_scores(const MlpMaps& m, const MlpGeom& g, const float* b1, const float* w2, const float* b2,
+                             const float* w3, const float* b3, int h1, int h2, long long rows, float* scores_out,
+                             cudaStream_t st, const DeviceInfo& di) {
+  const size_t smem = 1024 + static_cast<size_t>(g.w1_bytes) + static_cast<size_t>(g.stages) * g.stage_bytes +
+                      sizeof(MlpSmallParams);
+  LTR_CUDA(cudaFuncSetAttribute(mlp_scores_kernel<H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  const int ntiles = static_cast<int>((rows + kMlpTileDocs - 1) / kMlpTileDocs);
+  const int grid = ntiles < di.sms ? ntiles : di.sms;
+  mlp_scores_kernel<H1, H2><<<grid, kMlpFwdThreads, smem, st>>>(m.x, m.x_tail, m.w, m.w_tail, g, b1, w2, b2, w3, b3,
+                                                               h1, h2, rows, ntiles, scores_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+extern "C" {
+
+int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
+                              const float* w2, const float* b2, int H2, const float* w3, const float* b3,
+                              float* scores_out, void* stream) {
+  int rc = mlp_check(features, rows, F, w1, H1, w2, H2, w3);
+  if (rc != LTR_OK) return rc;
+  if (rows > 0 && !scores_out) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  if (rows == 0) return LTR_OK;
+  const size_t budget = 227u * 1024u - 1024u - sizeof(MlpSmallParams);
+  MlpGeom g = mlp_geometry(F, 1);
+  if (static_cast<size_t>(g.w1_bytes) + g.stage_bytes > budget) return LTR_EUNSUPPORTED;
+  int stages = static_cast<int>((budget - g.w1_bytes) / g.stage_bytes);
+  g.stages = stages > 4 ? 4 : stages;
+  MlpMaps m;
+  rc = mlp_make_maps(&m, g, features, rows, w1, H1);
+  if (rc != LTR_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (H1 == 50 && H2 == 10) return launch_mlp_scores<50, 10>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
+  if (H1 <= 32 && H2 <= 8) return launch_mlp_scores<32, 8>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
+  return launch_mlp_scores<64, 16>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""GPU probe of the tcgen05 MLP scorer through the C ABI: correctness against float64 on TF32-exact
+inputs, then timing.  python tools/mlp_probe.py [fwd|bwd|all]"""
+import ctypes
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from pytorchltr_b200 import _lib  # noqa: E402
+
+
+def tf32_exact(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def make(rows, F, H1, H2, seed=0, exact=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(rows, F, device="cuda", generator=g)
+    w1 = torch.randn(H1, F, device="cuda", generator=g) / F ** 0.5
+    if exact:
+        x, w1 = tf32_exact(x), tf32_exact(w1)
+    b1 = torch.randn(H1, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(H2, H1, device="cuda", generator=g) / H1 ** 0.5
+    b2 = torch.randn(H2, device="cuda", generator=g) * 0.1
+    w3 = torch.randn(1, H2, device="cuda", generator=g) / H2 ** 0.5
+    b3 = torch.randn(1, device="cuda", generator=g) * 0.1
+    return x, w1, b1, w2, b2, w3, b3
+
+
+def ref_scores(x, w1, b1, w2, b2, w3, b3):
+    d = torch.float64
+    h1 = torch.relu(x.to(d) @ w1.to(d).t() + b1.to(d))
+    h2 = torch.relu(h1 @ w2.to(d).t() + b2.to(d))
+    return (h2 @ w3.to(d).t() + b3.to(d)).reshape(-1)
+
+
+def run_fwd(lib, x, w1, b1, w2, b2, w3, b3):
+    rows, F = x.shape
+    out = torch.full((rows,), float("nan"), device="cuda")
+    rc = lib.ltr_mlp_scores(x.data_ptr(), rows, F, w1.data_ptr(), b1.data_ptr(), w1.shape[0], w2.data_ptr(),
+                            b2.data_ptr(), w2.shape[0], w3.data_ptr(), b3.data_ptr(), out.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    return out
+
+
+def main():
+    lib = _lib.lib()
+    ok = True
+    for (rows, F, H1, H2) in [(128, 136, 50, 10), (1000, 136, 50, 10), (200 * 1024 + 77, 136, 50, 10),
+                              (5000, 128, 50, 10), (5000, 32, 50, 10), (5000, 48, 64, 16), (5000, 700, 32, 8),
+                              (5000, 220, 20, 5), (3000, 24, 50, 10)]:
+        args = make(rows, F, H1, H2)
+        try:
+            out = run_fwd(lib, *args)
+        except Exception as e:  # noqa: BLE001
+            print(f"fwd rows={rows} F={F} H=({H1},{H2}): ERROR {e}")
+            ok = False
+            continue
+        ref = ref_scores(*args)
+        err = (out.double() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        good = err <= 2e-5 * max(scale, 1.0)
+        ok &= good
+        print(f"fwd rows={rows} F={F} H=({H1},{H2}): max|err|={err:.3e} (scale {scale:.2f}) {'OK' if good else 'FAIL'}")
+        if not good:
+            bad = ((out.double() - ref).abs() > 2e-5 * max(scale, 1.0)).nonzero().reshape(-1)
+            print("   first bad rows:", bad[:16].tolist(), "count", bad.numel())
+            print("   out", out[bad[:4]].tolist(), "ref", ref[bad[:4]].tolist())
+    # non-exact inputs: TF32 truncation error against float64
+    args = make(4096, 136, 50, 10, exact=False)
+    out = run_fwd(lib, *args)
+    ref = ref_scores(*args)
+    print(f"fwd full-precision inputs: max|err|={(out.double() - ref).abs().max().item():.3e} "
+          f"mean|err|={(out.double() - ref).abs().mean().item():.3e} (TF32 operands)")
+    # timing at the c4f shape
+    rows = 8192 * 200
+    args = make(rows, 136, 50, 10, exact=False)
+    out = torch.empty(rows, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        return lib.ltr_mlp_scores(args[0].data_ptr(), rows, 136, args[1].data_ptr(), args[2].data_ptr(), 50,
+                                  args[3].data_ptr(), args[4].data_ptr(), 10, args[5].data_ptr(),
+                                  args[6].data_ptr(), out.data_ptr(), st)
+    for _ in range(3):
+        _lib.check(call())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gb = rows * 136 * 4 / 1e9
+    print(f"fwd timing rows={rows}: {ms * 1e3:.1f} us  {gb / ms * 1e3:.0f} GB/s")
+    x = args[0]
+    lin = torch.nn.Sequential(torch.nn.Linear(136, 50), torch.nn.ReLU(), torch.nn.Linear(50, 10), torch.nn.ReLU(),
+                              torch.nn.Linear(10, 1)).cuda()
+    with torch.no_grad():
+        for _ in range(2):
+            lin(x)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(5):
+            lin(x)
+        torch.cuda.synchronize()
+        print(f"torch eager MLP forward (fp32): {(time.perf_counter() - t) / 5 * 1e6:.1f} us")
+    print("PROBE", "OK" if ok else "FAIL")
+
+
+if __name__ == "__main__":
+    main()
