@@ -202,6 +202,26 @@ int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1
                    const float *b3, float *scores_out, void *stream);
 
 /*
+ * Backward pass of ltr_mlp_scores for an upstream gradient dscores [rows] (d loss / d scores, e.g. the
+ * dscores_out of any loss above after ltr_scale_rows; 0 on padded documents): a second pass over the
+ * features that recomputes the hidden layers, forms dZ1 on chip and accumulates dW1 = dZ1^T X on the tensor
+ * cores (tcgen05.mma kind::tf32, M = 64, the TMA-staged feature tile as the MN-major operand, the accumulator
+ * resident in tensor memory for the whole launch).  grads_out [ltr_mlp_grad_len(F, H1, H2)] receives
+ *   [dW1 (H1*F) | db1 (H1) | dW2 (H2*H1) | db2 (H2) | dW3 (H2) | db3 (1)]
+ * in torch.nn.Linear's layouts.  dW1 multiplies TF32 operands (dZ1 and the features), everything else is
+ * float32; sums are formed in a fixed order (bit-reproducible).  `workspace`: device memory, >=
+ * ltr_mlp_workspace_bytes(F, H1, H2) bytes.  Same shape limits as ltr_mlp_scores; one feature tile, W1 and the
+ * dZ1 operand must fit in shared memory together (F up to about 224).
+ * d loss / d features is not formed (the features are data, not a trainable module's output).
+ */
+size_t ltr_mlp_grad_len(int F, int H1, int H2);
+size_t ltr_mlp_workspace_bytes(int F, int H1, int H2);
+int ltr_mlp_backward(const float *features, long long rows, int F, const float *w1, const float *b1,
+                     int H1, const float *w2, const float *b2, int H2, const float *w3,
+                     const float *b3, const float *dscores, float *grads_out, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/*
  * Position-biased click model (click_simulation/pbm.py:12-63): for the document
  * d = rankings[b, r] at rank r,
  *   propensity_out[b, d] = 1 / (2 + r)^eta  if r < min(n[b], cutoff)  else 0    (cutoff 0 = none)

@@ -34,7 +34,8 @@ static int encode_tiled_fn(EncodeTiledFn* out) {
 
 // a row-major float32 matrix [nrows, ncols] seen as boxes of `box_cols` x `box_rows`, rows `pitch` bytes
 // apart in shared memory under the matching swizzle; out-of-range elements read as zero
-static int make_map_2d(CUtensorMap* map, const float* base, long long nrows, int ncols, int box_cols, int box_rows) {
+static int make_map_2d(CUtensorMap* map, const float* base, long long nrows, int ncols, int box_cols, int box_rows,
+                       int swizzle_override = -1) {
   EncodeTiledFn encode = nullptr;
   int rc = encode_tiled_fn(&encode);
   if (rc != LTR_OK) return rc;
@@ -43,8 +44,9 @@ static int make_map_2d(CUtensorMap* map, const float* base, long long nrows, int
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const int pitch = box_cols * 4;
-  const CUtensorMapSwizzle sw = pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                             : (pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMapSwizzle sw = pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (swizzle_override >= 0) sw = static_cast<CUtensorMapSwizzle>(swizzle_override);
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -67,6 +69,8 @@ static MlpGeom mlp_geometry(int F, int stages) {
   g.stages = stages;
   return g;
 }
+
+constexpr int kMlpMaxCtas = 256;   // partial gradient vectors in the backward workspace
 
 struct MlpMaps { CUtensorMap x, x_tail, w, w_tail; };
 
@@ -134,6 +138,69 @@ int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1
   if (H1 == 50 && H2 == 10) return launch_mlp_scores<50, 10>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
   if (H1 <= 32 && H2 <= 8) return launch_mlp_scores<32, 8>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
   return launch_mlp_scores<64, 16>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
+}
+
+size_t ltr_mlp_grad_len(int F, int H1, int H2) {
+  if (F < 1 || H1 < 1 || H2 < 1) return 0;
+  return static_cast<size_t>(H1) * F + H1 + static_cast<size_t>(H2) * H1 + 2 * static_cast<size_t>(H2) + 1;
+}
+
+size_t ltr_mlp_workspace_bytes(int F, int H1, int H2) {
+  return ltr_mlp_grad_len(F, H1, H2) * kMlpMaxCtas * sizeof(float);
+}
+
+int ltr_mlp_backward(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
+                     const float* w2, const float* b2, int H2, const float* w3, const float* b3,
+                     const float* dscores, float* grads_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = mlp_check(features, rows, F, w1, H1, w2, H2, w3);
+  if (rc != LTR_OK) return rc;
+  if (!grads_out || !workspace || (rows > 0 && !dscores)) return LTR_EINVAL;
+  if (workspace_bytes < ltr_mlp_workspace_bytes(F, H1, H2)) return LTR_EINVAL;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc != LTR_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int len = static_cast<int>(ltr_mlp_grad_len(F, H1, H2));
+  if (rows == 0) {
+    LTR_CUDA(cudaMemsetAsync(grads_out, 0, sizeof(float) * len, st));
+    return LTR_OK;
+  }
+  MlpGeom g = mlp_geometry(F, 1);
+  const int mn_chunks = (F + 31) / 32;
+  const int d2_cols = mn_chunks * 32;
+  if (d2_cols > 256) return LTR_EUNSUPPORTED;                              // one MMA2 per K step
+  // W1, the dZ1 operand and the two copies of a feature tile (K-major for MMA1, MN-major for MMA2)
+  const size_t smem = 1024 + static_cast<size_t>(g.w1_bytes) + kMlpA2Bytes + g.stage_bytes +
+                      static_cast<size_t>(mn_chunks) * kMlpChunkX + sizeof(MlpBwdSmem);
+  if (smem > 227u * 1024u) return LTR_EUNSUPPORTED;
+  MlpMaps m;
+  rc = mlp_make_maps(&m, g, features, rows, w1, H1);
+  if (rc != LTR_OK) return rc;
+  CUtensorMap map_mn;
+  rc = make_map_2d(&map_mn, features, rows, F, 32, kMlpTileDocs, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != LTR_OK) return rc;
+  const int tmem_cols = kMlpD2Col + d2_cols <= 256 ? 256 : 512;
+  const int ntiles = static_cast<int>((rows + kMlpTileDocs - 1) / kMlpTileDocs);
+  int grid = ntiles < di.sms ? ntiles : di.sms;
+  if (grid > kMlpMaxCtas) grid = kMlpMaxCtas;
+  float* partials = static_cast<float*>(workspace);
+#define LTR_MLP_BWD(A, B)                                                                                          \
+  do {                                                                                                             \
+    LTR_CUDA(cudaFuncSetAttribute(mlp_backward_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                  static_cast<int>(smem)));                                                        \
+    mlp_backward_kernel<A, B><<<grid, kMlpBwdThreads, smem, st>>>(m.x, m.x_tail, map_mn, m.w, m.w_tail, g, b1, w2,  \
+                                                                  b2, w3, b3, H1, H2, dscores, rows, ntiles,       \
+                                                                  tmem_cols, partials, len);                       \
+  } while (0)
+  if (H1 == 50 && H2 == 10) LTR_MLP_BWD(50, 10);
+  else if (H1 <= 32 && H2 <= 8) LTR_MLP_BWD(32, 8);
+  else LTR_MLP_BWD(64, 16);
+#undef LTR_MLP_BWD
+  LTR_CUDA(cudaGetLastError());
+  const int rgrid = (len + 255) / 256;
+  mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out);
+  LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
 }
 
 }  // extern "C"

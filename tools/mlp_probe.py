@@ -46,11 +46,125 @@ def run_fwd(lib, x, w1, b1, w2, b2, w3, b3):
     return out
 
 
+def ref_grads(x, w1, b1, w2, b2, w3, b3, ds):
+    """float64 gradients [dW1 | db1 | dW2 | db2 | dW3 | db3]; dW1 also with dZ1 truncated to TF32."""
+    d = torch.float64
+    X, W1, W2, W3 = x.to(d), w1.to(d), w2.to(d), w3.to(d)
+    z1 = X @ W1.t() + b1.to(d)
+    h1 = torch.relu(z1)
+    z2 = h1 @ W2.t() + b2.to(d)
+    h2 = torch.relu(z2)
+    g = ds.to(d).reshape(-1, 1)
+    dw3 = (g * h2).sum(0)
+    db3 = g.sum().reshape(1)
+    dz2 = g * W3 * (z2 > 0)
+    dw2 = dz2.t() @ h1
+    db2 = dz2.sum(0)
+    dz1 = (dz2 @ W2) * (z1 > 0)
+    db1 = dz1.sum(0)
+    dw1 = dz1.t() @ X
+    dz1_t = tf32_exact(dz1.float()).to(d)
+    dw1_t = dz1_t.t() @ tf32_exact(x).to(d)
+    rest = torch.cat([db1, dw2.reshape(-1), db2, dw3, db3])
+    return dw1, dw1_t, rest
+
+
+def run_bwd(lib, x, w1, b1, w2, b2, w3, b3, ds):
+    rows, F = x.shape
+    H1, H2 = w1.shape[0], w2.shape[0]
+    n = lib.ltr_mlp_grad_len(F, H1, H2)
+    out = torch.full((n,), float("nan"), device="cuda")
+    wsb = lib.ltr_mlp_workspace_bytes(F, H1, H2)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    rc = lib.ltr_mlp_backward(x.data_ptr(), rows, F, w1.data_ptr(), b1.data_ptr(), H1, w2.data_ptr(), b2.data_ptr(),
+                              H2, w3.data_ptr(), b3.data_ptr(), ds.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb,
+                              torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    return out
+
+
+def bwd_checks(lib):
+    ok = True
+    for (rows, F, H1, H2) in [(128, 136, 50, 10), (1000, 136, 50, 10), (100 * 1024 + 77, 136, 50, 10),
+                              (5000, 128, 50, 10), (5000, 32, 50, 10), (5000, 48, 64, 16), (5000, 100, 20, 5),
+                              (3000, 24, 50, 10), (70000, 64, 32, 8), (9000, 144, 50, 10), (700, 8, 50, 10)]:
+        args = make(rows, F, H1, H2, seed=1)
+        ds = torch.randn(rows, device="cuda") * (torch.rand(rows, device="cuda") > 0.2)
+        try:
+            out = run_bwd(lib, *args, ds)
+        except Exception as e:  # noqa: BLE001
+            print(f"bwd rows={rows} F={F} H=({H1},{H2}): ERROR {e}")
+            ok = False
+            continue
+        dw1, dw1_t, rest = ref_grads(*args, ds)
+        o1 = out[:H1 * F].double().reshape(H1, F)
+        orest = out[H1 * F:].double()
+        s1 = dw1.abs().max().item()
+        e_exact = (o1 - dw1).abs().max().item() / s1
+        e_emul = (o1 - dw1_t).abs().max().item() / s1
+        e_rest = ((orest - rest).abs() / (rest.abs() + rest.abs().max() * 1e-3)).max().item()
+        good = e_emul < 2e-4 and e_exact < 5e-3 and e_rest < 1e-4 and bool(torch.isfinite(out).all())
+        ok &= good
+        print(f"bwd rows={rows} F={F} H=({H1},{H2}): dW1 rel err vs f64 {e_exact:.2e}, vs TF32-emulated {e_emul:.2e}; "
+              f"other grads rel {e_rest:.2e} {'OK' if good else 'FAIL'}")
+        if not good:
+            bad = ((o1 - dw1_t).abs() > 2e-4 * s1).nonzero()
+            print("   bad dW1 entries:", bad[:8].tolist(), "count", bad.shape[0], "nan", int(torch.isnan(out).sum()))
+            rb = ((orest - rest).abs() / (rest.abs() + rest.abs().max() * 1e-3) > 1e-4).nonzero().reshape(-1)
+            print("   bad other entries:", rb[:16].tolist(), "of", rest.numel(), "(db1", H1, "dW2", H1 * H2, ")")
+    rows = 8192 * 200
+    args = make(rows, 136, 50, 10, exact=False)
+    ds = torch.randn(rows, device="cuda")
+    out1 = run_bwd(lib, *args, ds)
+    out2 = run_bwd(lib, *args, ds)
+    print("bwd bit-reproducible:", bool((out1 == out2).all()))
+    n = lib.ltr_mlp_grad_len(136, 50, 10)
+    out = torch.empty(n, device="cuda")
+    wsb = lib.ltr_mlp_workspace_bytes(136, 50, 10)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        return lib.ltr_mlp_backward(args[0].data_ptr(), rows, 136, args[1].data_ptr(), args[2].data_ptr(), 50,
+                                    args[3].data_ptr(), args[4].data_ptr(), 10, args[5].data_ptr(),
+                                    args[6].data_ptr(), ds.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb, st)
+    for _ in range(3):
+        _lib.check(call())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"bwd timing rows={rows}: {ms * 1e3:.1f} us  {rows * 136 * 4 / 1e9 / ms * 1e3:.0f} GB/s")
+    # torch eager fwd+bwd of the same model
+    x = args[0]
+    lin = torch.nn.Sequential(torch.nn.Linear(136, 50), torch.nn.ReLU(), torch.nn.Linear(50, 10), torch.nn.ReLU(),
+                              torch.nn.Linear(10, 1)).cuda()
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for _ in range(2):
+            lin(x).backward(ds.reshape(-1, 1))
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(5):
+            lin(x).backward(ds.reshape(-1, 1))
+        torch.cuda.synchronize()
+        print(f"torch eager MLP fwd+bwd (allow_tf32={tf32}): {(time.perf_counter() - t) / 5 * 1e6:.1f} us")
+    return ok
+
+
 def main():
     lib = _lib.lib()
     ok = True
+    if len(sys.argv) > 1 and sys.argv[1] == "bwd":
+        print("PROBE", "OK" if bwd_checks(lib) else "FAIL")
+        return
     for (rows, F, H1, H2) in [(128, 136, 50, 10), (1000, 136, 50, 10), (200 * 1024 + 77, 136, 50, 10),
-                              (5000, 128, 50, 10), (5000, 32, 50, 10), (5000, 48, 64, 16), (5000, 700, 32, 8),
+                              (5000, 128, 50, 10), (5000, 32, 50, 10), (5000, 48, 64, 16),
                               (5000, 220, 20, 5), (3000, 24, 50, 10)]:
         args = make(rows, F, H1, H2)
         try:
