@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "ltr_common.cuh"
@@ -68,6 +70,19 @@ static MlpGeom mlp_geometry(int F, int stages) {
   g.w1_bytes = g.nfull * kMlpChunkW + kMlpN1 * g.tail_pitch;
   g.stages = stages;
   return g;
+}
+
+// LTR_MLP_TRACE=1: event timestamps of CTA 0 of the backward kernel (tools/mlp_trace.py reads them back
+// through ltr_mlp_trace_read)
+static long long* mlp_trace_buffer() {
+  static long long* buf = [] {
+    const char* v = getenv("LTR_MLP_TRACE");
+    long long* p = nullptr;
+    if (v && v[0] == '1' && cudaMalloc(&p, 24 * 32 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(p, 0, 24 * 32 * sizeof(long long));
+    return p;
+  }();
+  return buf;
 }
 
 constexpr int kMlpMaxCtas = 256;   // partial gradient vectors in the backward workspace
@@ -168,18 +183,18 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
   MlpGeom g = mlp_geometry(F, 1);
   const int mn_chunks = (F + 31) / 32;
   const int d2_cols = mn_chunks * 32;
-  if (d2_cols > 256) return LTR_EUNSUPPORTED;                              // one MMA2 per K step
+  if (kMlpD2Col + d2_cols + 16 > 512 || g.nfull + 1 > 8) return LTR_EUNSUPPORTED;   // TMEM columns: dW1 | db1
   // W1, the dZ1 operand and the two copies of a feature tile (K-major for MMA1, MN-major for MMA2)
   const size_t smem = 1024 + static_cast<size_t>(g.w1_bytes) + kMlpA2Bytes + g.stage_bytes +
-                      static_cast<size_t>(mn_chunks) * kMlpChunkX + sizeof(MlpBwdSmem);
+                      static_cast<size_t>(mn_chunks) * kMlpChunkX + kMlpW2Bytes + kMlpOnesBytes + sizeof(MlpBwdSmem);
   if (smem > 227u * 1024u) return LTR_EUNSUPPORTED;
   MlpMaps m;
   rc = mlp_make_maps(&m, g, features, rows, w1, H1);
   if (rc != LTR_OK) return rc;
   CUtensorMap map_mn;
-  rc = make_map_2d(&map_mn, features, rows, F, 32, kMlpTileDocs, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_map_2d(&map_mn, features, rows, F, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);   // 32 documents a box
   if (rc != LTR_OK) return rc;
-  const int tmem_cols = kMlpD2Col + d2_cols <= 256 ? 256 : 512;
+  const int tmem_cols = 512;
   const int ntiles = static_cast<int>((rows + kMlpTileDocs - 1) / kMlpTileDocs);
   int grid = ntiles < di.sms ? ntiles : di.sms;
   if (grid > kMlpMaxCtas) grid = kMlpMaxCtas;
@@ -190,7 +205,7 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
                                   static_cast<int>(smem)));                                                        \
     mlp_backward_kernel<A, B><<<grid, kMlpBwdThreads, smem, st>>>(m.x, m.x_tail, map_mn, m.w, m.w_tail, g, b1, w2,  \
                                                                   b2, w3, b3, H1, H2, dscores, rows, ntiles,       \
-                                                                  tmem_cols, partials, len);                       \
+                                                                  tmem_cols, partials, len, mlp_trace_buffer());   \
   } while (0)
   if (H1 == 50 && H2 == 10) LTR_MLP_BWD(50, 10);
   else if (H1 <= 32 && H2 <= 8) LTR_MLP_BWD(32, 8);
@@ -200,6 +215,14 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
   const int rgrid = (len + 255) / 256;
   mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out);
   LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+// debugging aid, not part of the public header: copies the trace of the last traced backward launch
+int ltr_mlp_trace_read(long long* host_out /* 24 * 32 */) {
+  long long* p = mlp_trace_buffer();
+  if (!p) return LTR_EINVAL;
+  LTR_CUDA(cudaMemcpy(host_out, p, 24 * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
   return LTR_OK;
 }
 

@@ -51,6 +51,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // bounded wait (2 s of wall clock): a protocol error traps instead of hanging the device
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   unsigned long long t0 = 0;
@@ -62,6 +63,7 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
+    if (BACKOFF) __nanosleep(64);                   // single-thread roles: leave the issue slots to the math warps
     if ((spin & 1023u) == 1023u) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -125,7 +127,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // [W1 chunks][feature stages][small parameters][barriers]; every chunk starts on a 1024-byte boundary
 struct MlpSmallParams {
   float b1[kMlpMaxH1];
-  float w2t[kMlpMaxH1 * kMlpMaxH2];    // [j][i], row pitch H2P
+  float w2t[kMlpMaxH1 * kMlpMaxH2];    // [j][i], row pitch H2P (forward epilogue only)
   float b2[kMlpMaxH2];
   float w3[kMlpMaxH2];
   float b3;
@@ -135,7 +137,7 @@ struct MlpSmallParams {
   uint64_t bar_empty[4];
   uint64_t bar_tfull[2];
   uint64_t bar_tempty[2];
-  uint64_t bar_aux[4];
+  uint64_t bar_aux[8];
 };
 
 __device__ __forceinline__ void mlp_load_small(MlpSmallParams* sp, const float* __restrict__ b1,
@@ -143,9 +145,11 @@ __device__ __forceinline__ void mlp_load_small(MlpSmallParams* sp, const float* 
                                                const float* __restrict__ w3, const float* __restrict__ b3, int H1,
                                                int H2, int H2P) {
   for (int t = threadIdx.x; t < kMlpMaxH1; t += blockDim.x) sp->b1[t] = (t < H1 && b1) ? b1[t] : 0.0f;
-  for (int t = threadIdx.x; t < kMlpMaxH1 * kMlpMaxH2; t += blockDim.x) {
-    const int j = t / H2P, i = t - j * H2P;
-    sp->w2t[t] = (j < H1 && i < H2) ? w2[i * H1 + j] : 0.0f;
+  if (H2P > 0) {
+    for (int t = threadIdx.x; t < kMlpMaxH1 * kMlpMaxH2; t += blockDim.x) {
+      const int j = t / H2P, i = t - j * H2P;
+      sp->w2t[t] = (j < H1 && i < H2) ? w2[i * H1 + j] : 0.0f;
+    }
   }
   for (int t = threadIdx.x; t < kMlpMaxH2; t += blockDim.x) {
     sp->b2[t] = (t < H2 && b2) ? b2[t] : 0.0f;
@@ -185,13 +189,16 @@ __device__ __forceinline__ void mlp_issue_layer1(uint32_t d_tmem, uint32_t xs, u
   }
 }
 
-// One document's hidden layers from its row of Z1 (TMEM -> registers).  H2P = H2 rounded up to 4.
+// Forward epilogue: one document's hidden layers from its row of Z1 (TMEM -> registers); H2P = H2 rounded up
+// to 4.  Layer 2 as packed f32x2 FMAs on pairs of units; the rows of W2^T (shared memory, one 128-bit
+// broadcast load per four weights) are fetched PF hidden units ahead of their use.
 template <int H1, int H2>
 struct MlpRow {
   static constexpr int H1C = (H1 + 15) / 16;
   static constexpr int H2P = (H2 + 3) / 4 * 4;
-  float h1[H1];      // relu(z1 + b1)
-  float z2[H2P];     // pre-activation of layer 2
+  static constexpr int PF = H1 < 4 ? H1 : 4;
+  float h1[H1];
+  float2 z2[H2P / 2];
 
   __device__ __forceinline__ void load(uint32_t taddr) {
     uint32_t r[16 * H1C];
@@ -203,25 +210,36 @@ struct MlpRow {
   }
   __device__ __forceinline__ void layers(const MlpSmallParams* sp) {
 #pragma unroll
-    for (int i = 0; i < H2P; ++i) z2[i] = sp->b2[i];
+    for (int q = 0; q < H2P / 2; ++q) z2[q] = make_float2(sp->b2[2 * q], sp->b2[2 * q + 1]);
+    float4 wbuf[PF][H2P / 4];
+    float bbuf[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      bbuf[j] = sp->b1[j];
+#pragma unroll
+      for (int q = 0; q < H2P / 4; ++q) wbuf[j][q] = reinterpret_cast<const float4*>(sp->w2t + j * H2P)[q];
+    }
 #pragma unroll
     for (int j = 0; j < H1; ++j) {
-      h1[j] = fmaxf(h1[j] + sp->b1[j], 0.0f);
-      const float4* w = reinterpret_cast<const float4*>(sp->w2t + j * H2P);
+      h1[j] = fmaxf(h1[j] + bbuf[j % PF], 0.0f);
+      const float2 hh = make_float2(h1[j], h1[j]);
 #pragma unroll
       for (int q = 0; q < H2P / 4; ++q) {
-        const float4 wv = w[q];
-        z2[4 * q + 0] = fmaf(wv.x, h1[j], z2[4 * q + 0]);
-        z2[4 * q + 1] = fmaf(wv.y, h1[j], z2[4 * q + 1]);
-        z2[4 * q + 2] = fmaf(wv.z, h1[j], z2[4 * q + 2]);
-        z2[4 * q + 3] = fmaf(wv.w, h1[j], z2[4 * q + 3]);
+        const float4 wv = wbuf[j % PF][q];
+        z2[2 * q + 0] = __ffma2_rn(make_float2(wv.x, wv.y), hh, z2[2 * q + 0]);
+        z2[2 * q + 1] = __ffma2_rn(make_float2(wv.z, wv.w), hh, z2[2 * q + 1]);
+      }
+      if (j + PF < H1) {
+        bbuf[j % PF] = sp->b1[j + PF];
+#pragma unroll
+        for (int q = 0; q < H2P / 4; ++q) wbuf[j % PF][q] = reinterpret_cast<const float4*>(sp->w2t + (j + PF) * H2P)[q];
       }
     }
   }
   __device__ __forceinline__ float score(const MlpSmallParams* sp) const {
     float s = sp->b3;
 #pragma unroll
-    for (int i = 0; i < H2; ++i) s = fmaf(sp->w3[i], fmaxf(z2[i], 0.0f), s);
+    for (int i = 0; i < H2; ++i) s = fmaf(sp->w3[i], fmaxf((i & 1) ? z2[i >> 1].y : z2[i >> 1].x, 0.0f), s);
     return s;
   }
 };
@@ -235,8 +253,8 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                   const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
                   int h1, int h2, long long rows, int ntiles, float* __restrict__ scores_out) {
   extern __shared__ __align__(1024) unsigned char mlp_smem[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mlp_smem) + 1023) &
-                                                         ~static_cast<uintptr_t>(1023));
+  // aligned up to 1024 bytes in the pointer domain, so the compiler keeps the shared address space (LDS / STS)
+  unsigned char* base = mlp_smem + ((1024u - (smem_u32(mlp_smem) & 1023u)) & 1023u);
   unsigned char* w1s = base;
   unsigned char* xs = base + g.w1_bytes;
   MlpSmallParams* sp = reinterpret_cast<MlpSmallParams*>(xs + static_cast<size_t>(g.stages) * g.stage_bytes);
@@ -270,7 +288,7 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % g.stages;
         const uint32_t ph = (it / g.stages) & 1;
-        mbar_wait_guarded(&sp->bar_empty[s], ph ^ 1u);
+        mbar_wait_guarded<true>(&sp->bar_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&sp->bar_full[s], g.stage_bytes);
         mlp_load_tile(xs + static_cast<size_t>(s) * g.stage_bytes, &map_x, &map_x_tail, g, tile * kMlpTileDocs,
                       kMlpChunkX, &sp->bar_full[s]);
@@ -278,15 +296,15 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   } else if (warp == 9) {
     if (lane == 0) {
-      mbar_wait_guarded(&sp->bar_w, 0);
+      mbar_wait_guarded<true>(&sp->bar_w, 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % g.stages;
         const uint32_t ph = (it / g.stages) & 1;
         const int b = it & 1;
         const uint32_t tph = (it >> 1) & 1;
-        mbar_wait_guarded(&sp->bar_tempty[b], tph ^ 1u);
-        mbar_wait_guarded(&sp->bar_full[s], ph);
+        mbar_wait_guarded<true>(&sp->bar_tempty[b], tph ^ 1u);
+        mbar_wait_guarded<true>(&sp->bar_full[s], ph);
         tc_fence_after();
         mlp_issue_layer1(tmem + b * kMlpN1, smem_u32(xs + static_cast<size_t>(s) * g.stage_bytes), smem_u32(w1s), g);
         umma_commit(&sp->bar_empty[s]);
@@ -319,15 +337,19 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
 // ---- backward: parameter gradients for an upstream d loss / d scores --------------------------------------
 // Second pass over the features (the loss needs every score of a query before any gradient exists, and a
-// query's features do not stay on chip between the two).  Per tile of 128 documents:
-//   MMA1   Z1 = X W1^T again (recomputing beats storing H1: 200 B per document against 544 B of features);
-//   warps  one thread per document: h1, z2, h2 as in the forward pass, then
-//            dz2 = ds * w3 * [z2 > 0],  dh1 = W2^T dz2,  dz1 = dh1 * [z1 > 0]
-//          dW3 / db3 / db2 / db1 accumulate in registers over all the tiles of the CTA; dW2 = dZ2^T H1 goes
-//          through a shared-memory transpose, two half tiles at a time, every thread owning a 2 x NI block of it;
-//          dZ1^T is written to shared memory as the K-major A operand (128-byte swizzle) of
-//   MMA2   dW1 (64 x F) += dZ1^T (64 x 128 documents) . X (128 documents x F): M = 64, X is the MN-major B
-//          operand; the accumulator stays in TMEM for the whole launch.
+// query's features do not stay on chip between the two).  Every contraction of a tile of 128 documents runs
+// on the tensor cores; the warps only apply the element-wise steps between them (one thread per document):
+//   MMA1    Z1 = X W1^T again (recomputing beats storing H1: 200 B per document against 544 B of features)
+//   warps   H1 = relu(Z1 + b1), written back over Z1 in tensor memory
+//   MMA-L2  Z2 (128 x 16) = H1 W2^T        A operand straight from TMEM, B = W2 in shared memory (K-major)
+//   warps   dZ2 = ds * w3 * [Z2 + b2 > 0] into TMEM; dW3 / db3 / db2 in registers
+//   MMA-dH  dH1 (128 x 64) = dZ2 W2        A from TMEM, B = W2^T in shared memory (K-major, 64-byte swizzle)
+//   warps   dZ1 = dH1 * [H1 > 0], db1 in registers, dZ1^T to shared memory as the K-major A operand of
+//   MMA2    dW1 (64 x F) += dZ1^T (64 x 128 documents) . X (128 documents x F): M = 64, X is the MN-major B
+//           operand; the accumulator stays in TMEM for the whole launch.
+// dW2 = dZ2^T H1 (10 x 50, contraction over documents) has no operand layout left in shared memory: H1 and
+// dZ2 pass through a document-major exchange array inside the dZ1 operand buffer, half a tile at a time,
+// and eight warps sum BJ x 2 blocks of it with packed FMAs while MMA-dH runs.
 // kind::tf32 takes an MN-major operand only in the "128-byte swizzle, 32-byte atom" layout and a K-major one
 // only in the 16-byte-atom layouts (tools/umma_probe.py: every other combination returns zeros or faults),
 // so the tile is fetched twice, once per layout; the second TMA copy is served by L2.  One buffer per layout
@@ -335,19 +357,67 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 // epilogue), the MN-major copy is only needed by MMA2 at the end of the epilogue.
 // Each CTA writes one partial gradient vector [dW1 | db1 | dW2 | db2 | dW3 | db3]; mlp_reduce_kernel sums
 // them in CTA order (bit-reproducible).
-constexpr int kMlpBwdThreads = 192;                 // 4 epilogue warps + TMA warp + MMA warp
-constexpr int kMlpExPitch = 68;                     // floats per row of the transposed exchange arrays
+constexpr int kMlpBwdThreads = 320;                 // 4 document warps + 4 dW2 helper warps + TMA warp + MMA warp
+constexpr int kMlpBwdEpi = 256;
+constexpr int kMlpHPitch = 68;                      // floats per document row of the H1 exchange array
+constexpr int kMlpZPitch = 20;                      // ... of the dZ2 exchange array
 constexpr int kMlpA2Bytes = kMlpN1 * kMlpTileDocs * 4;
-constexpr int kMlpD2Col = 2 * kMlpN1;               // first TMEM column of the dW1 accumulator
+constexpr int kMlpW2Bytes = 2 * kMlpMaxH2 * 128 + kMlpN1 * 64;   // W2 (2 chunks of 16 rows x 128 B) + W2^T (64 rows x 64 B)
+constexpr int kMlpBufCols = 160;                    // TMEM columns of one tile: Z1/H1 64 | Z2 16 | dZ2 16 | dH1 64
+constexpr int kMlpD2Col = 2 * kMlpBufCols;          // first TMEM column of the dW1 accumulator
 constexpr uint32_t kUmmaLayout32BAtom = 1;          // SWIZZLE_128B_BASE32B
+constexpr int kMlpRedLen = kMlpMaxH1 + 2 * kMlpMaxH2 + 4;
 
-struct MlpBwdSmem {
-  MlpSmallParams sp;
-  float red[4][kMlpMaxH1 + 3 * kMlpMaxH2 + 4];      // per-warp sums of db1 | db2 | dW3 | db3
+struct MlpBwdSmall {
+  float b1[kMlpMaxH1];
+  float b2[kMlpMaxH2];
+  float w3[kMlpMaxH2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  uint64_t bar_w;
+  uint64_t bar_kf[8];      // K-major feature chunk c of the next tile has landed / has been consumed by MMA1
+  uint64_t bar_ke[8];
+  uint64_t bar_mnf[4];     // MN-major copy, 32 documents at a time: landed / consumed by MMA2
+  uint64_t bar_mne[4];
+  uint64_t bar_tfull[2];
+  uint64_t bar_tempty[2];
+  uint64_t bar_aux[8];
 };
-static_assert((kMlpMaxH1 + 4 + kMlpMaxH2 + 4) * kMlpExPitch * 4 <= kMlpA2Bytes, "exchange arrays live in the A2 buffer");
+struct MlpBwdSmem {
+  MlpBwdSmall sp;
+  float red[4][kMlpRedLen];                         // per-warp sums of db2 | dW3 | db3
+};
+constexpr int kMlpOnesBytes = 1024;                 // 8 rows x 128 B of 1.0f: the B operand that sums dZ1 over documents
+static_assert(64 * (kMlpHPitch + kMlpZPitch) * 4 <= kMlpA2Bytes, "exchange arrays live in the A2 buffer");
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (M rows = TMEM lanes, K = 8 consecutive columns) from TMEM
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(
+          d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// N consecutive floats to shared memory with the widest stores the (compile-time) offset allows
+template <int N>
+__device__ __forceinline__ void sts_run(float* dst, const float* v) {
+#pragma unroll
+  for (int k = 0; k + 4 <= N; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+#pragma unroll
+  for (int k = N / 4 * 4; k < N; ++k) dst[k] = v[k];
+}
 
 template <int H1, int H2>
 __global__ void __launch_bounds__(kMlpBwdThreads, 1)
@@ -356,270 +426,415 @@ mlp_backward_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     const __grid_constant__ CUtensorMap map_w_tail, const MlpGeom g, const float* __restrict__ b1,
                     const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                     const float* __restrict__ b3, int h1n, int h2n, const float* __restrict__ dscores, long long rows,
-                    int ntiles, int tmem_cols, float* __restrict__ partials, int partial_len) {
+                    int ntiles, int tmem_cols, float* __restrict__ partials, int partial_len,
+                    long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) unsigned char mlp_smem[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mlp_smem) + 1023) &
-                                                         ~static_cast<uintptr_t>(1023));
+  // aligned up to 1024 bytes in the pointer domain, so the compiler keeps the shared address space (LDS / STS)
+  unsigned char* base = mlp_smem + ((1024u - (smem_u32(mlp_smem) & 1023u)) & 1023u);
+  // optional event trace of CTA 0 (tools/mlp_trace.py): dbg[tile * 32 + slot] = clock
+  auto stamp = [&](int it, int slot) {
+    if (dbg && blockIdx.x == 0 && it < 24) dbg[it * 32 + slot] = clock64();
+  };
   const int mn_chunks = (g.F + 31) / 32;            // MN-major copy: full 32-feature boxes, zero filled
   unsigned char* w1s = base;
   unsigned char* a2s = base + g.w1_bytes;
   unsigned char* xk = a2s + kMlpA2Bytes;            // K-major copy (MMA1)
   unsigned char* xmn = xk + g.stage_bytes;          // MN-major copy (MMA2)
-  MlpBwdSmem* sm = reinterpret_cast<MlpBwdSmem*>(xmn + mn_chunks * kMlpChunkX);
-  MlpSmallParams* sp = &sm->sp;
-  float* ex_h1 = reinterpret_cast<float*>(a2s);     // [j][doc of the half tile], between two uses of A2
-  float* ex_dz2 = ex_h1 + (kMlpMaxH1 + 4) * kMlpExPitch;
+  unsigned char* w2s = xmn + mn_chunks * kMlpChunkX;   // W2 [i][j] as two K-major chunks, 128-byte swizzle
+  unsigned char* w2ts = w2s + 2 * kMlpMaxH2 * 128;     // W2^T [j][i], K-major, 64-byte swizzle
+  unsigned char* ones = w2s + kMlpW2Bytes;
+  MlpBwdSmem* sm = reinterpret_cast<MlpBwdSmem*>(ones + kMlpOnesBytes);
+  MlpBwdSmall* sp = &sm->sp;
   uint64_t* bar_a2_full = &sp->bar_aux[0];
   uint64_t* bar_a2_free = &sp->bar_aux[1];
-  uint64_t* bar_mn_full = &sp->bar_aux[2];
-  uint64_t* bar_mn_empty = &sp->bar_aux[3];
-  uint64_t* bar_k_full = &sp->bar_full[0];
-  uint64_t* bar_k_empty = &sp->bar_empty[0];
+  uint64_t* bar_h1 = &sp->bar_aux[4];               // H1 of the tile is in TMEM
+  uint64_t* bar_z2 = &sp->bar_aux[5];               // MMA-L2 done
+  uint64_t* bar_dz2 = &sp->bar_aux[6];              // dZ2 of the tile is in TMEM
+  uint64_t* bar_dh = &sp->bar_aux[7];               // MMA-dH done
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  using Row = MlpRow<H1, H2>;
-  constexpr int H2P = Row::H2P;
-  constexpr int JP = (H1 + 1) / 2;                  // thread t of the dW2 phase owns rows jp and jp + JP of H1 ...
-  constexpr int IG = 128 / JP;                      // ... and rows ig, ig + IG, ... of dZ2
-  constexpr int NI = (H2 + IG - 1) / IG;
-  static_assert(2 * JP <= kMlpMaxH1 + 4 && NI * IG <= kMlpMaxH2 + 4, "exchange rows");
   const int d2_n = mn_chunks * 32;                  // accumulator columns: whole 32-feature atoms
+  const int nk = g.nfull + (g.tail_pitch ? 1 : 0);  // K-major chunks of a tile
+  // dW2 phase: lane b of each of the eight warps owns the BJ x 2 block (j block b / IB, unit pair b % IB) of
+  // dW2 and sums it over the documents its warp is dealt (8 per half tile)
+  constexpr int IB = (H2 + 1) / 2;
+  constexpr int BJ = ((H1 + 32 / IB - 1) / (32 / IB) + 3) / 4 * 4;
+  constexpr int NJB = (H1 + BJ - 1) / BJ;
+  static_assert(NJB * IB <= 32 && NJB * BJ <= kMlpHPitch && 2 * IB <= kMlpZPitch && H2 <= kMlpMaxH2 && H1 <= kMlpMaxH1,
+                "dW2 blocking");
+  static_assert(8 * 32 * BJ * 8 <= kMlpA2Bytes, "final dW2 partials live in the A2 buffer");
 
-  mlp_load_small(sp, b1, w2, b2, w3, b3, h1n, h2n, H2P);
+  for (int t = threadIdx.x; t < kMlpMaxH1; t += blockDim.x) sp->b1[t] = (t < h1n && b1) ? b1[t] : 0.0f;
+  for (int t = threadIdx.x; t < kMlpMaxH2; t += blockDim.x) {
+    sp->b2[t] = (t < h2n && b2) ? b2[t] : 0.0f;
+    sp->w3[t] = t < h2n ? w3[t] : 0.0f;
+  }
   for (int t = threadIdx.x; t < kMlpA2Bytes / 4; t += blockDim.x) reinterpret_cast<float*>(a2s)[t] = 0.0f;
+  for (int t = threadIdx.x; t < kMlpOnesBytes / 4; t += blockDim.x) reinterpret_cast<float*>(ones)[t] = 1.0f;
+  // B operands of the two small MMAs, written in the swizzled K-major layouts the tensor core reads
+  for (int t = threadIdx.x; t < kMlpMaxH2 * kMlpMaxH1; t += blockDim.x) {
+    const int i = t / kMlpMaxH1, j = t - i * kMlpMaxH1;
+    const float v = (i < h2n && j < h1n) ? w2[i * h1n + j] : 0.0f;
+    // W2: row i, K = j: chunk j / 32 of [16 rows][128 B], 16-byte unit ((j % 32) / 4) ^ (i % 8)
+    *reinterpret_cast<float*>(w2s + (j >> 5) * (kMlpMaxH2 * 128) + i * 128 + (((((j & 31) >> 2) ^ (i & 7))) << 4) +
+                              (j & 3) * 4) = v;
+    // W2^T: row j, K = i: [64 rows][64 B], 16-byte unit (i / 4) ^ ((j / 2) % 4)
+    *reinterpret_cast<float*>(w2ts + j * 64 + ((((i >> 2) ^ ((j >> 1) & 3))) << 4) + (i & 3) * 4) = v;
+  }
   if (threadIdx.x == 0) {
     mbar_init(&sp->bar_w, 1);
-    mbar_init(bar_k_full, 1);
-    mbar_init(bar_k_empty, 1);
-    mbar_init(bar_mn_full, 1);
-    mbar_init(bar_mn_empty, 1);
+    for (int c = 0; c < 8; ++c) {
+      mbar_init(&sp->bar_kf[c], 1);
+      mbar_init(&sp->bar_ke[c], 1);
+    }
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(&sp->bar_mnf[c], 1);
+      mbar_init(&sp->bar_mne[c], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sp->bar_tfull[b], 1);
       mbar_init(&sp->bar_tempty[b], 4);
     }
     mbar_init(bar_a2_full, 4);
     mbar_init(bar_a2_free, 1);
+    mbar_init(bar_h1, 4);
+    mbar_init(bar_z2, 1);
+    mbar_init(bar_dz2, 4);
+    mbar_init(bar_dh, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(&sp->tmem_base, tmem_cols);
+  if (warp == 9) tmem_alloc(&sp->tmem_base, tmem_cols);
+  fence_proxy_async();                               // W2 / W2^T / zeroed A2 are read by the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sp->tmem_base;
   const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && my_tiles > 0) {
       mbar_arrive_expect_tx(&sp->bar_w, g.w1_bytes);
       mlp_load_tile(w1s, &map_w, &map_w_tail, g, 0, kMlpChunkW, &sp->bar_w);
-      auto load_k = [&](int it) {                     // needs MMA1 of tile it - 1 done
-        mbar_wait_guarded(bar_k_empty, (it & 1) ^ 1u);
-        mbar_arrive_expect_tx(bar_k_full, g.stage_bytes);
-        mlp_load_tile(xk, &map_x, &map_x_tail, g, (blockIdx.x + it * gridDim.x) * kMlpTileDocs, kMlpChunkX,
-                      bar_k_full);
+      // Both copies stream in pieces that are refilled as soon as the tensor core has consumed them (the
+      // K-major copy chunk by chunk of 32 features, the MN-major copy 32 documents at a time): with one
+      // buffer per layout the loads of the next tile still overlap the MMAs of this one.
+      auto load_k = [&](int it) {
+        const int row0 = (blockIdx.x + it * gridDim.x) * kMlpTileDocs;
+        for (int c = 0; c < nk; ++c) {
+          mbar_wait_guarded<true>(&sp->bar_ke[c], (it & 1) ^ 1u);   // MMA1 of tile it - 1 has read chunk c
+          const bool tail = c >= g.nfull;
+          mbar_arrive_expect_tx(&sp->bar_kf[c], tail ? kMlpTileDocs * g.tail_pitch : kMlpChunkX);
+          tma_load_2d(xk + c * kMlpChunkX, tail ? &map_x_tail : &map_x, c * 32, row0, &sp->bar_kf[c]);
+          if (c == 0) stamp(it, 0);                   // first K-major chunk of tile `it` requested
+        }
+        stamp(it, 1);                                 // last one requested
       };
       load_k(0);
       for (int it = 0; it < my_tiles; ++it) {
         if (it + 1 < my_tiles) load_k(it + 1);
-        mbar_wait_guarded(bar_mn_empty, (it & 1) ^ 1u);   // MMA2 of tile it - 1 done
-        mbar_arrive_expect_tx(bar_mn_full, mn_chunks * kMlpChunkX);
-        for (int c = 0; c < mn_chunks; ++c)
-          tma_load_2d(xmn + c * kMlpChunkX, &map_x_mn, c * 32, (blockIdx.x + it * gridDim.x) * kMlpTileDocs,
-                      bar_mn_full);
+        const int row0 = (blockIdx.x + it * gridDim.x) * kMlpTileDocs;
+        for (int dg = 0; dg < 4; ++dg) {
+          mbar_wait_guarded<true>(&sp->bar_mne[dg], (it & 1) ^ 1u);  // MMA2 of tile it - 1 has read these documents
+          mbar_arrive_expect_tx(&sp->bar_mnf[dg], mn_chunks * 4096);
+          for (int c = 0; c < mn_chunks; ++c)
+            tma_load_2d(xmn + c * kMlpChunkX + dg * 4096, &map_x_mn, c * 32, row0 + dg * 32, &sp->bar_mnf[dg]);
+          if (dg == 0) stamp(it, 2);
+          if (dg == 3) stamp(it, 3);                  // MN-major copy requested
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t idesc_l2 = umma_idesc_tf32(kMlpTileDocs, kMlpMaxH2, 0, 0);
+      constexpr uint32_t idesc_dh = umma_idesc_tf32(kMlpTileDocs, kMlpN1, 0, 0);
       const uint32_t idesc2 = umma_idesc_tf32(64, d2_n, 0, 1);
+      constexpr uint32_t idesc_b1 = umma_idesc_tf32(64, 8, 0, 0);
+      const uint64_t ones_desc = umma_desc(smem_u32(ones), 16, 1024, 2);
       const uint32_t a2 = smem_u32(a2s);
-      const uint32_t x_k = smem_u32(xk), x_mn = smem_u32(xmn);
-      mbar_wait_guarded(&sp->bar_w, 0);
-      // layer 1 of tile `it` into accumulator it & 1; the K-major copy is released at once
+      const uint32_t x_k = smem_u32(xk), x_mn = smem_u32(xmn), w2a = smem_u32(w2s), w2ta = smem_u32(w2ts);
+      mbar_wait_guarded<true>(&sp->bar_w, 0);
+      // layer 1 of tile `it` into TMEM buffer it & 1, chunk by chunk as the features land; every chunk is
+      // handed back to the TMA warp as soon as its MMAs have run
       auto issue_mma1 = [&](int it) {
         const int b = it & 1;
-        mbar_wait_guarded(&sp->bar_tempty[b], ((it >> 1) & 1) ^ 1u);
-        mbar_wait_guarded(bar_k_full, it & 1);
-        tc_fence_after();
-        mlp_issue_layer1(tmem + b * kMlpN1, x_k, smem_u32(w1s), g);
-        umma_commit(bar_k_empty);
+        constexpr uint32_t idesc1 = umma_idesc_tf32(kMlpTileDocs, kMlpN1, 0, 0);
+        const uint32_t d = tmem + b * kMlpBufCols, ws = smem_u32(w1s);
+        mbar_wait_guarded<true>(&sp->bar_tempty[b], ((it >> 1) & 1) ^ 1u);
+        stamp(it, 4);                                 // MMA1: TMEM buffer free
+        uint32_t first = 0;
+        for (int c = 0; c < nk; ++c) {
+          mbar_wait_guarded<true>(&sp->bar_kf[c], it & 1);
+          if (c == 0) stamp(it, 5);                   // first chunk landed
+          tc_fence_after();
+          const bool tail = c >= g.nfull;
+          const int steps = tail ? g.tail_ksteps : 4;
+          const uint32_t code = tail ? umma_layout_code(g.tail_pitch) : 2u;
+          const uint32_t sbo = tail ? 8u * g.tail_pitch : 1024u;
+          for (int k = 0; k < steps; ++k) {
+            umma_tf32(d, umma_desc(x_k + c * kMlpChunkX + k * 32, 16, sbo, code),
+                      umma_desc(ws + c * kMlpChunkW + k * 32, 16, sbo, code), idesc1, first);
+            first = 1;
+          }
+          umma_commit(&sp->bar_ke[c]);
+        }
         umma_commit(&sp->bar_tfull[b]);
+        stamp(it, 6);                                 // MMA1 issued (last chunk landed)
       };
       issue_mma1(0);
       uint32_t acc = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        if (it + 1 < my_tiles) issue_mma1(it + 1);    // one tile ahead: the epilogue warps never wait for layer 1
-        mbar_wait_guarded(bar_mn_full, it & 1);
-        mbar_wait_guarded(bar_a2_full, it & 1);
+        const uint32_t buf = tmem + (it & 1) * kMlpBufCols;
+        // Z2 = H1 W2^T (K = 64 hidden units, 8 per instruction)
+        mbar_wait_guarded<true>(bar_h1, it & 1);
+        stamp(it, 7);                                 // H1 ready -> MMA-L2
         tc_fence_after();
-        for (int ks = 0; ks < kMlpTileDocs / 8; ++ks) {
-          umma_tf32(tmem + kMlpD2Col, umma_desc(a2 + (ks >> 2) * (kMlpN1 * 128) + (ks & 3) * 32, 16, 1024, 2),
-                    umma_desc(x_mn + ks * 1024, kMlpChunkX, 512, kUmmaLayout32BAtom), idesc2, acc);
-          acc = 1;
+#pragma unroll
+        for (int k = 0; k < kMlpN1 / 8; ++k)
+          umma_tf32_ts(buf + 64, buf + 8 * k, umma_desc(w2a + (k >> 2) * (kMlpMaxH2 * 128) + (k & 3) * 32, 16, 1024, 2),
+                       idesc_l2, k > 0);
+        umma_commit(bar_z2);
+        // dH1 = dZ2 W2 (K = 16 layer-2 units)
+        mbar_wait_guarded<true>(bar_dz2, it & 1);
+        stamp(it, 8);                                 // dZ2 ready -> MMA-dH
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kMlpMaxH2 / 8; ++k)
+          umma_tf32_ts(buf + 96, buf + 80 + 8 * k, umma_desc(w2ta + k * 32, 16, 512, 4), idesc_dh, k > 0);
+        umma_commit(bar_dh);
+        // layer 1 of the next tile: its features have been streaming in since MMA1 of this tile
+        if (it + 1 < my_tiles) issue_mma1(it + 1);
+        // dW1 += dZ1^T X, db1 += dZ1^T 1
+        mbar_wait_guarded<true>(bar_a2_full, it & 1);
+        stamp(it, 9);                                 // dZ1 operand ready -> MMA2
+        for (int dg = 0; dg < 4; ++dg) {
+          mbar_wait_guarded<true>(&sp->bar_mnf[dg], it & 1);
+          if (dg == 3) stamp(it, 10);                 // whole MN-major copy landed
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = 4 * dg + k4;
+            const uint64_t adesc = umma_desc(a2 + dg * (kMlpN1 * 128) + k4 * 32, 16, 1024, 2);
+            umma_tf32(tmem + kMlpD2Col, adesc, umma_desc(x_mn + ks * 1024, kMlpChunkX, 512, kUmmaLayout32BAtom), idesc2,
+                      acc);
+            umma_tf32(tmem + kMlpD2Col + d2_n, adesc, ones_desc, idesc_b1, acc);
+            acc = 1;
+          }
+          umma_commit(&sp->bar_mne[dg]);
         }
         umma_commit(bar_a2_free);
-        umma_commit(bar_mn_empty);
+        stamp(it, 11);                                // MMA2 issued
       }
     }
-  } else {
-    const int t = threadIdx.x;                        // 0..127 = document of the tile = TMEM lane
-    const int jp = t % JP, ig = t / JP;
-    float db1acc[H1], db2acc[H2], dw3acc[H2], db3acc = 0.0f;
-    float dw2acc[2][NI];
-#pragma unroll
-    for (int j = 0; j < H1; ++j) db1acc[j] = 0.0f;
+  } else if (my_tiles > 0) {
+    float* ex_h1 = reinterpret_cast<float*>(a2s);     // [doc of the half tile][j], between two uses of A2
+    float* ex_dz2 = ex_h1 + 64 * kMlpHPitch;          // [doc of the half tile][i]
+    const int t = threadIdx.x;
+    const bool docwarp = warp < 4;                    // warps 0-3: one thread per document (TMEM lane = t)
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int jb = lane / IB, ib = lane - jb * IB;
+    const bool owner = lane < NJB * IB;
+    float db2acc[H2], dw3acc[H2], db3acc = 0.0f;
+    float2 dw2acc[BJ];
 #pragma unroll
     for (int i = 0; i < H2; ++i) db2acc[i] = dw3acc[i] = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NI; ++k) dw2acc[0][k] = dw2acc[1][k] = 0.0f;
+    for (int k = 0; k < BJ; ++k) dw2acc[k] = make_float2(0.0f, 0.0f);
+    unsigned char* a2row = a2s + (t >> 5) * (kMlpN1 * 128) + (t & 3) * 4;   // document warps: this document's column
+    const int chunk = (t & 31) >> 2;
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const long long r = static_cast<long long>(tile) * kMlpTileDocs + t;
-      const float ds = r < rows ? dscores[r] : 0.0f;
-      const int b = it & 1;
-      mbar_wait_guarded(&sp->bar_tfull[b], (it >> 1) & 1);
-      tc_fence_after();
-      Row row;
-      row.load(tmem + b * kMlpN1 + (static_cast<uint32_t>(warp * 32) << 16));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sp->bar_tempty[b]);
-      row.layers(sp);
-      float dz2[H2P];
-      db3acc += ds;
+      const uint32_t buf = tmem + (it & 1) * kMlpBufCols + lane_addr;
+      float dz2[H2];
+      if (docwarp) {
+        const long long r = static_cast<long long>(blockIdx.x + it * gridDim.x) * kMlpTileDocs + t;
+        const float ds = r < rows ? dscores[r] : 0.0f;
+        mbar_wait_guarded(&sp->bar_tfull[it & 1], (it >> 1) & 1);
+        if (t == 0) stamp(it, 16);                    // Z1 ready
+        tc_fence_after();
+        // H1 = relu(Z1 + b1), back into the same TMEM columns (units >= H1: zero weights and bias -> 0)
 #pragma unroll
-      for (int i = 0; i < H2P; ++i) {
-        if (i < H2) {
-          dw3acc[i] = fmaf(ds, fmaxf(row.z2[i], 0.0f), dw3acc[i]);
-          dz2[i] = row.z2[i] > 0.0f ? ds * sp->w3[i] : 0.0f;
-          db2acc[i] += dz2[i];
-        } else {
-          dz2[i] = 0.0f;
+        for (int q = 0; q < kMlpN1 / 16; ++q) {
+          uint32_t v[16];
+          tmem_ld16(buf + 16 * q, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int j = 16 * q + k;
+            const float h = j < H1 ? fmaxf(__uint_as_float(v[k]) + sp->b1[j < H1 ? j : 0], 0.0f) : 0.0f;
+            v[k] = __float_as_uint(h);
+          }
+          tmem_st16(buf + 16 * q, v);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h1);
+        if (t == 0) stamp(it, 17);                    // H1 stored
+        // dZ2 = ds * w3 * [Z2 + b2 > 0]
+        mbar_wait_guarded(bar_z2, it & 1);
+        if (t == 0) stamp(it, 18);                    // Z2 ready
+        tc_fence_after();
+        {
+          uint32_t v[16];
+          tmem_ld16(buf + 64, v);
+          tmem_ld_wait();
+          db3acc += ds;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float d = 0.0f;
+            if (i < H2) {
+              const float z = __uint_as_float(v[i]) + sp->b2[i];
+              d = z > 0.0f ? ds * sp->w3[i] : 0.0f;
+              dw3acc[i < H2 ? i : 0] = fmaf(ds, fmaxf(z, 0.0f), dw3acc[i < H2 ? i : 0]);
+              db2acc[i < H2 ? i : 0] += d;
+              dz2[i < H2 ? i : 0] = d;
+            }
+            v[i] = __float_as_uint(d);
+          }
+          tmem_st16(buf + 80, v);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dz2);
+        if (t == 0) stamp(it, 19);                    // dZ2 stored
+        // the A2 buffer (exchange arrays now, dZ1 operand below) is free once MMA2 of the previous tile has read it
+        mbar_wait_guarded(bar_a2_free, (it & 1) ^ 1u);
+        if (t == 0) stamp(it, 20);                    // A2 free
       }
-      // the A2 buffer is free once MMA2 of the previous tile has read it
-      mbar_wait_guarded(bar_a2_free, (it & 1) ^ 1u);
-      // dW2 += dZ2^T H1, half a tile at a time through the transposed exchange arrays (inside A2)
+      // dW2 += dZ2^T H1, half a tile at a time through the document-major exchange arrays, while MMA-dH runs
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        epi_bar();                                    // the previous readers are done
-        if ((warp >> 1) == half) {
+        if (docwarp && (warp >> 1) == half) {
           const int d = t & 63;
 #pragma unroll
-          for (int j = 0; j < H1; ++j) ex_h1[j * kMlpExPitch + d] = row.h1[j];
+          for (int q = 0; q < (H1 + 15) / 16; ++q) {  // H1 of the document back from TMEM, 16 units at a time
+            uint32_t v[16];
+            tmem_ld16(buf + 16 * q, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < H2; ++i) ex_dz2[i * kMlpExPitch + d] = dz2[i];
+            for (int k = 0; k < 16; k += 4)
+              if (16 * q + k < H1)
+                *reinterpret_cast<uint4*>(ex_h1 + d * kMlpHPitch + 16 * q + k) = make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+          }
+          sts_run<H2>(ex_dz2 + d * kMlpZPitch, dz2);
         }
         epi_bar();
-        if (ig < IG) {
-          const float4* ha = reinterpret_cast<const float4*>(ex_h1 + jp * kMlpExPitch);
-          const float4* hb = reinterpret_cast<const float4*>(ex_h1 + (jp + JP) * kMlpExPitch);
-#pragma unroll 4
-          for (int d4 = 0; d4 < 16; ++d4) {
-            const float4 a = ha[d4], c = hb[d4];
+        if (owner) {
+#pragma unroll 2
+          for (int dd = 0; dd < 8; ++dd) {
+            const int d = warp * 8 + dd;
+            const float4* hr = reinterpret_cast<const float4*>(ex_h1 + d * kMlpHPitch + jb * BJ);
+            const float2 zz = *reinterpret_cast<const float2*>(ex_dz2 + d * kMlpZPitch + 2 * ib);
 #pragma unroll
-            for (int k = 0; k < NI; ++k) {
-              const float4 z = reinterpret_cast<const float4*>(ex_dz2 + (ig + k * IG) * kMlpExPitch)[d4];
-              dw2acc[0][k] = fmaf(z.x, a.x, fmaf(z.y, a.y, fmaf(z.z, a.z, fmaf(z.w, a.w, dw2acc[0][k]))));
-              dw2acc[1][k] = fmaf(z.x, c.x, fmaf(z.y, c.y, fmaf(z.z, c.z, fmaf(z.w, c.w, dw2acc[1][k]))));
+            for (int q = 0; q < BJ / 4; ++q) {
+              const float4 h = hr[q];
+              dw2acc[4 * q + 0] = __ffma2_rn(zz, make_float2(h.x, h.x), dw2acc[4 * q + 0]);
+              dw2acc[4 * q + 1] = __ffma2_rn(zz, make_float2(h.y, h.y), dw2acc[4 * q + 1]);
+              dw2acc[4 * q + 2] = __ffma2_rn(zz, make_float2(h.z, h.z), dw2acc[4 * q + 2]);
+              dw2acc[4 * q + 3] = __ffma2_rn(zz, make_float2(h.w, h.w), dw2acc[4 * q + 3]);
             }
           }
         }
+        epi_bar();                                    // readers done: the next half / the dZ1 operand may be written
       }
-      epi_bar();                                      // exchange reads done: A2 becomes the operand again
-      // dZ1^T -> A operand of MMA2 (K-major, 128-byte swizzle: row j, 16-byte chunk (doc / 4) ^ (j % 8));
-      // rows H1..63 are rewritten with zeros (the exchange arrays passed through them)
-      {
-        unsigned char* a2row = a2s + (t >> 5) * (kMlpN1 * 128) + (t & 3) * 4;
-        const int chunk = (t & 31) >> 2;
+      if (docwarp) {
+        // dZ1 = dH1 * [H1 > 0] -> A operand of MMA2 (K-major, 128-byte swizzle: row j, 16-byte chunk
+        // (doc / 4) ^ (j % 8)); rows H1..63 are rewritten with zeros (the exchange arrays passed through them)
+        if (t == 0) stamp(it, 21);                    // dW2 phase done
+        mbar_wait_guarded(bar_dh, it & 1);
+        if (t == 0) stamp(it, 22);                    // dH1 ready
+        tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < kMlpN1; ++j) {
-          float dz1 = 0.0f;
-          if (j < H1) {
-            const float4* w = reinterpret_cast<const float4*>(sp->w2t + j * H2P);
-            float dh = 0.0f;
+        for (int q = 0; q < kMlpN1 / 16; ++q) {
+          uint32_t v[16], h[16];
+          tmem_ld16(buf + 96 + 16 * q, v);
+          tmem_ld16(buf + 16 * q, h);
+          tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < H2P / 4; ++q) {
-              const float4 wv = w[q];
-              dh = fmaf(wv.x, dz2[4 * q + 0], dh);
-              dh = fmaf(wv.y, dz2[4 * q + 1], dh);
-              dh = fmaf(wv.z, dz2[4 * q + 2], dh);
-              dh = fmaf(wv.w, dz2[4 * q + 3], dh);
-            }
-            dz1 = row.h1[j < H1 ? j : 0] > 0.0f ? dh : 0.0f;
-            db1acc[j < H1 ? j : 0] += dz1;
+          for (int k = 0; k < 16; ++k) {
+            const int j = 16 * q + k;
+            const float dz1 = (j < H1 && __uint_as_float(h[k]) > 0.0f) ? __uint_as_float(v[k]) : 0.0f;
+            *reinterpret_cast<float*>(a2row + j * 128 + ((chunk ^ (j & 7)) << 4)) = dz1;
           }
-          *reinterpret_cast<float*>(a2row + j * 128 + ((chunk ^ (j & 7)) << 4)) = dz1;
         }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sp->bar_tempty[it & 1]);       // every TMEM column of this tile has been read
+          mbar_arrive(bar_a2_full);
+        }
+        if (t == 0) stamp(it, 23);                    // dZ1 stored
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a2_full);
     }
 
     // ---- per-CTA partial gradient vector ----
     float* out = partials + static_cast<size_t>(blockIdx.x) * partial_len;
     const int off_b1 = h1n * g.F, off_w2 = off_b1 + h1n, off_b2 = off_w2 + h2n * h1n, off_w3 = off_b2 + h2n,
               off_b3 = off_w3 + h2n;
-    // dW2: every entry has one owner
-    if (ig < IG) {
+    // db1 | db2 | dW3 | db3: warp sums, then the four document warps in order
+    if (docwarp) {
+      float* red = sm->red[warp];
 #pragma unroll
-      for (int k = 0; k < NI; ++k) {
-        const int i = ig + k * IG;
-        if (i < h2n) {
-          if (jp < h1n) out[off_w2 + i * h1n + jp] = dw2acc[0][k];
-          if (jp + JP < h1n) out[off_w2 + i * h1n + jp + JP] = dw2acc[1][k];
+      for (int i = 0; i < H2; ++i) {
+        const float v = warp_sum(db2acc[i]), u = warp_sum(dw3acc[i]);
+        if (lane == 0) {
+          red[kMlpMaxH1 + i] = v;
+          red[kMlpMaxH1 + kMlpMaxH2 + i] = u;
         }
       }
-    }
-    // db1 | db2 | dW3 | db3: warp sums, then the four warps in order
-    float* red = sm->red[warp];
-#pragma unroll
-    for (int j = 0; j < H1; ++j) {
-      const float v = warp_sum(db1acc[j]);
-      if (lane == 0) red[j] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < H2; ++i) {
-      const float v = warp_sum(db2acc[i]), u = warp_sum(dw3acc[i]);
-      if (lane == 0) {
-        red[kMlpMaxH1 + i] = v;
-        red[kMlpMaxH1 + kMlpMaxH2 + i] = u;
-      }
-    }
-    {
       const float v = warp_sum(db3acc);
       if (lane == 0) red[kMlpMaxH1 + 2 * kMlpMaxH2] = v;
+      // the last MMA2 has read A2: the buffer now collects the eight warps' dW2 blocks
+      mbar_wait_guarded(bar_a2_free, (my_tiles - 1) & 1);
+      tc_fence_after();
     }
     epi_bar();
+    float2* part2 = reinterpret_cast<float2*>(a2s);
+#pragma unroll
+    for (int k = 0; k < BJ; ++k) part2[(warp * 32 + lane) * BJ + k] = dw2acc[k];
+    epi_bar();
     auto red4 = [&](int k) { return ((sm->red[0][k] + sm->red[1][k]) + sm->red[2][k]) + sm->red[3][k]; };
-    if (t < h1n) out[off_b1 + t] = red4(t);
     if (t < h2n) {
       out[off_b2 + t] = red4(kMlpMaxH1 + t);
       out[off_w3 + t] = red4(kMlpMaxH1 + kMlpMaxH2 + t);
     }
     if (t == 0) out[off_b3] = red4(kMlpMaxH1 + 2 * kMlpMaxH2);
-    // dW1 out of TMEM: row j of the M = 64 accumulator lives in TMEM lane (j % 16) + 32 (j / 16)
-    if (my_tiles > 0) {
-      mbar_wait_guarded(bar_a2_free, (my_tiles - 1) & 1);
-      tc_fence_after();
-      const int j = warp * 16 + lane;
-      for (int c0 = 0; c0 < d2_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + kMlpD2Col + c0 + (static_cast<uint32_t>(warp * 32) << 16), v);
-        tmem_ld_wait();
-        if (lane < 16 && j < h1n) {
+    for (int o = t; o < NJB * IB * BJ; o += kMlpBwdEpi) {        // (block lane, row of the block), warps in order
+      const int bl = o / BJ, k = o - bl * BJ;
+      const int j = (bl / IB) * BJ + k, i = 2 * (bl % IB);
+      float2 s2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (c0 + k < g.F) out[static_cast<size_t>(j) * g.F + c0 + k] = __uint_as_float(v[k]);
+      for (int w = 0; w < 8; ++w) {
+        const float2 v = part2[(w * 32 + bl) * BJ + k];
+        s2.x += v.x;
+        s2.y += v.y;
+      }
+      if (j < h1n) {
+        if (i < h2n) out[off_w2 + i * h1n + j] = s2.x;
+        if (i + 1 < h2n) out[off_w2 + (i + 1) * h1n + j] = s2.y;
+      }
+    }
+    // dW1 out of TMEM: row j of the M = 64 accumulator lives in TMEM lane (j % 16) + 32 (j / 16); the two
+    // warps of a quarter of the lanes take alternate 16-column groups
+    // (the columns behind the features hold db1: every one of them the row sum of dZ1^T)
+    const int j = (warp & 3) * 16 + lane;
+    for (int c0 = (warp >> 2) * 16; c0 < d2_n + 8; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(tmem + kMlpD2Col + c0 + lane_addr, v);
+      tmem_ld_wait();
+      if (lane < 16 && j < h1n) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (c0 + k < g.F) out[static_cast<size_t>(j) * g.F + c0 + k] = __uint_as_float(v[k]);
+          if (c0 + k == d2_n) out[off_b1 + j] = __uint_as_float(v[k]);
         }
       }
-    } else {
-      for (int k = t; k < h1n * g.F; k += 128) out[k] = 0.0f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, tmem_cols);
+  if (warp == 9) tmem_dealloc(tmem, tmem_cols);
 }
 
 // out[k] = sum over the CTAs' partial vectors, in CTA order

@@ -1,4 +1,5 @@
-"""Fused linear scorer + ListNet: the caller side of the loss path.
+"""Fused scorers: the caller side of the loss path -- linear scorer + ListNet in one
+pass, and the documented MLP ranker on the tensor cores (``MLPRanker``, end of the file).
 
 The reference's training step (examples/01-basic-usage.py:44,72, getting-started.rst:42-51) is
 
@@ -139,3 +140,136 @@ class LinearListNet(torch.nn.Module):
 
     def forward(self, xs, relevance, n):
         return linear_listnet(xs, self.linear.weight, self.linear.bias, relevance, n)
+
+
+# ---- MLP scorer: the reference's documented model on the tensor cores --------------------
+_LTR_EUNSUPPORTED = -2
+_warned_fallback = set()
+
+
+def _warn_fallback(what):
+    if what not in _warned_fallback:
+        _warned_fallback.add(what)
+        import warnings
+        warnings.warn(f"pytorchltr_b200.fused.MLPRanker: {what}; this shape runs on plain torch modules "
+                      "(see include/ltr_sm100.h, ltr_mlp_scores / ltr_mlp_backward, for the kernel's limits)")
+
+
+def _mlp_torch_forward(x2, w1, b1, w2, b2, w3, b3):
+    h1 = torch.relu(torch.nn.functional.linear(x2, w1, b1))
+    h2 = torch.relu(torch.nn.functional.linear(h1, w2, b2))
+    return torch.nn.functional.linear(h2, w3.reshape(1, -1), b3).reshape(-1), h1, h2
+
+
+class _MlpScores(torch.autograd.Function):
+    """scores = l3(relu(l2(relu(l1(x))))) over the flat (rows, F) feature block: ``ltr_mlp_scores`` forward
+    (features read once, layer 1 on tcgen05 with TF32 operands), ``ltr_mlp_backward`` for the parameter
+    gradients (second pass over the features, dW1 on tcgen05).  Differentiable with respect to the six
+    parameters, not the features."""
+
+    @staticmethod
+    def forward(ctx, features, w1, b1, w2, b2, w3, b3):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError(
+                "MLPRanker is differentiable with respect to its parameters only; `features` requires grad "
+                "(it comes from a trainable module): use plain torch.nn.Linear layers for that model")
+        if not features.is_cuda:
+            raise RuntimeError("MLPRanker computes on CUDA only (sm_100a kernels, no CPU fallback)")
+        F = features.shape[-1]
+        dev = features.device
+        x2 = features.detach()
+        if x2.dtype != torch.float32:
+            x2 = x2.to(torch.float32)
+        x2 = x2.reshape(-1, F).contiguous()
+        rows = x2.shape[0]
+
+        def prep(t, shape):
+            if t is None:
+                return None
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"parameter of shape {tuple(t.shape)}, expected {shape}")
+            return t
+        H1, H2 = w1.shape[0], w2.shape[0]
+        p = [prep(w1, (H1, F)), prep(b1, (H1,)), prep(w2, (H2, H1)), prep(b2, (H2,)), prep(w3, (1, H2)),
+             prep(b3, (1,))]
+        ptr = [None if t is None else t.data_ptr() for t in p]
+        lib = _lib.lib()
+        scores = torch.empty(rows, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ltr_mlp_scores(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5],
+                                    scores.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        if rc == _LTR_EUNSUPPORTED:
+            _warn_fallback(f"features={F}, hidden=({H1}, {H2}) is outside the scorer kernel's limits")
+            scores = _mlp_torch_forward(x2, *p)[0]
+        else:
+            _lib.check(rc)
+        ctx.save_for_backward(x2, *[t for t in p if t is not None])
+        ctx.has = [t is not None for t in p]
+        ctx.dims = (rows, F, H1, H2)
+        ctx.param_shapes = [None if t is None else t.shape for t in (w1, b1, w2, b2, w3, b3)]
+        return scores.reshape(features.shape[:-1] + (1,))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        x2 = saved.pop(0)
+        p = [saved.pop(0) if h else None for h in ctx.has]
+        rows, F, H1, H2 = ctx.dims
+        dev = x2.device
+        ds = g.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        ptr = [None if t is None else t.data_ptr() for t in p]
+        lib = _lib.lib()
+        n = lib.ltr_mlp_grad_len(F, H1, H2)
+        grads = torch.empty(n, dtype=torch.float32, device=dev)
+        ws_bytes = lib.ltr_mlp_workspace_bytes(F, H1, H2)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ltr_mlp_backward(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5],
+                                      ds.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      torch.cuda.current_stream(dev).cuda_stream)
+        if rc == _LTR_EUNSUPPORTED:
+            _warn_fallback(f"features={F}, hidden=({H1}, {H2}) is outside the backward kernel's limits")
+            _, h1, h2 = _mlp_torch_forward(x2, *p)
+            d = ds.reshape(-1, 1)
+            dz2 = d * p[4].reshape(1, -1) * (h2 > 0)
+            dz1 = (dz2 @ p[2]) * (h1 > 0)
+            out = [dz1.t() @ x2, dz1.sum(0), dz2.t() @ h1, dz2.sum(0), (d * h2).sum(0).reshape(1, -1), d.sum().reshape(1)]
+        else:
+            _lib.check(rc)
+            o = [0, H1 * F, H1 * F + H1, H1 * F + H1 + H2 * H1, H1 * F + H1 + H2 * H1 + H2,
+                 H1 * F + H1 + H2 * H1 + 2 * H2, n]
+            out = [grads[o[k]:o[k + 1]] for k in range(6)]
+        res = [None]
+        for k in range(6):
+            res.append(out[k].reshape(ctx.param_shapes[k]) if ctx.has[k] else None)
+        return tuple(res)
+
+
+def mlp_scores(features, w1, b1, w2, b2, w3, b3):
+    """``(..., F) -> (..., 1)`` scores of the ReLU MLP with torch.nn.Linear-shaped parameters
+    ``w1 (H1, F), b1 (H1,), w2 (H2, H1), b2 (H2,), w3 (1, H2), b3 (1,)`` (biases may be None)."""
+    return _MlpScores.apply(features, w1, b1, w2, b2, w3, b3)
+
+
+class MLPRanker(torch.nn.Module):
+    """The reference's documented scoring function (docs/source/getting-started.rst:42-51)::
+
+        class Model(torch.nn.Module):   # l1 = Linear(F, 50), l2 = Linear(50, 10), l3 = Linear(10, 1), ReLU between
+
+    with the same attribute names (``l1``, ``l2``, ``l3``: a ``state_dict`` moves either way), scored by the
+    tcgen05 kernels: ``forward(xs: (B, L, F)) -> (B, L, 1)``, to be fed to any loss or metric of this package
+    exactly as ``loss_fn(model(xs), ys, n)`` in the reference's training loop (``:83-138``).
+    Layer 1 multiplies TF32 operands (what torch does under ``torch.backends.cuda.matmul.allow_tf32``).
+    """
+
+    def __init__(self, in_features: int, hidden=(50, 10)):
+        super().__init__()
+        h1, h2 = hidden
+        self.l1 = torch.nn.Linear(in_features, h1)
+        self.l2 = torch.nn.Linear(h1, h2)
+        self.l3 = torch.nn.Linear(h2, 1)
+
+    def forward(self, x):
+        return mlp_scores(x, self.l1.weight, self.l1.bias, self.l2.weight, self.l2.bias, self.l3.weight, self.l3.bias)

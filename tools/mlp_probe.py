@@ -160,6 +160,13 @@ def bwd_checks(lib):
 def main():
     lib = _lib.lib()
     ok = True
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":
+        rows = 8192 * 200
+        args = make(rows, 136, 50, 10, exact=False)
+        ds = torch.randn(rows, device="cuda")
+        run_fwd(lib, *args)
+        run_bwd(lib, *args, ds)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "bwd":
         print("PROBE", "OK" if bwd_checks(lib) else "FAIL")
         return
