@@ -238,3 +238,52 @@ def pbm_probabilities(rankings, ys, n, relevance_probs, cutoff=None, eta=1.0):
         pr[b, rk[b]] = obs[b]                                             # :58-62 (inverse permutation)
         cp[b, rk[b]] = rp[ranked_y] * obs[b]                              # :48-53
     return cp, pr
+
+
+# ---- MLP ranker (docs/source/getting-started.rst:42-51: l1 -> relu -> l2 -> relu -> l3), float64 numpy ----
+def tf32_trunc(a):
+    """float32 values with the low 13 mantissa bits cleared: what a kind::tf32 tensor-core operand keeps."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    return (a.view(np.int32) & np.int32(~0x1FFF)).view(np.float32)
+
+
+def mlp_scores(features, w1, b1, w2, b2, w3, b3, tf32=False):
+    """Scores of the documented model on ``features (rows, F)``: float64 arithmetic on the float32 inputs.
+    ``tf32=True`` restates the kernel's operand precision: layer 1 multiplies TF32-truncated features and
+    weights (everything else exact)."""
+    x = np.asarray(features, dtype=np.float32).reshape(-1, np.shape(features)[-1])
+    xa, w1a = (tf32_trunc(x), tf32_trunc(w1)) if tf32 else (x, np.asarray(w1, dtype=np.float32))
+    d = np.float64
+    z1 = xa.astype(d) @ w1a.astype(d).T + np.asarray(b1, d)
+    h1 = np.maximum(z1, 0.0)
+    z2 = h1 @ np.asarray(w2, d).T + np.asarray(b2, d)
+    h2 = np.maximum(z2, 0.0)
+    return (h2 @ np.asarray(w3, d).reshape(-1, 1)).reshape(-1) + float(np.asarray(b3, d).reshape(-1)[0])
+
+
+def mlp_grads(features, w1, b1, w2, b2, w3, b3, dscores, tf32=False):
+    """Parameter gradients ``(dW1, db1, dW2, db2, dW3, db3)`` for an upstream ``dscores (rows,)``.
+    ``tf32=True`` restates the backward kernel's operand precision: every tensor-core product multiplies
+    TF32-truncated operands (X and W1; H1 and W2 for the layer-2 pre-activation that decides the ReLU mask;
+    dZ2 and W2 for dH1; dZ1 and X for dW1; dZ1 for db1), the remaining sums are exact."""
+    d = np.float64
+    x = np.asarray(features, dtype=np.float32).reshape(-1, np.shape(features)[-1])
+    t = tf32_trunc if tf32 else (lambda a: np.asarray(a, dtype=np.float32))
+    w1f, w2f, w3f = (np.asarray(a, dtype=np.float32) for a in (w1, w2, w3))
+    g = np.asarray(dscores, d).reshape(-1, 1)
+    z1 = t(x).astype(d) @ t(w1f).astype(d).T + np.asarray(b1, d)
+    h1 = np.maximum(z1, 0.0)
+    h1_op = t(h1.astype(np.float32)).astype(d) if tf32 else h1
+    z2 = h1_op @ t(w2f).astype(d).T + np.asarray(b2, d)
+    h2 = np.maximum(z2, 0.0)
+    dw3 = (g * h2).sum(0).reshape(1, -1)
+    db3 = g.sum().reshape(1)
+    dz2 = g * w3f.astype(d).reshape(1, -1) * (z2 > 0)
+    dw2 = dz2.T @ h1
+    db2 = dz2.sum(0)
+    dz2_op = t(dz2.astype(np.float32)).astype(d) if tf32 else dz2
+    dz1 = (dz2_op @ t(w2f).astype(d)) * (z1 > 0)
+    dz1_op = t(dz1.astype(np.float32)).astype(d) if tf32 else dz1
+    db1 = dz1_op.sum(0)
+    dw1 = dz1_op.T @ t(x).astype(d)
+    return dw1, db1, dw2, db2, dw3, db3
