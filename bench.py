@@ -71,6 +71,12 @@ CONFIGS = {
     # (SURVEY.md 8(f) N1).  Single GPU per rank (weak scaling); 891 MB of features per batch.
     "c4f": dict(fused="linear_listnet", loss="ListNetLoss", B=8192, L=200, F=136, skew=True,
                 workload="Linear(136,1) scorer + ListNet fused, MSLR-WEB30K-shaped (B=8192, L=200, F=136) fp32"),
+    # config 4 with the reference's documented model (docs/source/getting-started.rst:42-51, 136 -> 50 -> 10 -> 1
+    # ReLU MLP) and its documented loss (:73-75): scorer forward and backward on tcgen05 (ltr_mlp_scores /
+    # ltr_mlp_backward), the loss kernel between them
+    "c4mlp": dict(fused="mlp", loss="PairwiseHingeLoss", B=8192, L=200, F=136, skew=True,
+                  workload="MLP(136-50-10-1) ranker + PairwiseHingeLoss, MSLR-WEB30K-shaped (B=8192, L=200, F=136) "
+                           "tf32 layer 1 / fp32"),
     # forward-only ranking metrics (second half of config 4): 12 L + 12 algorithmic bytes / query
     "c4m": dict(metric="ndcg", k=10, B=8192, L=200, skew=True,
                 workload="ndcg@10 synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
@@ -79,7 +85,7 @@ CONFIGS = {
     "c4d": dict(metric="dcg", k=None, B=8192, L=200, skew=True,
                 workload="dcg at every rank synthetic MSLR-WEB30K-shaped (B=8192, L=200) fp32"),
 }
-DEFAULT_SUB = "ns,c2,c3,c4,c4m,c4a,c4d"
+DEFAULT_SUB = "ns,c2,c3,c4,c4m,c4a,c4d,c4mlp"
 ORACLE_MODE = {"LambdaNDCGLoss2": ("lambda", "ndcg2"), "LambdaNDCGLoss1": ("lambda", "ndcg1"),
                "LambdaARPLoss1": ("lambda", "arp1"), "LambdaARPLoss2": ("lambda", "arp2"),
                "PairwiseHingeLoss": ("additive", "hinge"), "PairwiseDCGHingeLoss": ("additive", "dcg_hinge"),
@@ -284,11 +290,20 @@ def run_reference(args, name, cfg, rank, world):
     fused_w = rng.standard_normal(fused_F or 1).astype(np.float32) * 0.1
     feat_cache = {}
 
+    mlp_p = [rng.standard_normal(sh).astype(np.float32) * 0.1
+             for sh in ((50, fused_F or 1), (50,), (10, 50), (10,), (1, 10), (1,))]
+
     def port_step(s, y, n):
         if fused_F:
             key = len(n)
             if key not in feat_cache:
                 feat_cache[key] = rng.standard_normal((key, L, fused_F), dtype=np.float32)
+            if cfg.get("fused") == "mlp":      # numpy restatement of the model around the C port of the loss
+                x2 = feat_cache[key].reshape(-1, fused_F)
+                sc = oracle.mlp_scores(x2, *mlp_p).reshape(key, L).astype(np.float32)
+                out = oracle_step(oracle, family, mode, cfg, sc, y, n)
+                oracle.mlp_grads(x2, *mlp_p, np.asarray(out[1]).reshape(-1) / key)
+                return out
             return oracle.linear_listnet(feat_cache[key], fused_w, None, y, n)
         return oracle_step(oracle, family, mode, cfg, s, y, n)
 
@@ -1035,6 +1050,195 @@ def python_reference_baseline(name, cfg, dev):
 
 
 # --------------------------------------------------------------------------- our arm
+def measure_mlp(args, cfg, dev, rank=0):
+    """Config c4mlp: `loss_fn(MLPRanker(F)(xs), ys, n).mean().backward()` -- the training step of the reference's
+    getting-started guide -- timed as a CUDA graph, kernel by kernel through the C ABI, and against the same
+    model built from torch.nn.Linear layers."""
+    import numpy as np
+    import torch
+
+    import pytorchltr_b200.loss as losses
+    from pytorchltr_b200 import _lib
+    from pytorchltr_b200.fused import MLPRanker
+
+    B, L, F = cfg["B"], cfg["L"], cfg["F"]
+    rows = B * L
+    _, y_np, n_np = make_batch_numpy(4321 + 1000 * rank, B, L, True)
+    gen = torch.Generator(device=dev).manual_seed(78 + rank)
+    xs = torch.randn(B, L, F, device=dev, generator=gen)            # 891 MB: larger than L2 by itself
+    ys, ns = torch.from_numpy(y_np).to(dev), torch.from_numpy(n_np).to(dev)
+    torch.manual_seed(6)
+    model = MLPRanker(F).to(dev)
+    plain = torch.nn.Sequential(torch.nn.Linear(F, 50), torch.nn.ReLU(), torch.nn.Linear(50, 10), torch.nn.ReLU(),
+                                torch.nn.Linear(10, 1)).to(dev)
+    with torch.no_grad():
+        for a, b in zip((plain[0], plain[2], plain[4]), (model.l1, model.l2, model.l3)):
+            a.weight.copy_(b.weight)
+            a.bias.copy_(b.bias)
+    loss_fn = getattr(losses, cfg["loss"])()
+
+    def step(m=model):
+        m.zero_grad(set_to_none=True)
+        out = loss_fn(m(xs), ys, ns)
+        out.mean().backward()
+        return out
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    launch, run = "eager", step
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run, launch = graph.replay, "cuda_graph"
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA graph capture of the MLP step failed ({e!r}); eager\n")
+            torch.cuda.synchronize()
+    steps = max(10, min(args.steps, 50))
+    ms = timed(run, steps, 3)
+    unfused = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        unfused["allow_tf32" if tf32 else "fp32"] = timed(lambda: step(plain), 5, 2)
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+    # kernel by kernel through the C ABI
+    lib = _lib.lib()
+    p = [t.detach().contiguous() for t in (model.l1.weight, model.l1.bias, model.l2.weight, model.l2.bias,
+                                           model.l3.weight, model.l3.bias)]
+    x2 = xs.reshape(rows, F)
+    scores = torch.empty(rows, device=dev)
+    ds = torch.randn(rows, device=dev, generator=gen)
+    glen = lib.ltr_mlp_grad_len(F, 50, 10)
+    grads = torch.empty(glen, device=dev)
+    wsb = lib.ltr_mlp_workspace_bytes(F, 50, 10)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd():
+        _lib.check(lib.ltr_mlp_scores(x2.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
+                                      p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), scores.data_ptr(), st))
+
+    def bwd():
+        _lib.check(lib.ltr_mlp_backward(x2.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
+                                        p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), ds.data_ptr(),
+                                        grads.data_ptr(), ws.data_ptr(), wsb, st))
+
+    fwd_ms, bwd_ms = timed(fwd, 20, 3), timed(bwd, 20, 3)
+    sc2 = scores.reshape(B, L).clone()
+
+    def loss_only():
+        loss_fn(sc2, ys, ns)
+
+    loss_ms = timed(loss_only, 20, 3)
+    alg = rows * (4 * F + 4)                                   # features once + the score / upstream gradient
+    peak, peak_src = hbm_peak()
+    flops_fwd = 2.0 * rows * (F * 50 + 50 * 10 + 10)
+    flops_bwd = 2.0 * rows * (F * 50 + 50 * 10 + 10) + 2.0 * rows * (F * 50 + 2 * 50 * 10 + 10)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    ncu = {}
+    if os.path.exists(tpath):
+        ncu = json.load(open(tpath)).get("c4mlp") or {}
+
+    # parity spot check against the float64 restatement with TF32 operands (not timed)
+    import oracle
+    pn = [t.cpu().numpy() for t in p]
+    idx = torch.arange(0, rows, rows // 4096, device=dev)[:4096]
+    fwd()
+    torch.cuda.synchronize()
+    xn = x2[idx].cpu().numpy()
+    ref = oracle.mlp_scores(xn, *pn, tf32=True)
+    got = scores[idx].cpu().double().numpy()
+    serr = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    nsub = 128 * 64
+    dsn = ds[:nsub].clone()
+    rc = lib.ltr_mlp_backward(x2.data_ptr(), nsub, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
+                              p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), dsn.data_ptr(), grads.data_ptr(),
+                              ws.data_ptr(), wsb, st)
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    gref = oracle.mlp_grads(x2[:nsub].cpu().numpy(), *pn, dsn.cpu().numpy(), tf32=True)
+    gref = np.concatenate([g.reshape(-1) for g in gref])
+    gerr = float(np.linalg.norm(grads.cpu().double().numpy() - gref) / max(1e-30, np.linalg.norm(gref)))
+    parity = {"scores_max_err_rel": serr, "grads_norm_err_rel": gerr, "rows_checked": 4096 + nsub,
+              "oracle": "oracle.mlp_scores / mlp_grads, float64 on TF32-truncated operands",
+              "ok": bool(serr <= 2e-5 and gerr <= 2e-2)}
+    return {
+        "workload": cfg["workload"], "B": B, "L": L, "F": F, "steps": steps, "launch": launch,
+        "ms_per_step": ms, "queries_per_s": B / (ms * 1e-3),
+        "kernels_ms": {"ltr_mlp_scores": fwd_ms, "loss (" + cfg["loss"] + ", forward + gradient)": loss_ms,
+                       "ltr_mlp_backward": bwd_ms},
+        "unfused_torch_ms_per_step": unfused,
+        "roofline_forward": {"bound": "hbm", "kernel": "mlp_scores_kernel<50, 10>", "achieved": alg / (fwd_ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": alg / (fwd_ms * 1e-3) / 1e9 / peak,
+                             "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                             "tflops_tf32": flops_fwd / (fwd_ms * 1e-3) / 1e12, "traffic": ncu.get("fwd_dram_bytes"),
+                             "tensor_pipe_active_pct": ncu.get("fwd_tensor_pct")},
+        "roofline_backward": {"bound": "hbm", "kernel": "mlp_backward_kernel<50, 10>",
+                              "achieved": alg / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": alg / (bwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
+                              "peak_source": peak_src, "tflops_tf32": flops_bwd / (bwd_ms * 1e-3) / 1e12,
+                              "traffic": ncu.get("bwd_dram_bytes"), "tensor_pipe_active_pct": ncu.get("bwd_tensor_pct")},
+        "parity_spot_check": parity,
+    }
+
+
+def run_mlp(args, cfg, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    m = measure_mlp(args, cfg, dev, rank)
+    sampler.stop()
+    ms = m["ms_per_step"]
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        cb = config_block(cfg, world)
+        cb.update({"F": cfg["F"], "model": "MLPRanker 136-50-10-1"})
+        line = {
+            "metric": "loss fwd+bwd queries/sec", "value": cfg["B"] * world / (ms * 1e-3), "unit": "queries/s",
+            "n_gpus": world, "steps": m["steps"], "warmup": 3, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (layer 1) / f32", "data": "synthetic", "config": cb,
+            "details": {k: m[k] for k in ("launch", "kernels_ms", "unfused_torch_ms_per_step")},
+            "roofline": m["roofline_forward"], "roofline_backward": m["roofline_backward"], "cpu_baseline": None,
+            "e2e": None, "clocks": sampler.summary("timed region"), "gpu_launches": 6 * m["steps"],
+            "gpu_launches_note": "per step: mlp_scores, loss kernel (+ ordering), row scale, mlp_backward, reduce",
+            "parity_spot_check": m["parity_spot_check"],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args, name, cfg, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -1074,6 +1278,17 @@ def run_ours(args, name, cfg, rank, local_rank, world):
         import gc
         for sname in [x for x in args.sub.split(",") if x and x != name]:
             scfg = CONFIGS[sname]
+            if scfg.get("fused") == "mlp":
+                m.pop("loss_fn", None)
+                gc.collect()
+                torch.cuda.empty_cache()
+                try:
+                    sub[sname] = measure_mlp(args, scfg, dev)
+                except Exception as e:  # pragma: no cover
+                    sub[sname] = {"workload": scfg["workload"], "error": repr(e)}
+                gc.collect()
+                torch.cuda.empty_cache()
+                continue
             if scfg.get("fused"):
                 continue
             m.pop("loss_fn", None)
@@ -1142,6 +1357,9 @@ def main():
     if world != args.gpus and rank == 0:
         sys.stderr.write(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun "
                          f"for N > 1; running {world} rank(s)\n")
+    if cfg.get("fused") == "mlp":
+        run_mlp(args, cfg, rank, local_rank, world)
+        return
     if cfg.get("fused"):
         run_fused(args, cfg, rank, local_rank, world)
         return
