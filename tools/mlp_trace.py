@@ -22,7 +22,8 @@ lib.ltr_mlp_trace_read.argtypes = [ctypes.c_void_p]
 rc = lib.ltr_mlp_trace_read(buf)
 assert rc == 0, rc
 a = np.array(buf[:], dtype=np.int64).reshape(24, 32)
-names = {0: "Kreq0", 1: "KreqN", 2: "MNreq0", 3: "MNreqN", 4: "m1.buf", 5: "m1.k0", 6: "m1.iss", 7: "h1.rdy", 8: "dz2.rdy",
+names = {0: "Kreq0", 1: "KreqN", 2: "MNreq0", 3: "MNreqN",  # TMA requests: K-major chunks, MN-major document groups
+         4: "m1.buf", 5: "m1.k0", 6: "m1.iss", 7: "h1.rdy", 8: "dz2.rdy",
          9: "a2.rdy", 10: "mn.all", 11: "m2.iss", 16: "Z1", 17: "H1st", 18: "Z2", 19: "dZ2st", 20: "A2free", 21: "dW2done",
          22: "dH", 23: "dZ1st"}
 t0 = a[2, 16]
