@@ -115,6 +115,13 @@ def main():
         for (lbo, sbo, tag) in ((128, K * 16, "lbo=kgroup sbo=mngroup"), (K * 16, 128, "lbo=mngroup sbo=kgroup")):
             run(f"T5 B MN-major NONE {tag} N={N}", A64, Bn, aa, an, none_addr, (N // 4) * K * 16, 64, N, 0, 1,
                 (16, 1024, SW128), (lbo, sbo, NONE), 4, 32, 128)
+    # T8: tail-style SW32 / SW64 MN-major
+    for (pitch, layout, N) in ((32, SW32, 8), (64, SW64, 16)):
+        Bn = tf32(rng.standard_normal((N, K)))
+        ba8, bn8 = mnmajor_rows(N, K, pitch, layout)
+        run(f"T8 B MN-major pitch {pitch} N={N}", A64, Bn, aa, an, ba8, bn8, 64, N, 0, 1, (16, 1024, SW128),
+            (16, 8 * pitch, layout), 4, 32, 8 * pitch)
+
     # T6: K-major A with the 32-byte-atom swizzle (what TMA's SWIZZLE_128B_ATOM_32B would leave), M = 128
     aa6, an6 = kmajor_swizzled(128, K, 128, B32ATOM)
     run("T6 A K-major 128B_ATOM_32B M=128", A, Bm, aa6, an6, ba, bn, 128, 64, 0, 0, (16, 1024, B32ATOM),
@@ -123,12 +130,6 @@ def main():
     ba7, bn7 = kmajor_swizzled(64, K, 128, B32ATOM)
     run("T7 B K-major 128B_ATOM_32B", A, Bm, aa, an * 2, ba7, bn7, 128, 64, 0, 0, (16, 1024, SW128),
         (16, 1024, B32ATOM), 4, 32, 32) if False else None
-    # T8: tail-style SW32 / SW64 MN-major
-    for (pitch, layout, N) in ((32, SW32, 8), (64, SW64, 16)):
-        Bn = tf32(rng.standard_normal((N, K)))
-        ba8, bn8 = mnmajor_rows(N, K, pitch, layout)
-        run(f"T8 B MN-major pitch {pitch} N={N}", A64, Bn, aa, an, ba8, bn8, 64, N, 0, 1, (16, 1024, SW128),
-            (16, 8 * pitch, layout), 4, 32, 8 * pitch)
 
 
 if __name__ == "__main__":
