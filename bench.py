@@ -1135,23 +1135,31 @@ def measure_mlp(args, cfg, dev, rank=0):
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
-    def fwd():
-        _lib.check(lib.ltr_mlp_scores(x2.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
-                                      p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), scores.data_ptr(), st))
+    hz = torch.empty(rows, lib.ltr_mlp_hz_pitch(50, 10), device=dev)
 
-    def bwd():
+    def fwd(keep=True):
+        _lib.check(lib.ltr_mlp_scores(x2.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
+                                      p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), scores.data_ptr(),
+                                      hz.data_ptr() if keep else None, st))
+
+    def bwd(kept=True):
         _lib.check(lib.ltr_mlp_backward(x2.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
-                                        p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), ds.data_ptr(),
-                                        grads.data_ptr(), ws.data_ptr(), wsb, st))
+                                        p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(),
+                                        hz.data_ptr() if kept else None, ds.data_ptr(), grads.data_ptr(),
+                                        ws.data_ptr(), wsb, st))
 
     fwd_ms, bwd_ms = timed(fwd, 20, 3), timed(bwd, 20, 3)
+    fwd_infer_ms = timed(lambda: fwd(False), 20, 3)
+    bwd_recompute_ms = timed(lambda: bwd(False), 20, 3)
     sc2 = scores.reshape(B, L).clone()
 
     def loss_only():
         loss_fn(sc2, ys, ns)
 
     loss_ms = timed(loss_only, 20, 3)
-    alg = rows * (4 * F + 4)                                   # features once + the score / upstream gradient
+    hzb = 4 * hz.shape[1]                                      # kept activation row
+    alg = rows * (4 * F + 4 + hzb)                             # features + activations once + score / upstream gradient
+    alg_infer = rows * (4 * F + 4)
     peak, peak_src = hbm_peak()
     flops_fwd = 2.0 * rows * (F * 50 + 50 * 10 + 10)
     flops_bwd = 2.0 * rows * (F * 50 + 50 * 10 + 10) + 2.0 * rows * (F * 50 + 2 * 50 * 10 + 10)
@@ -1173,8 +1181,8 @@ def measure_mlp(args, cfg, dev, rank=0):
     nsub = 128 * 64
     dsn = ds[:nsub].clone()
     rc = lib.ltr_mlp_backward(x2.data_ptr(), nsub, F, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
-                              p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), dsn.data_ptr(), grads.data_ptr(),
-                              ws.data_ptr(), wsb, st)
+                              p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), hz.data_ptr(), dsn.data_ptr(),
+                              grads.data_ptr(), ws.data_ptr(), wsb, st)
     _lib.check(rc)
     torch.cuda.synchronize()
     gref = oracle.mlp_grads(x2[:nsub].cpu().numpy(), *pn, dsn.cpu().numpy(), tf32=True)
@@ -1186,15 +1194,19 @@ def measure_mlp(args, cfg, dev, rank=0):
     return {
         "workload": cfg["workload"], "B": B, "L": L, "F": F, "steps": steps, "launch": launch,
         "ms_per_step": ms, "queries_per_s": B / (ms * 1e-3),
-        "kernels_ms": {"ltr_mlp_scores": fwd_ms, "loss (" + cfg["loss"] + ", forward + gradient)": loss_ms,
-                       "ltr_mlp_backward": bwd_ms},
+        "kernels_ms": {"ltr_mlp_scores (keeping H1 | Z2 for the backward pass)": fwd_ms,
+                       "loss (" + cfg["loss"] + ", forward + gradient)": loss_ms,
+                       "ltr_mlp_backward (from the kept activations)": bwd_ms,
+                       "ltr_mlp_scores (inference: scores only)": fwd_infer_ms,
+                       "ltr_mlp_backward (recomputing layer 1, no kept activations)": bwd_recompute_ms},
+        "inference_hbm_frac": alg_infer / (fwd_infer_ms * 1e-3) / 1e9 / peak,
         "unfused_torch_ms_per_step": unfused,
         "roofline_forward": {"bound": "hbm", "kernel": "mlp_scores_kernel<50, 10>", "achieved": alg / (fwd_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": alg / (fwd_ms * 1e-3) / 1e9 / peak,
                              "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                              "tflops_tf32": flops_fwd / (fwd_ms * 1e-3) / 1e12, "traffic": ncu.get("fwd_dram_bytes"),
                              "tensor_pipe_active_pct": ncu.get("fwd_tensor_pct")},
-        "roofline_backward": {"bound": "hbm", "kernel": "mlp_backward_kernel<50, 10>",
+        "roofline_backward": {"bound": "hbm", "kernel": "mlp_backward_hz_kernel<50, 10>",
                               "achieved": alg / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": alg / (bwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
                               "peak_source": peak_src, "tflops_tf32": flops_bwd / (bwd_ms * 1e-3) / 1e12,

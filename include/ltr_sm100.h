@@ -196,10 +196,16 @@ int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride
  * torch.backends.cuda.matmul.allow_tf32 = True; layers 2-3 are float32.  The features are read once, only
  * the score leaves the SM.  Requires F % 4 == 0, 16-byte aligned features / w1, H1 <= 64, H2 <= 16
  * (LTR_EUNSUPPORTED otherwise: the caller keeps its own modules for such a model).
+ * hz_out (NULL to skip; what a training step passes): [rows * ltr_mlp_hz_pitch(H1, H2)] floats, the activations
+ * ltr_mlp_backward can start from instead of recomputing layer 1 -- per document relu(W1 x + b1) in columns
+ * [0, H1), the layer-2 pre-activation in [roundup4(H1), + H2), zeros elsewhere (256 B at 50-10, written with
+ * 128-bit stores next to the 544 B of features read).  ltr_mlp_hz_pitch is 0 for shapes without this path
+ * (H1 = 50, H2 = 10 and H1 <= 32, H2 <= 8 have it).
  */
+int ltr_mlp_hz_pitch(int H1, int H2);
 int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1, const float *b1,
                    int H1, const float *w2, const float *b2, int H2, const float *w3,
-                   const float *b3, float *scores_out, void *stream);
+                   const float *b3, float *scores_out, float *hz_out, void *stream);
 
 /*
  * Backward pass of ltr_mlp_scores for an upstream gradient dscores [rows] (d loss / d scores, e.g. the
@@ -213,13 +219,17 @@ int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1
  * ltr_mlp_workspace_bytes(F, H1, H2) bytes.  Same shape limits as ltr_mlp_scores; one feature tile, W1 and the
  * dZ1 operand must fit in shared memory together (F up to about 224).
  * d loss / d features is not formed (the features are data, not a trainable module's output).
+ * hz: the activation rows kept by ltr_mlp_scores (hz_out), or NULL.  With them the launch reads features and
+ * activations once each (no W1, no layer 1 again), uses the forward pass's own ReLU masks (the gradient of
+ * exactly the function the forward kernel computed) and forms ALL sums over documents as one tensor-core
+ * product per 8 documents: [dZ1^T ; dZ2^T] (64 x 8) . [X | H1 | 1] gives dW1, dW2, db1, db2 in one accumulator.
  */
 size_t ltr_mlp_grad_len(int F, int H1, int H2);
 size_t ltr_mlp_workspace_bytes(int F, int H1, int H2);
 int ltr_mlp_backward(const float *features, long long rows, int F, const float *w1, const float *b1,
                      int H1, const float *w2, const float *b2, int H2, const float *w3,
-                     const float *b3, const float *dscores, float *grads_out, void *workspace,
-                     size_t workspace_bytes, void *stream);
+                     const float *b3, const float *hz, const float *dscores, float *grads_out,
+                     void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Position-biased click model (click_simulation/pbm.py:12-63): for the document

@@ -20,7 +20,7 @@ SYMBOLS = (
     "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate",
     "ltr_pbm_probabilities", "ltr_loss_host_ex", "ltr_scale_rows_host", "ltr_collate_sampled", "ltr_collate_sparse",
     "ltr_p2p_create", "ltr_p2p_connect", "ltr_p2p_allreduce_sum", "ltr_p2p_error", "ltr_p2p_destroy",
-    "ltr_mlp_scores", "ltr_mlp_grad_len", "ltr_mlp_workspace_bytes", "ltr_mlp_backward",
+    "ltr_mlp_scores", "ltr_mlp_hz_pitch", "ltr_mlp_grad_len", "ltr_mlp_workspace_bytes", "ltr_mlp_backward",
 )
 
 ADD_HINGE, ADD_DCG_HINGE, ADD_LOGISTIC = 0, 1, 2
@@ -101,14 +101,17 @@ def _declare(lib):
     lib.ltr_p2p_destroy.argtypes = [c_void_p]
     lib.ltr_mlp_scores.restype = c_int
     lib.ltr_mlp_scores.argtypes = [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ltr_mlp_hz_pitch.restype = c_int
+    lib.ltr_mlp_hz_pitch.argtypes = [c_int, c_int]
     lib.ltr_mlp_grad_len.restype = c_size_t
     lib.ltr_mlp_grad_len.argtypes = [c_int, c_int, c_int]
     lib.ltr_mlp_workspace_bytes.restype = c_size_t
     lib.ltr_mlp_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.ltr_mlp_backward.restype = c_int
     lib.ltr_mlp_backward.argtypes = [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]
     lib.ltr_collate_sampled.restype = c_int
     lib.ltr_collate_sampled.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -116,7 +116,7 @@ static int mlp_check(const float* features, long long rows, int F, const float* 
 template <int H1, int H2>
 static int launch_mlp_scores(const MlpMaps& m, const MlpGeom& g, const float* b1, const float* w2, const float* b2,
                              const float* w3, const float* b3, int h1, int h2, long long rows, float* scores_out,
-                             cudaStream_t st, const DeviceInfo& di) {
+                             float* hz_out, cudaStream_t st, const DeviceInfo& di) {
   const size_t smem = 1024 + static_cast<size_t>(g.w1_bytes) + static_cast<size_t>(g.stages) * g.stage_bytes +
                       sizeof(MlpSmallParams);
   LTR_CUDA(cudaFuncSetAttribute(mlp_scores_kernel<H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -124,16 +124,54 @@ static int launch_mlp_scores(const MlpMaps& m, const MlpGeom& g, const float* b1
   const int ntiles = static_cast<int>((rows + kMlpTileDocs - 1) / kMlpTileDocs);
   const int grid = ntiles < di.sms ? ntiles : di.sms;
   mlp_scores_kernel<H1, H2><<<grid, kMlpFwdThreads, smem, st>>>(m.x, m.x_tail, m.w, m.w_tail, g, b1, w2, b2, w3, b3,
-                                                               h1, h2, rows, ntiles, scores_out);
+                                                               h1, h2, rows, ntiles, scores_out, hz_out);
   LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+static int mlp_hz_pitch(int H1, int H2) {
+  if (H1 == 50 && H2 == 10) return MlpHz<50, 10>::P;
+  if (H1 >= 1 && H2 >= 1 && H1 <= 32 && H2 <= 8) return MlpHz<32, 8>::P;
+  return 0;
+}
+
+template <int H1, int H2>
+static int launch_mlp_backward_hz(const float* features, const float* hz, long long rows, int F, const float* w2,
+                                  const float* w3, int h1, int h2, const float* dscores, float* partials, int len,
+                                  int* grid_out, cudaStream_t st, const DeviceInfo& di) {
+  using Hz = MlpHz<H1, H2>;
+  constexpr int NHZ = (Hz::P + 31) / 32;
+  const int nk = (F + 31) / 32;
+  if (2 * kMlpHzBufCols + 32 * nk + 32 * NHZ + 16 > 512) return LTR_EUNSUPPORTED;      // TMEM columns
+  const size_t smem = 1024 + kMlpA2Bytes + static_cast<size_t>(nk + 2 * NHZ) * kMlpChunkX + kMlpN1 * 64 +
+                      kMlpOnesBytes + sizeof(MlpHzSmall);
+  if (smem > 227u * 1024u) return LTR_EUNSUPPORTED;
+  CUtensorMap map_x, map_hz;
+  int rc = make_map_2d(&map_x, features, rows, F, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != LTR_OK) return rc;
+  rc = make_map_2d(&map_hz, hz, rows, Hz::P, 32, kMlpTileDocs, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != LTR_OK) return rc;
+  MlpGeom g = mlp_geometry(F, 1);
+  const int ntiles = static_cast<int>((rows + kMlpTileDocs - 1) / kMlpTileDocs);
+  int grid = ntiles < di.sms ? ntiles : di.sms;
+  if (grid > kMlpMaxCtas) grid = kMlpMaxCtas;
+  LTR_CUDA(cudaFuncSetAttribute(mlp_backward_hz_kernel<H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  mlp_backward_hz_kernel<H1, H2><<<grid, kMlpHzThreads, smem, st>>>(map_x, map_hz, g, w2, w3, h1, h2, dscores, rows,
+                                                                    ntiles, partials, len);
+  LTR_CUDA(cudaGetLastError());
+  *grid_out = grid;
   return LTR_OK;
 }
 
 extern "C" {
 
+// floats per document of the activation rows ltr_mlp_scores can keep for ltr_mlp_backward (0: this shape has none)
+int ltr_mlp_hz_pitch(int H1, int H2) { return mlp_hz_pitch(H1, H2); }
+
 int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
                               const float* w2, const float* b2, int H2, const float* w3, const float* b3,
-                              float* scores_out, void* stream) {
+                              float* scores_out, float* hz_out, void* stream) {
   int rc = mlp_check(features, rows, F, w1, H1, w2, H2, w3);
   if (rc != LTR_OK) return rc;
   if (rows > 0 && !scores_out) return LTR_EINVAL;
@@ -150,9 +188,12 @@ int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1
   rc = mlp_make_maps(&m, g, features, rows, w1, H1);
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (H1 == 50 && H2 == 10) return launch_mlp_scores<50, 10>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
-  if (H1 <= 32 && H2 <= 8) return launch_mlp_scores<32, 8>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
-  return launch_mlp_scores<64, 16>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, st, di);
+  if (hz_out && (ltr_mlp_hz_pitch(H1, H2) == 0 || !aligned16(hz_out))) return LTR_EINVAL;
+  if (H1 == 50 && H2 == 10)
+    return launch_mlp_scores<50, 10>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, hz_out, st, di);
+  if (H1 <= 32 && H2 <= 8)
+    return launch_mlp_scores<32, 8>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, hz_out, st, di);
+  return launch_mlp_scores<64, 16>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, nullptr, st, di);
 }
 
 size_t ltr_mlp_grad_len(int F, int H1, int H2) {
@@ -165,7 +206,7 @@ size_t ltr_mlp_workspace_bytes(int F, int H1, int H2) {
 }
 
 int ltr_mlp_backward(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
-                     const float* w2, const float* b2, int H2, const float* w3, const float* b3,
+                     const float* w2, const float* b2, int H2, const float* w3, const float* b3, const float* hz,
                      const float* dscores, float* grads_out, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = mlp_check(features, rows, F, w1, H1, w2, H2, w3);
   if (rc != LTR_OK) return rc;
@@ -178,6 +219,19 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
   const int len = static_cast<int>(ltr_mlp_grad_len(F, H1, H2));
   if (rows == 0) {
     LTR_CUDA(cudaMemsetAsync(grads_out, 0, sizeof(float) * len, st));
+    return LTR_OK;
+  }
+  if (hz) {
+    // the forward pass kept [H1 | Z2]: every byte once, no layer 1 again
+    if (ltr_mlp_hz_pitch(H1, H2) == 0 || !aligned16(hz)) return LTR_EINVAL;
+    int hgrid = 0;
+    rc = H1 == 50 ? launch_mlp_backward_hz<50, 10>(features, hz, rows, F, w2, w3, H1, H2, dscores,
+                                                   static_cast<float*>(workspace), len, &hgrid, st, di)
+                  : launch_mlp_backward_hz<32, 8>(features, hz, rows, F, w2, w3, H1, H2, dscores,
+                                                  static_cast<float*>(workspace), len, &hgrid, st, di);
+    if (rc != LTR_OK) return rc;
+    mlp_reduce_kernel<<<(len + 255) / 256, 256, 0, st>>>(static_cast<float*>(workspace), hgrid, len, grads_out);
+    LTR_CUDA(cudaGetLastError());
     return LTR_OK;
   }
   MlpGeom g = mlp_geometry(F, 1);

@@ -189,6 +189,17 @@ __device__ __forceinline__ void mlp_issue_layer1(uint32_t d_tmem, uint32_t xs, u
   }
 }
 
+// Activation row kept for the backward pass (ltr_mlp_scores with hz_out): P floats per document,
+// H1 = relu(Z1 + b1) in columns [0, H1), the layer-2 pre-activation Z2 (bias included) in [Z0, Z0 + H2), zeros
+// elsewhere.  The backward kernel uses the row index of the dZ1 operand for both: rows [0, H1) carry dZ1,
+// rows [Z0, Z0 + H2) carry dZ2 -- which needs Z0 + H2 <= 64 (true for 50-10 and 32-8).
+template <int H1, int H2>
+struct MlpHz {
+  static constexpr int Z0 = (H1 + 3) / 4 * 4;
+  static constexpr int P = (Z0 + H2 + 3) / 4 * 4;
+  static constexpr bool kFits = Z0 + H2 <= kMlpN1;
+};
+
 // Forward epilogue: one document's hidden layers from its row of Z1 (TMEM -> registers); H2P = H2 rounded up
 // to 4.  Layer 2 as packed f32x2 FMAs on pairs of units; the rows of W2^T (shared memory, one 128-bit
 // broadcast load per four weights) are fetched PF hidden units ahead of their use.
@@ -251,7 +262,8 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_tail,
                   const MlpGeom g, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
-                  int h1, int h2, long long rows, int ntiles, float* __restrict__ scores_out) {
+                  int h1, int h2, long long rows, int ntiles, float* __restrict__ scores_out,
+                  float* __restrict__ hz_out) {
   extern __shared__ __align__(1024) unsigned char mlp_smem[];
   // aligned up to 1024 bytes in the pointer domain, so the compiler keeps the shared address space (LDS / STS)
   unsigned char* base = mlp_smem + ((1024u - (smem_u32(mlp_smem) & 1023u)) & 1023u);
@@ -328,6 +340,25 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       row.layers(sp);
       const long long r = static_cast<long long>(tile) * kMlpTileDocs + quarter * 32 + lane;
       if (r < rows) scores_out[r] = row.score(sp);
+      if (hz_out && r < rows) {
+        // the activations the backward pass needs, one row per document: [H1 | 0 | Z2 | 0] (MlpHz)
+        using Hz = MlpHz<H1, H2>;
+        float4* o = reinterpret_cast<float4*>(hz_out + static_cast<size_t>(r) * Hz::P);
+#pragma unroll
+        for (int q = 0; q < Hz::P / 4; ++q) {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = 4 * q + k;
+            v[k] = j < H1 ? row.h1[j < H1 ? j : 0]
+                          : (j >= Hz::Z0 && j < Hz::Z0 + H2
+                                 ? (((j - Hz::Z0) & 1) ? row.z2[(j >= Hz::Z0 && j < Hz::Z0 + H2 ? j - Hz::Z0 : 0) >> 1].y
+                                                       : row.z2[(j >= Hz::Z0 && j < Hz::Z0 + H2 ? j - Hz::Z0 : 0) >> 1].x)
+                                 : 0.0f);
+          }
+          o[q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -835,6 +866,295 @@ mlp_backward_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ---- backward from kept activations (ltr_mlp_backward with hz != NULL) --------------------------------------
+// When the forward pass kept [H1 | Z2] per document (256 B for 50-10, next to 544 B of features), the backward
+// pass needs neither W1 nor layer 1 again, reads every byte ONCE, and every sum over documents becomes one
+// tensor-core product with the same A operand.  Per tile of 128 documents:
+//   warps   dZ2 = ds * w3 * [Z2 > 0] (Z2 read from the staged activation tile) -> TMEM; dW3 / db3 in registers
+//   MMA-dH  dH1 (128 x 64) = dZ2 W2          A from TMEM, W2^T in shared memory
+//   warps   dZ1 = dH1 * [H1 > 0]; rows [0, H1) of the operand buffer get dZ1^T, rows [Z0, Z0 + H2) get dZ2^T
+//   MMA2    [dZ1^T ; dZ2^T] (64 x 128 documents) . [X | H1 Z2 | 1] (128 documents x (F + 64 + 8)): the rows of
+//           dZ1 against X give dW1, the rows of dZ2 against H1 give dW2, either against the ones give db1 / db2
+//           (the other blocks of the product are never read).  X and the activation tile are both MN-major
+//           operands exactly as TMA leaves them (128-byte swizzle, 32-byte atom); accumulators stay in TMEM.
+// The masks are the forward pass's own (same H1 and Z2 bits), so the result is the gradient of exactly the
+// function the forward kernel computed, up to the TF32 operands of the three products.
+constexpr int kMlpHzThreads = 192;                  // 4 document warps + TMA warp + MMA warp
+constexpr int kMlpHzBufCols = 80;                   // TMEM columns of one tile: dZ2 16 | dH1 64
+
+struct MlpHzSmall {
+  float b1pad[4];
+  float w3[kMlpMaxH2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  uint64_t bar_mnf[4];     // feature tile, 32 documents at a time: landed / consumed by MMA2
+  uint64_t bar_mne[4];
+  uint64_t bar_hzf[2];     // activation tile (two stages): landed / consumed by MMA2
+  uint64_t bar_hze[2];
+  uint64_t bar_tempty[2];  // TMEM columns of the tile read by the warps
+  uint64_t bar_dz2, bar_dh, bar_a2_full, bar_a2_free;
+  float red[4][2 * kMlpMaxH2 + 4];
+};
+
+template <int H1, int H2>
+__global__ void __launch_bounds__(kMlpHzThreads, 1)
+mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __grid_constant__ CUtensorMap map_hz,
+                       const MlpGeom g, const float* __restrict__ w2, const float* __restrict__ w3, int h1n, int h2n,
+                       const float* __restrict__ dscores, long long rows, int ntiles, float* __restrict__ partials,
+                       int partial_len) {
+  using Hz = MlpHz<H1, H2>;
+  static_assert(Hz::kFits, "dZ2 rows must fit behind the dZ1 rows of the 64-row operand");
+  constexpr int NHZ = (Hz::P + 31) / 32;            // activation chunks of 32 columns
+  constexpr int HZN = 32 * NHZ;                     // accumulator columns they take
+  extern __shared__ __align__(1024) unsigned char mlp_smem[];
+  unsigned char* base = mlp_smem + ((1024u - (smem_u32(mlp_smem) & 1023u)) & 1023u);
+  const int nk = (g.F + 31) / 32;
+  const int xn = 32 * nk;
+  unsigned char* a2s = base;                        // [dZ1^T ; dZ2^T], K-major, 128-byte swizzle
+  unsigned char* xmn = a2s + kMlpA2Bytes;           // feature tile, MN-major form
+  unsigned char* hzs = xmn + nk * kMlpChunkX;       // two stages of the activation tile, MN-major form
+  unsigned char* w2ts = hzs + 2 * NHZ * kMlpChunkX; // W2^T [j][i], K-major, 64-byte swizzle
+  unsigned char* ones = w2ts + kMlpN1 * 64;
+  MlpHzSmall* sp = reinterpret_cast<MlpHzSmall*>(ones + kMlpOnesBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int tmem_cols = 512;
+  const uint32_t d2col = 2 * kMlpHzBufCols;         // dW1 block | dW2 block | bias block
+  for (int t = threadIdx.x; t < kMlpMaxH2; t += blockDim.x) sp->w3[t] = t < h2n ? w3[t] : 0.0f;
+  for (int t = threadIdx.x; t < kMlpA2Bytes / 4; t += blockDim.x) reinterpret_cast<float*>(a2s)[t] = 0.0f;
+  for (int t = threadIdx.x; t < kMlpOnesBytes / 4; t += blockDim.x) reinterpret_cast<float*>(ones)[t] = 1.0f;
+  for (int t = threadIdx.x; t < kMlpMaxH2 * kMlpMaxH1; t += blockDim.x) {
+    const int i = t / kMlpMaxH1, j = t - i * kMlpMaxH1;
+    const float v = (i < h2n && j < h1n) ? w2[i * h1n + j] : 0.0f;
+    *reinterpret_cast<float*>(w2ts + j * 64 + ((((i >> 2) ^ ((j >> 1) & 3))) << 4) + (i & 3) * 4) = v;
+  }
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(&sp->bar_mnf[c], 1);
+      mbar_init(&sp->bar_mne[c], 1);
+    }
+    for (int c = 0; c < 2; ++c) {
+      mbar_init(&sp->bar_hzf[c], 1);
+      mbar_init(&sp->bar_hze[c], 1);
+      mbar_init(&sp->bar_tempty[c], 4);
+    }
+    mbar_init(&sp->bar_dz2, 4);
+    mbar_init(&sp->bar_dh, 1);
+    mbar_init(&sp->bar_a2_full, 4);
+    mbar_init(&sp->bar_a2_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(&sp->tmem_base, tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sp->tmem_base;
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 4) {
+    if (lane == 0 && my_tiles > 0) {
+      auto load_hz = [&](int it) {                    // stage it & 1, free once MMA2 of tile it - 2 has read it
+        const int s = it & 1;
+        mbar_wait_guarded<true>(&sp->bar_hze[s], ((it >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(&sp->bar_hzf[s], NHZ * kMlpChunkX);
+        for (int c = 0; c < NHZ; ++c)
+          tma_load_2d(hzs + (s * NHZ + c) * kMlpChunkX, &map_hz, c * 32, (blockIdx.x + it * gridDim.x) * kMlpTileDocs,
+                      &sp->bar_hzf[s]);
+      };
+      load_hz(0);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int row0 = (blockIdx.x + it * gridDim.x) * kMlpTileDocs;
+        for (int dg = 0; dg < 4; ++dg) {
+          mbar_wait_guarded<true>(&sp->bar_mne[dg], (it & 1) ^ 1u);   // MMA2 of tile it - 1 has read these documents
+          mbar_arrive_expect_tx(&sp->bar_mnf[dg], nk * 4096);
+          for (int c = 0; c < nk; ++c)
+            tma_load_2d(xmn + c * kMlpChunkX + dg * 4096, &map_x_mn, c * 32, row0 + dg * 32, &sp->bar_mnf[dg]);
+        }
+        if (it + 1 < my_tiles) load_hz(it + 1);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t idesc_dh = umma_idesc_tf32(kMlpTileDocs, kMlpN1, 0, 0);
+      constexpr uint32_t idesc_b = umma_idesc_tf32(64, 8, 0, 0);
+      constexpr uint32_t idesc_hz = umma_idesc_tf32(64, HZN, 0, 1);
+      const uint32_t idesc_x = umma_idesc_tf32(64, xn, 0, 1);
+      const uint64_t ones_desc = umma_desc(smem_u32(ones), 16, 1024, 2);
+      const uint32_t a2 = smem_u32(a2s), x_mn = smem_u32(xmn), hz0 = smem_u32(hzs), w2ta = smem_u32(w2ts);
+      uint32_t acc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        const uint32_t buf = tmem + b * kMlpHzBufCols;
+        // dH1 = dZ2 W2 (K = 16 layer-2 units); the dH1 columns are free once tile it - 2 has been read
+        mbar_wait_guarded<true>(&sp->bar_tempty[b], ((it >> 1) & 1) ^ 1u);
+        mbar_wait_guarded<true>(&sp->bar_dz2, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kMlpMaxH2 / 8; ++k)
+          umma_tf32_ts(buf + 16, buf + 8 * k, umma_desc(w2ta + k * 32, 16, 512, 4), idesc_dh, k > 0);
+        umma_commit(&sp->bar_dh);
+        // [dW1 | dW2 | db] += [dZ1^T ; dZ2^T] [X | H1 Z2 | 1]
+        mbar_wait_guarded<true>(&sp->bar_a2_full, it & 1);   // (the warps read the activation tile before: it has landed)
+        const uint32_t hz = hz0 + b * NHZ * kMlpChunkX;
+        for (int dg = 0; dg < 4; ++dg) {
+          mbar_wait_guarded<true>(&sp->bar_mnf[dg], it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = 4 * dg + k4;
+            const uint64_t adesc = umma_desc(a2 + dg * (kMlpN1 * 128) + k4 * 32, 16, 1024, 2);
+            umma_tf32(tmem + d2col, adesc, umma_desc(x_mn + ks * 1024, kMlpChunkX, 512, kUmmaLayout32BAtom), idesc_x, acc);
+            umma_tf32(tmem + d2col + xn, adesc, umma_desc(hz + ks * 1024, kMlpChunkX, 512, kUmmaLayout32BAtom), idesc_hz,
+                      acc);
+            umma_tf32(tmem + d2col + xn + HZN, adesc, ones_desc, idesc_b, acc);
+            acc = 1;
+          }
+          umma_commit(&sp->bar_mne[dg]);
+        }
+        umma_commit(&sp->bar_hze[b]);
+        umma_commit(&sp->bar_a2_free);
+      }
+    }
+  } else if (my_tiles > 0) {
+    const int t = threadIdx.x;                        // document of the tile = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    float dw3acc[H2], db3acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < H2; ++i) dw3acc[i] = 0.0f;
+    unsigned char* a2row = a2s + (t >> 5) * (kMlpN1 * 128) + (t & 3) * 4;   // this document's column of the operand
+    const int chunk = (t & 31) >> 2;
+    auto a2_store = [&](int j, float v) {
+      *reinterpret_cast<float*>(a2row + j * 128 + ((chunk ^ (j & 7)) << 4)) = v;
+    };
+    // this document's activation row: column c sits in chunk c / 32 at 32-byte unit ((c % 32) / 8) ^ (t % 4)
+    auto hz_vec = [&](const unsigned char* stage, int c) {   // c a multiple of 4
+      return *reinterpret_cast<const float4*>(stage + (c >> 5) * kMlpChunkX + t * 128 +
+                                              (((((c & 31) >> 3) ^ (t & 3)) << 5) | ((c & 4) << 2)));
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      const uint32_t buf = tmem + b * kMlpHzBufCols + lane_addr;
+      const unsigned char* stage = hzs + b * NHZ * kMlpChunkX;
+      const long long r = static_cast<long long>(blockIdx.x + it * gridDim.x) * kMlpTileDocs + t;
+      const float ds = r < rows ? dscores[r] : 0.0f;
+      mbar_wait_guarded(&sp->bar_hzf[b], (it >> 1) & 1);
+      // dZ2 = ds * w3 * [Z2 > 0]
+      float dz2[H2];
+      {
+        float z[(H2 + 3) / 4 * 4 + 4];
+        constexpr int zq0 = Hz::Z0 / 4 * 4;           // Z0 is a multiple of 4
+#pragma unroll
+        for (int q = 0; q < (H2 + 3) / 4; ++q) {
+          const float4 v = hz_vec(stage, zq0 + 4 * q);
+          z[4 * q] = v.x; z[4 * q + 1] = v.y; z[4 * q + 2] = v.z; z[4 * q + 3] = v.w;
+        }
+        db3acc += ds;
+        uint32_t v16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float d = 0.0f;
+          if (i < H2) {
+            d = z[i] > 0.0f ? ds * sp->w3[i] : 0.0f;
+            dw3acc[i < H2 ? i : 0] = fmaf(ds, fmaxf(z[i], 0.0f), dw3acc[i < H2 ? i : 0]);
+            dz2[i < H2 ? i : 0] = d;
+          }
+          v16[i] = __float_as_uint(d);
+        }
+        // the dZ2 / dH1 columns of this TMEM buffer are free once this thread's warp has read tile it - 2 (program order)
+        tmem_st16(buf, v16);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sp->bar_dz2);
+      // H1 > 0 of the document as bit masks (two words)
+      uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+      for (int q = 0; q < (H1 + 3) / 4; ++q) {
+        const float4 v = hz_vec(stage, 4 * q);
+        const uint32_t bits = (v.x > 0.0f ? 1u : 0u) | (v.y > 0.0f ? 2u : 0u) | (v.z > 0.0f ? 4u : 0u) | (v.w > 0.0f ? 8u : 0u);
+        if (q < 8) m0 |= bits << (4 * q);
+        else m1 |= bits << (4 * (q - 8));
+      }
+      // the operand buffer is free once MMA2 of the previous tile has read it
+      mbar_wait_guarded(&sp->bar_a2_free, (it & 1) ^ 1u);
+#pragma unroll
+      for (int i = 0; i < H2; ++i) a2_store(Hz::Z0 + i, dz2[i]);
+      mbar_wait_guarded(&sp->bar_dh, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < (H1 + 15) / 16; ++q) {
+        uint32_t v[16];
+        tmem_ld16(buf + 16 + 16 * q, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int j = 16 * q + k;
+          if (j < H1) {
+            const bool on = ((j < 32 ? m0 >> j : m1 >> (j - 32)) & 1u) != 0;
+            a2_store(j, on ? __uint_as_float(v[k]) : 0.0f);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sp->bar_tempty[b]);
+        mbar_arrive(&sp->bar_a2_full);
+      }
+    }
+
+    // ---- per-CTA partial gradient vector ----
+    float* out = partials + static_cast<size_t>(blockIdx.x) * partial_len;
+    const int off_b1 = h1n * g.F, off_w2 = off_b1 + h1n, off_b2 = off_w2 + h2n * h1n, off_w3 = off_b2 + h2n,
+              off_b3 = off_w3 + h2n;
+    float* red = sp->red[warp];
+#pragma unroll
+    for (int i = 0; i < H2; ++i) {
+      const float u = warp_sum(dw3acc[i]);
+      if (lane == 0) red[i] = u;
+    }
+    {
+      const float v = warp_sum(db3acc);
+      if (lane == 0) red[kMlpMaxH2] = v;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    auto red4 = [&](int k) { return ((sp->red[0][k] + sp->red[1][k]) + sp->red[2][k]) + sp->red[3][k]; };
+    if (t < h2n) out[off_w3 + t] = red4(t);
+    if (t == 0) out[off_b3] = red4(kMlpMaxH2);
+    // accumulator rows out of TMEM: row j lives in lane (j % 16) + 32 (j / 16); rows [0, H1) are dZ1 rows (dW1,
+    // db1), rows [Z0, Z0 + H2) dZ2 rows (dW2, db2)
+    mbar_wait_guarded(&sp->bar_a2_free, (my_tiles - 1) & 1);
+    tc_fence_after();
+    const int j = warp * 16 + lane;
+    const int ncols = xn + HZN + 8;
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + d2col + c0 + lane_addr, v);
+      tmem_ld_wait();
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int c = c0 + k;
+          const float val = __uint_as_float(v[k]);
+          if (j < h1n) {
+            if (c < g.F) out[static_cast<size_t>(j) * g.F + c] = val;
+            if (c == xn + HZN) out[off_b1 + j] = val;
+          } else if (j >= Hz::Z0 && j - Hz::Z0 < h2n) {
+            if (c >= xn && c - xn < h1n) out[off_w2 + (j - Hz::Z0) * h1n + (c - xn)] = val;
+            if (c == xn + HZN) out[off_b2 + (j - Hz::Z0)] = val;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, tmem_cols);
 }
 
 // out[k] = sum over the CTAs' partial vectors, in CTA order

@@ -196,15 +196,25 @@ class _MlpScores(torch.autograd.Function):
         ptr = [None if t is None else t.data_ptr() for t in p]
         lib = _lib.lib()
         scores = torch.empty(rows, dtype=torch.float32, device=dev)
+        # a training step keeps [H1 | Z2] per document for the backward pass (as autograd would keep the
+        # activations of the torch layers); an inference call writes the scores only
+        hz = None
+        pitch = lib.ltr_mlp_hz_pitch(H1, H2)
+        if pitch and any(ctx.needs_input_grad[1:]):
+            hz = torch.empty((rows, pitch), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = lib.ltr_mlp_scores(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5],
-                                    scores.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                                    scores.data_ptr(), None if hz is None else hz.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream)
         if rc == _LTR_EUNSUPPORTED:
             _warn_fallback(f"features={F}, hidden=({H1}, {H2}) is outside the scorer kernel's limits")
             scores = _mlp_torch_forward(x2, *p)[0]
         else:
             _lib.check(rc)
-        ctx.save_for_backward(x2, *[t for t in p if t is not None])
+        if rc == _LTR_EUNSUPPORTED:
+            hz = None
+        ctx.save_for_backward(x2, *[t for t in p if t is not None], *([] if hz is None else [hz]))
+        ctx.has_hz = hz is not None
         ctx.has = [t is not None for t in p]
         ctx.dims = (rows, F, H1, H2)
         ctx.param_shapes = [None if t is None else t.shape for t in (w1, b1, w2, b2, w3, b3)]
@@ -216,6 +226,7 @@ class _MlpScores(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         x2 = saved.pop(0)
         p = [saved.pop(0) if h else None for h in ctx.has]
+        hz = saved.pop(0) if ctx.has_hz else None
         rows, F, H1, H2 = ctx.dims
         dev = x2.device
         ds = g.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
@@ -227,8 +238,12 @@ class _MlpScores(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.ltr_mlp_backward(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5],
-                                      ds.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws_bytes,
-                                      torch.cuda.current_stream(dev).cuda_stream)
+                                      None if hz is None else hz.data_ptr(), ds.data_ptr(), grads.data_ptr(),
+                                      ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
+            if rc == _LTR_EUNSUPPORTED and hz is not None:      # F beyond the kept-activation kernel: recompute
+                rc = lib.ltr_mlp_backward(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4],
+                                          ptr[5], None, ds.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws_bytes,
+                                          torch.cuda.current_stream(dev).cuda_stream)
         if rc == _LTR_EUNSUPPORTED:
             _warn_fallback(f"features={F}, hidden=({H1}, {H2}) is outside the backward kernel's limits")
             _, h1, h2 = _mlp_torch_forward(x2, *p)

@@ -54,7 +54,7 @@ def test_tf32_trunc_keeps_19_bits():
 def test_mlp_symbols_exported():
     import ctypes
     lib = ctypes.CDLL(_lib.LIB_PATH)
-    for sym in ("ltr_mlp_scores", "ltr_mlp_backward", "ltr_mlp_grad_len", "ltr_mlp_workspace_bytes"):
+    for sym in ("ltr_mlp_scores", "ltr_mlp_backward", "ltr_mlp_grad_len", "ltr_mlp_workspace_bytes", "ltr_mlp_hz_pitch"):
         assert hasattr(lib, sym)
     lib.ltr_mlp_grad_len.restype = ctypes.c_size_t
     lib.ltr_mlp_grad_len.argtypes = [ctypes.c_int] * 3
@@ -80,16 +80,27 @@ def test_mlp_ranker_state_dict_matches_documented_model():
 
 
 # ---- GPU ------------------------------------------------------------------------------------------------
-def _call_scores(lib, x, p):
+def _call_scores(lib, x, p, hz=None):
     rows, F = x.shape
     out = torch.full((rows,), float("nan"), device=x.device)
     rc = lib.ltr_mlp_scores(x.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), p[0].shape[0], p[2].data_ptr(),
                             p[3].data_ptr(), p[2].shape[0], p[4].data_ptr(), p[5].data_ptr(), out.data_ptr(),
-                            torch.cuda.current_stream().cuda_stream)
+                            None if hz is None else hz.data_ptr(), torch.cuda.current_stream().cuda_stream)
     return rc, out
 
 
-def _call_backward(lib, x, p, ds):
+def _kept_activations(lib, x, p):
+    """forward pass keeping [H1 | Z2] (None when the shape has no such path)"""
+    pitch = lib.ltr_mlp_hz_pitch(p[0].shape[0], p[2].shape[0])
+    if pitch == 0:
+        return None
+    hz = torch.full((x.shape[0], pitch), float("nan"), device=x.device)
+    rc, _ = _call_scores(lib, x, p, hz)
+    assert rc == 0
+    return hz
+
+
+def _call_backward(lib, x, p, ds, hz=None):
     rows, F = x.shape
     H1, H2 = p[0].shape[0], p[2].shape[0]
     n = lib.ltr_mlp_grad_len(F, H1, H2)
@@ -97,8 +108,8 @@ def _call_backward(lib, x, p, ds):
     wsb = lib.ltr_mlp_workspace_bytes(F, H1, H2)
     ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
     rc = lib.ltr_mlp_backward(x.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), H1, p[2].data_ptr(),
-                              p[3].data_ptr(), H2, p[4].data_ptr(), p[5].data_ptr(), ds.data_ptr(), out.data_ptr(),
-                              ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+                              p[3].data_ptr(), H2, p[4].data_ptr(), p[5].data_ptr(), None if hz is None else hz.data_ptr(),
+                              ds.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
     return rc, out
 
 
@@ -177,6 +188,69 @@ def test_mlp_backward_vs_oracle(rows, F, H1, H2):
     assert rc == 0 and torch.equal(out, out2)
 
 
+def _near_kink_exact(x, pn):
+    """documents with a layer-1 or layer-2 pre-activation within float32 accumulation error of zero"""
+    d = np.float64
+    t = oracle.tf32_trunc
+    z1 = t(x).astype(d) @ t(pn[0]).astype(d).T + pn[1].astype(d)
+    z2 = np.maximum(z1, 0.0) @ pn[2].astype(d).T + pn[3].astype(d)
+    return (np.abs(z2) < 2e-5).any(axis=1) | (np.abs(z1) < 2e-5).any(axis=1)
+
+
+@gpu
+@pytest.mark.parametrize("rows,F,H1,H2", [s_ for s_ in SHAPES if (s_[2], s_[3]) in ((50, 10), (32, 8), (20, 5))])
+def test_mlp_backward_from_kept_activations_vs_oracle(rows, F, H1, H2):
+    """ltr_mlp_scores(hz_out) + ltr_mlp_backward(hz): the activation rows hold relu(Z1 + b1) and Z2 of the forward
+    pass (float32 layer 2), the masks are the forward pass's own, and dW1 / dW2 / db1 / db2 come out of one
+    tensor-core product with TF32 operands (dZ1, dZ2, X, H1)."""
+    lib = _lib.lib()
+    p = _params(F, H1, H2, 9, "cuda")
+    gen = torch.Generator(device="cuda").manual_seed(10)
+    x = torch.randn(rows, F, device="cuda", generator=gen)
+    ds = torch.randn(rows, device="cuda", generator=gen) * (torch.rand(rows, device="cuda", generator=gen) > 0.2)
+    pn = [t.cpu().numpy() for t in p]
+    xn = x.cpu().numpy()
+    ds[torch.from_numpy(_near_kink_exact(xn, pn)).cuda()] = 0.0
+    hz = _kept_activations(lib, x, p)
+    assert hz is not None
+    # the kept rows themselves: [H1 | 0 | Z2 | 0]
+    d = np.float64
+    t = oracle.tf32_trunc
+    z1 = t(xn).astype(d) @ t(pn[0]).astype(d).T + pn[1].astype(d)
+    h1 = np.maximum(z1, 0.0)
+    z2 = h1 @ pn[2].astype(d).T + pn[3].astype(d)
+    hzn = hz.cpu().numpy().astype(d)
+    z0 = 52 if (H1, H2) == (50, 10) else 32          # columns of the kernel instantiation (50-10, or 32-8 padded)
+    assert np.abs(hzn[:, :H1] - h1).max() <= 2e-5 * max(1.0, np.abs(h1).max())
+    assert np.abs(hzn[:, z0:z0 + H2] - z2).max() <= 2e-5 * max(1.0, np.abs(z2).max())
+    assert (hzn[:, H1:z0] == 0).all() and (hzn[:, z0 + H2:] == 0).all() and hzn.shape[1] == (64 if H1 == 50 else 40)
+    rc, out = _call_backward(lib, x, p, ds, hz)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    got = _split(out.cpu().numpy().astype(np.float64), F, H1, H2)
+    # restatement of this path: exact masks, TF32 operands in dH1 = dZ2 W2, dW1 = dZ1^T X, dW2 = dZ2^T H1, db1, db2
+    g = ds.cpu().numpy().astype(d).reshape(-1, 1)
+    h2 = np.maximum(z2, 0.0)
+    dz2 = g * pn[4].astype(d).reshape(1, -1) * (z2 > 0)
+    dz2_op = t(dz2.astype(np.float32)).astype(d)
+    dz1 = (dz2_op @ t(pn[2]).astype(d)) * (z1 > 0)
+    dz1_op = t(dz1.astype(np.float32)).astype(d)
+    ref = [dz1_op.T @ t(xn).astype(d), dz1_op.sum(0), dz2_op.T @ t(h1.astype(np.float32)).astype(d), dz2_op.sum(0),
+           (g * h2).sum(0).reshape(1, -1), g.sum().reshape(1)]
+    exact = oracle.mlp_grads(xn, *pn, ds.cpu().numpy())
+    for name, a, r, e in zip(("dW1", "db1", "dW2", "db2", "dW3", "db3"), got, ref, exact):
+        scale = max(np.abs(e).max(), 1e-6)
+        assert np.abs(a - r.reshape(a.shape)).max() <= 3e-4 * scale, name
+        assert np.linalg.norm(a - e.reshape(a.shape)) <= 0.1 * max(np.linalg.norm(e), 1e-6), name
+    rc, out2 = _call_backward(lib, x, p, ds, hz)
+    assert rc == 0 and torch.equal(out, out2)
+    # and the two backward paths agree with each other to the TF32 operand precision
+    rc, out3 = _call_backward(lib, x, p, ds)
+    assert rc == 0
+    assert (out - out3).norm().item() <= 0.1 * out3.norm().item()
+
+
 @gpu
 def test_mlp_backward_is_additive_over_documents():
     """Size-independent property: the gradients of a launch whose CTAs each stream several tiles equal the sum
@@ -188,15 +262,18 @@ def test_mlp_backward_is_additive_over_documents():
     gen = torch.Generator(device="cuda").manual_seed(8)
     x = torch.randn(rows, F, device="cuda", generator=gen)
     ds = torch.randn(rows, device="cuda", generator=gen)
-    rc, full = _call_backward(lib, x, p, ds)
-    assert rc == 0
-    acc = torch.zeros_like(full, dtype=torch.float64)
-    step = 128 * 100
-    for r0 in range(0, rows, step):
-        rc, part = _call_backward(lib, x[r0:r0 + step].contiguous(), p, ds[r0:r0 + step].contiguous())
+    hz = _kept_activations(lib, x, p)
+    for kept in (None, hz):
+        rc, full = _call_backward(lib, x, p, ds, kept)
         assert rc == 0
-        acc += part.double()
-    assert (full.double() - acc).abs().max().item() <= 2e-6 * acc.abs().max().item()
+        acc = torch.zeros_like(full, dtype=torch.float64)
+        step = 128 * 100
+        for r0 in range(0, rows, step):
+            rc, part = _call_backward(lib, x[r0:r0 + step].contiguous(), p, ds[r0:r0 + step].contiguous(),
+                                      None if kept is None else kept[r0:r0 + step].contiguous())
+            assert rc == 0
+            acc += part.double()
+        assert (full.double() - acc).abs().max().item() <= 2e-6 * acc.abs().max().item()
 
 
 @gpu
@@ -297,7 +374,7 @@ def test_mlp_ranker_rejects_feature_gradients_and_captures():
     with torch.cuda.stream(s):
         with torch.cuda.graph(g, stream=s):
             rc = lib.ltr_mlp_backward(x.data_ptr(), 16 * 64, 136, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
-                                      p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), ds.data_ptr(),
+                                      p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), None, ds.data_ptr(),
                                       out.data_ptr(), ws.data_ptr(), wsb, s.cuda_stream)
             assert rc == 0
     g.replay()

@@ -35,15 +35,20 @@ def ref_scores(x, w1, b1, w2, b2, w3, b3):
     return (h2 @ w3.to(d).t() + b3.to(d)).reshape(-1)
 
 
-def run_fwd(lib, x, w1, b1, w2, b2, w3, b3):
+def run_fwd(lib, x, w1, b1, w2, b2, w3, b3, hz=None):
     rows, F = x.shape
     out = torch.full((rows,), float("nan"), device="cuda")
     rc = lib.ltr_mlp_scores(x.data_ptr(), rows, F, w1.data_ptr(), b1.data_ptr(), w1.shape[0], w2.data_ptr(),
                             b2.data_ptr(), w2.shape[0], w3.data_ptr(), b3.data_ptr(), out.data_ptr(),
-                            torch.cuda.current_stream().cuda_stream)
+                            None if hz is None else hz.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
     torch.cuda.synchronize()
     return out
+
+
+def make_hz(lib, x, w1, w2):
+    pitch = lib.ltr_mlp_hz_pitch(w1.shape[0], w2.shape[0])
+    return None if pitch == 0 else torch.full((x.shape[0], pitch), float("nan"), device="cuda")
 
 
 def ref_grads(x, w1, b1, w2, b2, w3, b3, ds):
@@ -69,7 +74,7 @@ def ref_grads(x, w1, b1, w2, b2, w3, b3, ds):
     return dw1, dw1_t, rest
 
 
-def run_bwd(lib, x, w1, b1, w2, b2, w3, b3, ds):
+def run_bwd(lib, x, w1, b1, w2, b2, w3, b3, ds, hz=None):
     rows, F = x.shape
     H1, H2 = w1.shape[0], w2.shape[0]
     n = lib.ltr_mlp_grad_len(F, H1, H2)
@@ -77,8 +82,8 @@ def run_bwd(lib, x, w1, b1, w2, b2, w3, b3, ds):
     wsb = lib.ltr_mlp_workspace_bytes(F, H1, H2)
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     rc = lib.ltr_mlp_backward(x.data_ptr(), rows, F, w1.data_ptr(), b1.data_ptr(), H1, w2.data_ptr(), b2.data_ptr(),
-                              H2, w3.data_ptr(), b3.data_ptr(), ds.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb,
-                              torch.cuda.current_stream().cuda_stream)
+                              H2, w3.data_ptr(), b3.data_ptr(), None if hz is None else hz.data_ptr(), ds.data_ptr(),
+                              out.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
     torch.cuda.synchronize()
     return out
@@ -130,18 +135,21 @@ def bwd_checks(lib):
     def call():
         return lib.ltr_mlp_backward(args[0].data_ptr(), rows, 136, args[1].data_ptr(), args[2].data_ptr(), 50,
                                     args[3].data_ptr(), args[4].data_ptr(), 10, args[5].data_ptr(),
-                                    args[6].data_ptr(), ds.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb, st)
-    for _ in range(3):
-        _lib.check(call())
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        call()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"bwd timing rows={rows}: {ms * 1e3:.1f} us  {rows * 136 * 4 / 1e9 / ms * 1e3:.0f} GB/s")
+                                    args[6].data_ptr(), hzp, ds.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb, st)
+    hz = make_hz(lib, args[0], args[1], args[3])
+    run_fwd(lib, *args, hz=hz)
+    for name, hzp in (("recompute", None), ("kept activations", hz.data_ptr())):
+        for _ in range(3):
+            _lib.check(call())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"bwd timing ({name}) rows={rows}: {ms * 1e3:.1f} us  {rows * 136 * 4 / 1e9 / ms * 1e3:.0f} GB/s of features")
     # torch eager fwd+bwd of the same model
     x = args[0]
     lin = torch.nn.Sequential(torch.nn.Linear(136, 50), torch.nn.ReLU(), torch.nn.Linear(50, 10), torch.nn.ReLU(),
@@ -166,8 +174,10 @@ def main():
         rows = 8192 * 200
         args = make(rows, 136, 50, 10, exact=False)
         ds = torch.randn(rows, device="cuda")
-        run_fwd(lib, *args)
+        hz = make_hz(lib, args[0], args[1], args[3])
+        run_fwd(lib, *args, hz=hz)
         run_bwd(lib, *args, ds)
+        run_bwd(lib, *args, ds, hz=hz)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "bwd":
         print("PROBE", "OK" if bwd_checks(lib) else "FAIL")
@@ -207,19 +217,21 @@ def main():
     def call():
         return lib.ltr_mlp_scores(args[0].data_ptr(), rows, 136, args[1].data_ptr(), args[2].data_ptr(), 50,
                                   args[3].data_ptr(), args[4].data_ptr(), 10, args[5].data_ptr(),
-                                  args[6].data_ptr(), out.data_ptr(), st)
-    for _ in range(3):
-        _lib.check(call())
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        call()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    gb = rows * 136 * 4 / 1e9
-    print(f"fwd timing rows={rows}: {ms * 1e3:.1f} us  {gb / ms * 1e3:.0f} GB/s")
+                                  args[6].data_ptr(), out.data_ptr(), hzp, st)
+    hz = make_hz(lib, args[0], args[1], args[3])
+    for name, hzp, nbytes in (("scores only", None, rows * 136 * 4), ("keeping activations", hz.data_ptr(),
+                                                                      rows * (136 + hz.shape[1]) * 4)):
+        for _ in range(3):
+            _lib.check(call())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"fwd timing ({name}) rows={rows}: {ms * 1e3:.1f} us  {nbytes / 1e9 / ms * 1e3:.0f} GB/s")
     x = args[0]
     lin = torch.nn.Sequential(torch.nn.Linear(136, 50), torch.nn.ReLU(), torch.nn.Linear(50, 10), torch.nn.ReLU(),
                               torch.nn.Linear(10, 1)).cuda()
