@@ -1185,11 +1185,11 @@ def measure_mlp(args, cfg, dev, rank=0):
                               grads.data_ptr(), ws.data_ptr(), wsb, st)
     _lib.check(rc)
     torch.cuda.synchronize()
-    gref = oracle.mlp_grads(x2[:nsub].cpu().numpy(), *pn, dsn.cpu().numpy(), tf32=True)
+    gref = oracle.mlp_grads_kept(x2[:nsub].cpu().numpy(), *pn, dsn.cpu().numpy())
     gref = np.concatenate([g.reshape(-1) for g in gref])
     gerr = float(np.linalg.norm(grads.cpu().double().numpy() - gref) / max(1e-30, np.linalg.norm(gref)))
     parity = {"scores_max_err_rel": serr, "grads_norm_err_rel": gerr, "rows_checked": 4096 + nsub,
-              "oracle": "oracle.mlp_scores / mlp_grads, float64 on TF32-truncated operands",
+              "oracle": "oracle.mlp_scores(tf32=True) / mlp_grads_kept, float64 on TF32-truncated operands",
               "ok": bool(serr <= 2e-5 and gerr <= 2e-2)}
     return {
         "workload": cfg["workload"], "B": B, "L": L, "F": F, "steps": steps, "launch": launch,

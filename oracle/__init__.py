@@ -287,3 +287,24 @@ def mlp_grads(features, w1, b1, w2, b2, w3, b3, dscores, tf32=False):
     db1 = dz1_op.sum(0)
     dw1 = dz1_op.T @ t(x).astype(d)
     return dw1, db1, dw2, db2, dw3, db3
+
+
+def mlp_grads_kept(features, w1, b1, w2, b2, w3, b3, dscores):
+    """Restatement of ``ltr_mlp_backward`` started from the activations the forward kernel kept (``hz``): layer 1
+    with TF32 operands, layer 2 exact (the forward kernel runs it in float32), the forward pass's own ReLU masks,
+    TF32 operands in the three tensor-core products dH1 = dZ2 W2, [dW1, db1] = dZ1^T [X, 1], [dW2, db2] = dZ2^T [H1, 1]."""
+    d = np.float64
+    t = tf32_trunc
+    x = np.asarray(features, dtype=np.float32).reshape(-1, np.shape(features)[-1])
+    w1f, w2f, w3f = (np.asarray(a, dtype=np.float32) for a in (w1, w2, w3))
+    g = np.asarray(dscores, d).reshape(-1, 1)
+    z1 = t(x).astype(d) @ t(w1f).astype(d).T + np.asarray(b1, d)
+    h1 = np.maximum(z1, 0.0)
+    z2 = h1 @ w2f.astype(d).T + np.asarray(b2, d)
+    h2 = np.maximum(z2, 0.0)
+    dz2 = g * w3f.astype(d).reshape(1, -1) * (z2 > 0)
+    dz2_op = t(dz2.astype(np.float32)).astype(d)
+    dz1 = (dz2_op @ t(w2f).astype(d)) * (z1 > 0)
+    dz1_op = t(dz1.astype(np.float32)).astype(d)
+    return (dz1_op.T @ t(x).astype(d), dz1_op.sum(0), dz2_op.T @ t(h1.astype(np.float32)).astype(d), dz2_op.sum(0),
+            (g * h2).sum(0).reshape(1, -1), g.sum().reshape(1))

@@ -230,14 +230,7 @@ def test_mlp_backward_from_kept_activations_vs_oracle(rows, F, H1, H2):
     assert torch.isfinite(out).all()
     got = _split(out.cpu().numpy().astype(np.float64), F, H1, H2)
     # restatement of this path: exact masks, TF32 operands in dH1 = dZ2 W2, dW1 = dZ1^T X, dW2 = dZ2^T H1, db1, db2
-    g = ds.cpu().numpy().astype(d).reshape(-1, 1)
-    h2 = np.maximum(z2, 0.0)
-    dz2 = g * pn[4].astype(d).reshape(1, -1) * (z2 > 0)
-    dz2_op = t(dz2.astype(np.float32)).astype(d)
-    dz1 = (dz2_op @ t(pn[2]).astype(d)) * (z1 > 0)
-    dz1_op = t(dz1.astype(np.float32)).astype(d)
-    ref = [dz1_op.T @ t(xn).astype(d), dz1_op.sum(0), dz2_op.T @ t(h1.astype(np.float32)).astype(d), dz2_op.sum(0),
-           (g * h2).sum(0).reshape(1, -1), g.sum().reshape(1)]
+    ref = oracle.mlp_grads_kept(xn, *pn, ds.cpu().numpy())
     exact = oracle.mlp_grads(xn, *pn, ds.cpu().numpy())
     for name, a, r, e in zip(("dW1", "db1", "dW2", "db2", "dW3", "db3"), got, ref, exact):
         scale = max(np.abs(e).max(), 1e-6)
