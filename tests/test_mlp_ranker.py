@@ -44,6 +44,23 @@ def test_oracle_mlp_matches_torch_float64():
         np.testing.assert_allclose(got.reshape(want.shape), want.grad.numpy(), rtol=1e-10, atol=1e-12)
 
 
+def test_oracle_kept_activation_restatement_is_the_exact_gradient_on_tf32_exact_operands():
+    """With every tensor-core operand exactly representable in TF32 the restatement of the kept-activation
+    backward pass equals the plain float64 gradient (masks included)."""
+    rng = np.random.default_rng(3)
+    F, H1, H2, rows = 12, 5, 3, 64
+    q = lambda a: np.round(np.asarray(a) * 8) / 8                    # few mantissa bits: products of TF32-exact values
+    x = q(rng.standard_normal((rows, F))).astype(np.float32)
+    p = [q(rng.standard_normal(s)).astype(np.float32) for s in ((H1, F), (H1,), (H2, H1), (H2,), (1, H2), (1,))]
+    ds = q(rng.standard_normal(rows)).astype(np.float32)
+    a = oracle.mlp_grads(x, *p, ds)
+    b = oracle.mlp_grads_kept(x, *p, ds)
+    c = oracle.mlp_grads(x, *p, ds, tf32=True)
+    for u, v, w in zip(a, b, c):
+        np.testing.assert_allclose(v.reshape(u.shape), u, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(w.reshape(u.shape), u, rtol=1e-12, atol=1e-12)
+
+
 def test_tf32_trunc_keeps_19_bits():
     a = np.array([1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -11, -3.1415927, 1e-30, 65504.0], dtype=np.float32)
     t = oracle.tf32_trunc(a)
