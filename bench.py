@@ -1194,6 +1194,9 @@ def measure_mlp(args, cfg, dev, rank=0):
     return {
         "workload": cfg["workload"], "B": B, "L": L, "F": F, "steps": steps, "launch": launch,
         "ms_per_step": ms, "queries_per_s": B / (ms * 1e-3),
+        # uniform keys of the sub-config block: the two scorer kernels together, against the HBM floor of both
+        "kernel_ms": fwd_ms + bwd_ms, "hbm_frac": 2 * alg / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak,
+        "hbm_gbs": 2 * alg / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "issue_frac": None, "issue_bound": None,
         "kernels_ms": {"ltr_mlp_scores (keeping H1 | Z2 for the backward pass)": fwd_ms,
                        "loss (" + cfg["loss"] + ", forward + gradient)": loss_ms,
                        "ltr_mlp_backward (from the kept activations)": bwd_ms,
