@@ -182,6 +182,12 @@ class _MlpScores(torch.autograd.Function):
             x2 = x2.to(torch.float32)
         x2 = x2.reshape(-1, F).contiguous()
         rows = x2.shape[0]
+        # TMA needs feature rows of a multiple of 16 bytes: other widths (MQ2007's 46, Yahoo's 699) get zero
+        # columns appended -- one extra copy of the features per call; a dataset kept on the device can be
+        # stored padded once instead (zero features times zero weight columns change nothing)
+        Fp = (F + 3) // 4 * 4
+        if Fp != F:
+            x2 = torch.nn.functional.pad(x2, (0, Fp - F))
 
         def prep(t, shape):
             if t is None:
@@ -193,6 +199,10 @@ class _MlpScores(torch.autograd.Function):
         H1, H2 = w1.shape[0], w2.shape[0]
         p = [prep(w1, (H1, F)), prep(b1, (H1,)), prep(w2, (H2, H1)), prep(b2, (H2,)), prep(w3, (1, H2)),
              prep(b3, (1,))]
+        if Fp != F:
+            p[0] = torch.nn.functional.pad(p[0], (0, Fp - F))
+        ctx.F_in = F
+        F = Fp
         ptr = [None if t is None else t.data_ptr() for t in p]
         lib = _lib.lib()
         scores = torch.empty(rows, dtype=torch.float32, device=dev)
@@ -256,6 +266,8 @@ class _MlpScores(torch.autograd.Function):
             o = [0, H1 * F, H1 * F + H1, H1 * F + H1 + H2 * H1, H1 * F + H1 + H2 * H1 + H2,
                  H1 * F + H1 + H2 * H1 + 2 * H2, n]
             out = [grads[o[k]:o[k + 1]] for k in range(6)]
+        if ctx.F_in != F:                              # drop the gradient of the padding columns of W1
+            out[0] = out[0].reshape(H1, F)[:, :ctx.F_in]
         res = [None]
         for k in range(6):
             res.append(out[k].reshape(ctx.param_shapes[k]) if ctx.has[k] else None)

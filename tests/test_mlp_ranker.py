@@ -138,6 +138,7 @@ def _split(out, F, H1, H2):
 
 SHAPES = [(128, 136, 50, 10), (1000, 136, 50, 10), (40000, 136, 50, 10), (5000, 128, 50, 10), (5000, 32, 50, 10),
           (3000, 24, 50, 10), (700, 8, 50, 10), (5000, 48, 64, 16), (5000, 100, 20, 5), (9000, 64, 32, 8), (1, 136, 50, 10)]
+KEPT_SHAPES = [s_ for s_ in SHAPES if (s_[2], s_[3]) in ((50, 10), (32, 8), (20, 5))] + [(3000, 220, 50, 10)]
 
 
 @gpu
@@ -215,7 +216,7 @@ def _near_kink_exact(x, pn):
 
 
 @gpu
-@pytest.mark.parametrize("rows,F,H1,H2", [s_ for s_ in SHAPES if (s_[2], s_[3]) in ((50, 10), (32, 8), (20, 5))])
+@pytest.mark.parametrize("rows,F,H1,H2", KEPT_SHAPES)
 def test_mlp_backward_from_kept_activations_vs_oracle(rows, F, H1, H2):
     """ltr_mlp_scores(hz_out) + ltr_mlp_backward(hz): the activation rows hold relu(Z1 + b1) and Z2 of the forward
     pass (float32 layer 2), the masks are the forward pass's own, and dW1 / dW2 / db1 / db2 come out of one
@@ -255,10 +256,12 @@ def test_mlp_backward_from_kept_activations_vs_oracle(rows, F, H1, H2):
         assert np.linalg.norm(a - e.reshape(a.shape)) <= 0.1 * max(np.linalg.norm(e), 1e-6), name
     rc, out2 = _call_backward(lib, x, p, ds, hz)
     assert rc == 0 and torch.equal(out, out2)
-    # and the two backward paths agree with each other to the TF32 operand precision
+    # and the two backward paths agree with each other to the TF32 operand precision (where the recompute
+    # kernel takes the shape: its two copies of a feature tile limit it to F <= ~140)
     rc, out3 = _call_backward(lib, x, p, ds)
-    assert rc == 0
-    assert (out - out3).norm().item() <= 0.1 * out3.norm().item()
+    assert rc in (0, -2)
+    if rc == 0:
+        assert (out - out3).norm().item() <= 0.1 * out3.norm().item()
 
 
 @gpu
@@ -333,6 +336,42 @@ def test_mlp_ranker_matches_unfused_modules(loss_name):
             assert gb is not None and torch.isfinite(gb).all()
             # TF32 operands in the scorer (and the ReLU-mask flips they cause next to a kink): norm-wise bound
             assert (ga - gb).norm().item() <= 0.1 * ga.norm().item() + 1e-6, loss_name   # (d/db3 of these losses is 0)
+
+
+@gpu
+@pytest.mark.parametrize("F", [46, 220, 699])
+def test_mlp_ranker_other_feature_widths(F):
+    """MQ2007 (46: padded to 48 on the fly), Istella (220: kernels as they are), Yahoo (699: beyond a shared-memory
+    tile, runs on torch's layers with a warning) -- the module works for all of them."""
+    import warnings
+    from pytorchltr_b200.fused import MLPRanker
+    torch.manual_seed(2)
+    B, Lq = 16, 40
+    xs = torch.randn(B, Lq, F, device="cuda")
+    fused = MLPRanker(F).cuda()
+    plain = torch.nn.Sequential(torch.nn.Linear(F, 50), torch.nn.ReLU(), torch.nn.Linear(50, 10), torch.nn.ReLU(),
+                                torch.nn.Linear(10, 1)).cuda()
+    with torch.no_grad():
+        for a, b in zip((plain[0], plain[2], plain[4]), (fused.l1, fused.l2, fused.l3)):
+            a.weight.copy_(b.weight)
+            a.bias.copy_(b.bias)
+    g = torch.randn(B, Lq, 1, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s_f = fused(xs)
+        s_p = plain(xs)
+        s_f.backward(g)
+        s_p.backward(g)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert (s_f - s_p).abs().max().item() <= 4e-3 * max(1.0, s_p.abs().max().item())
+    for a, b in zip((plain[0], plain[2], plain[4]), (fused.l1, fused.l2, fused.l3)):
+        assert a.weight.grad.shape == b.weight.grad.shape
+        assert (a.weight.grad - b.weight.grad).norm().item() <= 0.1 * a.weight.grad.norm().item() + 1e-6
+        assert (a.bias.grad - b.bias.grad).norm().item() <= 0.1 * a.bias.grad.norm().item() + 1e-6
 
 
 @gpu
