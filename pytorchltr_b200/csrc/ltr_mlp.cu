@@ -230,7 +230,7 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
                   : launch_mlp_backward_hz<32, 8>(features, hz, rows, F, w2, w3, H1, H2, dscores,
                                                   static_cast<float*>(workspace), len, &hgrid, st, di);
     if (rc != LTR_OK) return rc;
-    mlp_reduce_kernel<<<(len + 255) / 256, 256, 0, st>>>(static_cast<float*>(workspace), hgrid, len, grads_out);
+    mlp_reduce_kernel<<<(len + 63) / 64, 256, 0, st>>>(static_cast<float*>(workspace), hgrid, len, grads_out);
     LTR_CUDA(cudaGetLastError());
     return LTR_OK;
   }
@@ -266,7 +266,7 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
   else LTR_MLP_BWD(64, 16);
 #undef LTR_MLP_BWD
   LTR_CUDA(cudaGetLastError());
-  const int rgrid = (len + 255) / 256;
+  const int rgrid = (len + 63) / 64;
   mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;

@@ -1157,14 +1157,21 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
   if (warp == 5) tmem_dealloc(tmem, tmem_cols);
 }
 
-// out[k] = sum over the CTAs' partial vectors, in CTA order
+// out[k] = sum over the CTAs' partial vectors in a fixed order: four runs of consecutive CTAs per element (one
+// thread each, coalesced 256-byte rows), then ((r0 + r1) + r2) + r3
 __global__ void __launch_bounds__(256)
 mlp_reduce_kernel(const float* __restrict__ partials, int nparts, int len, float* __restrict__ out) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
-    float s = 0.0f;
-    for (int p = 0; p < nparts; ++p) s += partials[static_cast<size_t>(p) * len + k];
-    out[k] = s;
-  }
+  __shared__ float run[4][64];
+  const int kl = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int k = blockIdx.x * 64 + kl;
+  const int per = (nparts + 3) / 4;
+  const int p0 = sub * per, p1 = p0 + per < nparts ? p0 + per : nparts;
+  float s = 0.0f;
+  if (k < len)
+    for (int p = p0; p < p1; ++p) s += partials[static_cast<size_t>(p) * len + k];
+  run[sub][kl] = s;
+  __syncthreads();
+  if (sub == 0 && k < len) out[k] = ((run[0][kl] + run[1][kl]) + run[2][kl]) + run[3][kl];
 }
 
 }  // namespace ltr

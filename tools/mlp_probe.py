@@ -175,9 +175,10 @@ def main():
         args = make(rows, 136, 50, 10, exact=False)
         ds = torch.randn(rows, device="cuda")
         hz = make_hz(lib, args[0], args[1], args[3])
-        run_fwd(lib, *args, hz=hz)
-        run_bwd(lib, *args, ds)
-        run_bwd(lib, *args, ds, hz=hz)
+        run_fwd(lib, *args)                           # inference: scores only
+        run_fwd(lib, *args, hz=hz)                    # training: keeps [H1 | Z2]
+        run_bwd(lib, *args, ds, hz=hz)                # backward from the kept activations (+ reduce)
+        run_bwd(lib, *args, ds)                       # backward recomputing layer 1 (+ reduce)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "bwd":
         print("PROBE", "OK" if bwd_checks(lib) else "FAIL")
