@@ -998,11 +998,20 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
                                                 grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di);
 }
 
-// PairwiseHingeLoss / PairwiseDCGHingeLoss for L > 128: O(n log n) by sorting
-// (ltr_hinge_sorted.cuh).  LTR_HINGE=pairs keeps the O(n^2) pair kernels (A-B timing, cross-check).
-inline bool hinge_by_pairs() {
+// PairwiseHingeLoss / PairwiseDCGHingeLoss for long lists: O(n log n) by sorting (ltr_hinge_sorted.cuh).  The
+// sorted kernel pays ~17 ns per query whatever the list size (one 256-thread CTA, a dozen barriers), the pair
+// kernels ~0.4 ns per pair: measured crossover between 320 and 400 documents (tools/hinge_sweep.py: 8192 x 200
+// takes 86 us by pairs against 145 us sorted; 1024 x 1024 takes 155 us against 57 us).  Same gradients bit
+// for bit either way.  LTR_HINGE=pairs / sorted forces one form for every list above 128 (A-B timing, cross-check).
+constexpr int kHingeSortMinL = 384;
+inline int hinge_form() {            // 0 = by list size, 1 = pairs, 2 = sorted
   const char* v = getenv("LTR_HINGE");
-  return v && strcmp(v, "pairs") == 0;
+  if (!v) return 0;
+  return strcmp(v, "pairs") == 0 ? 1 : (strcmp(v, "sorted") == 0 ? 2 : 0);
+}
+inline bool hinge_sorted_for(int L) {
+  const int f = hinge_form();
+  return f == 2 || (f == 0 && L > kHingeSortMinL);
 }
 
 constexpr int kHingeMaxL = 4096;
@@ -1049,7 +1058,7 @@ int dispatch_pair(int pm, const float* scores, const void* rel, int rel_bytes, c
     // query-wide chunk ring up to 1024 documents, 128 x 128 rank tiles beyond
     const bool ring = L <= kRingMaxL && !force_tiles();
     if ((pm == PM_HINGE || pm == PM_DCG_HINGE) && L > kWarpL && L <= kHingeMaxL && !ranking_out &&
-        !force_tiles() && !hinge_by_pairs())
+        !force_tiles() && hinge_sorted_for(L))
       return launch_hinge_sorted(scores, rel, rel_bytes, n, n_bytes, B, L, pm == PM_DCG_HINGE ? 1 : 0, loss_out,
                                  grad_out, loss_sum, st, di);
 #define LTR_TILED(TWMODE, DCG)                                                                          \

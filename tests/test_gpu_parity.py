@@ -690,7 +690,8 @@ def test_cuda_fused_linear_listnet_module_matches_unfused_modules():
 @pytest.mark.parametrize("mode", ["hinge", "dcg_hinge"])
 @pytest.mark.parametrize("B,L", [(6, 200), (3, 1000), (40, 130), (3, 1500), (2, 4096)])
 def test_cuda_sorted_hinge_matches_pair_kernels_and_oracle(mode, B, L, monkeypatch):
-    """Lists longer than 128 take the O(n log n) sorted hinge kernel.  Scores on a 1/4 grid put many
+    """Lists longer than 384 take the O(n log n) sorted hinge kernel (shorter ones the pair kernels: the sorted
+    form only pays beyond the measured crossover); LTR_HINGE forces either.  Scores on a 1/4 grid put many
     pairs exactly on the kink (s_i - s_j == 1: active, gradient -1 / +1) and create ties; the integer
     valued gradients must equal the float32 restatement of the reference bit for bit, and the O(n^2)
     pair kernels (LTR_HINGE=pairs) must agree."""
@@ -705,12 +706,16 @@ def test_cuda_sorted_hinge_matches_pair_kernels_and_oracle(mode, B, L, monkeypat
     if B > 4:
         y[4, : n[4]] = rng.integers(-5, 60, size=n[4])   # grades outside 0..31: in-kernel O(n^2) fallback
     wts = rng.uniform(0.5, 2.0, size=B).astype(np.float32)
-    loss, grad = _run_cuda(mode, s, y, n, weights=wts)
     ref_loss, ref_grad = oracle.pairwise_additive(mode, s, y, n, f32=True)
+    loss0, grad0 = _run_cuda(mode, s, y, n, weights=wts)                  # the form the list size selects
+    _assert_parity(loss0, grad0, ref_loss, ref_grad * wts[:, None].astype(np.float64))
+    monkeypatch.setenv("LTR_HINGE", "sorted")
+    loss, grad = _run_cuda(mode, s, y, n, weights=wts)
     _assert_parity(loss, grad, ref_loss, ref_grad * wts[:, None].astype(np.float64))
     if mode == "hinge":
         assert np.array_equal(grad, ref_grad * wts[:, None].astype(np.float64).astype(np.float32)) or \
             np.array_equal(grad.astype(np.float32), (ref_grad.astype(np.float32) * wts[:, None]))
+        assert np.array_equal(grad, grad0)
     monkeypatch.setenv("LTR_HINGE", "pairs")
     loss2, grad2 = _run_cuda(mode, s, y, n, weights=wts)
     assert np.allclose(loss, loss2, rtol=1e-5, atol=1e-6)
