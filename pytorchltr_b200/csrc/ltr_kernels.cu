@@ -989,8 +989,13 @@ int launch_pair_ring(const float* scores, const void* rel, int rel_bytes, const 
                      int B, int L, float sigma, int dcg_mod, float* loss_out, float* grad_out, int64_t* ranking_out,
                      float* loss_sum, void* ws, size_t ws_bytes, cudaStream_t st, const DeviceInfo& di) {
   // LTR_RING_WARPS=8 keeps eight warps per query for every list size (A-B timing)
+  // (2 warps per query up to 256 documents: 8-10 % over 4 warps for the sigmoid losses at 132..256 documents,
+  // tools/ring_warps_ab.py)
   static const int forced = env_int("LTR_RING_WARPS", 0);
   const bool short_lists = forced ? forced == kRingWarpsShort : L <= kRingShortL;
+  if ((forced == 2 || forced == 0) && L <= kRingTinyL)
+    return launch_pair_ring_w<TW, 2>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, dcg_mod, loss_out, grad_out,
+                                     ranking_out, loss_sum, ws, ws_bytes, st, di);
   if (short_lists)
     return launch_pair_ring_w<TW, kRingWarpsShort>(scores, rel, rel_bytes, n, n_bytes, B, L, sigma, dcg_mod, loss_out,
                                                    grad_out, ranking_out, loss_sum, ws, ws_bytes, st, di);

@@ -44,6 +44,7 @@ constexpr int kRingMaxL = 1024;
 constexpr int kRingWarpsLong = 8;
 constexpr int kRingWarpsShort = 4;
 constexpr int kRingShortL = 512;
+constexpr int kRingTinyL = 256;                     // two warps per query up to here
 
 // ---- 128-key blocks sorted in registers -------------------------------------------------------------
 // Element index inside the block = lane * 4 + r; `gbase` is the block's first index in the whole
@@ -515,7 +516,8 @@ __device__ __forceinline__ float ring_pairs(const RingSmem& m, const PairTables&
 }
 
 template <int TW, int W>
-__global__ void __launch_bounds__(W * 32, W == kRingWarpsLong ? LTR_RING_MIN_CTAS : LTR_RING_SHORT_CTAS)
+__global__ void __launch_bounds__(W * 32, W == kRingWarpsLong ? LTR_RING_MIN_CTAS
+                                          : (W == kRingWarpsShort ? LTR_RING_SHORT_CTAS : 2 * LTR_RING_SHORT_CTAS))
 pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                  int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,
