@@ -43,7 +43,7 @@ constexpr int kRingMaxL = 1024;
 // at one of its barriers costs the SM half as much.
 constexpr int kRingWarpsLong = 8;
 constexpr int kRingWarpsShort = 4;
-constexpr int kRingShortL = 512;
+constexpr int kRingShortL = 640;                    // (4 warps still ahead of 8 at 516..640 documents, equal at 768: tools/ring_warps_ab2.py)
 constexpr int kRingTinyL = 256;                     // two warps per query up to here
 
 // ---- 128-key blocks sorted in registers -------------------------------------------------------------
