@@ -517,7 +517,8 @@ __device__ __forceinline__ float ring_pairs(const RingSmem& m, const PairTables&
 
 template <int TW, int W>
 __global__ void __launch_bounds__(W * 32, W == kRingWarpsLong ? LTR_RING_MIN_CTAS
-                                          : (W == kRingWarpsShort ? LTR_RING_SHORT_CTAS : 2 * LTR_RING_SHORT_CTAS))
+                                          : (W == kRingWarpsShort ? LTR_RING_SHORT_CTAS
+                                                                    : (W == 2 ? 2 * LTR_RING_SHORT_CTAS : 16)))
 pair_ring_kernel(const float* __restrict__ scores, const void* __restrict__ rel, int rel_bytes,
                  const void* __restrict__ n, int n_bytes, int B, int L, int P, float sigma, int variant,
                  int tma, float* __restrict__ loss_out, float* __restrict__ grad_out,
