@@ -44,7 +44,10 @@ constexpr int kRingMaxL = 1024;
 constexpr int kRingWarpsLong = 8;
 constexpr int kRingWarpsShort = 4;
 constexpr int kRingShortL = 640;                    // (4 warps still ahead of 8 at 516..640 documents, equal at 768: tools/ring_warps_ab2.py)
-constexpr int kRingTinyL = 256;                     // two warps per query up to here
+#ifndef LTR_RING_TINY_L
+#define LTR_RING_TINY_L 256
+#endif
+constexpr int kRingTinyL = LTR_RING_TINY_L;         // one or two warps per query up to here
 
 // ---- 128-key blocks sorted in registers -------------------------------------------------------------
 // Element index inside the block = lane * 4 + r; `gbase` is the block's first index in the whole
