@@ -1256,8 +1256,10 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
     LTR_CUDA(cudaGetLastError());
     return LTR_OK;
   }
-  if (L <= 256 && !force_generic()) {
-    // short lists: one warp per query, in-register ranking, double-buffered TMA row staging
+  if (L <= 1024 && !force_generic()) {
+    // one warp per query, in-register ranking (E = 1 .. 32 documents per lane), double-buffered TMA row staging.
+    // Up to 1024 documents since round 2: the CTA-per-query kernel behind it costs 8x more per query at 260
+    // documents than this one at 256 (tools/metric_sweep.py)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const PairTables* tabs = nullptr;
     rc = pair_tables(st, &tabs);
@@ -1265,23 +1267,26 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
     int tma = rows_tma_ok(scores, rel, rel_bytes, L);
     if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
     const long long want = (static_cast<long long>(B) + kMetricWarps - 1) / kMetricWarps;
-#define LTR_RANKM_LAUNCH(E)                                                                                    \
+#define LTR_RANKM_LAUNCH(E, WPB)                                                                               \
   do {                                                                                                        \
     int per_sm = 0;                                                                                           \
-    LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_metrics_warp_kernel<E>,              \
-                                                           kMetricWarps * 32, 0));                            \
+    const long long want_ctas = (static_cast<long long>(B) + (WPB) - 1) / (WPB);                              \
+    LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_metrics_warp_kernel<E, WPB>,         \
+                                                           (WPB) * 32, 0));                                   \
     if (per_sm < 1) return LTR_EUNSUPPORTED;                                                                  \
     const long long cap = static_cast<long long>(per_sm) * di.sms;                                            \
     /* every warp the same number of queries: no second partial wave */                                       \
-    const long long rounds = (want + cap - 1) / cap;                                                          \
-    const int grid = static_cast<int>((want + rounds - 1) / rounds);                                          \
-    rank_metrics_warp_kernel<E><<<grid, kMetricWarps * 32, 0, st>>>(metric, scores, rel, rel_bytes, n, n_bytes, B, L, \
-                                                                    k, exp_gain, tma, out, out_ld, tabs);     \
+    const long long rounds = (want_ctas + cap - 1) / cap;                                                     \
+    const int grid = static_cast<int>((want_ctas + rounds - 1) / rounds);                                     \
+    rank_metrics_warp_kernel<E, WPB><<<grid, (WPB) * 32, 0, st>>>(metric, scores, rel, rel_bytes, n, n_bytes, B, L, \
+                                                                  k, exp_gain, tma, out, out_ld, tabs);       \
   } while (0)
-    if (L <= 32) LTR_RANKM_LAUNCH(1);
-    else if (L <= 64) LTR_RANKM_LAUNCH(2);
-    else if (L <= 128) LTR_RANKM_LAUNCH(4);
-    else LTR_RANKM_LAUNCH(8);
+    if (L <= 32) LTR_RANKM_LAUNCH(1, 4);
+    else if (L <= 64) LTR_RANKM_LAUNCH(2, 4);
+    else if (L <= 128) LTR_RANKM_LAUNCH(4, 4);
+    else if (L <= 256) LTR_RANKM_LAUNCH(8, 4);
+    else if (L <= 512) LTR_RANKM_LAUNCH(16, 2);
+    else LTR_RANKM_LAUNCH(32, 1);
 #undef LTR_RANKM_LAUNCH
     LTR_CUDA(cudaGetLastError());
     return LTR_OK;

@@ -1,6 +1,6 @@
 // ltr_metrics_warp.cuh -- dcg / ndcg / arp (evaluation/dcg.py, evaluation/arp.py) and the
 // standalone rank_by_score (utils/tensor_operations.py:48-64) with one WARP per query for list
-// sizes up to 256: the row is read once with coalesced loads, ranked by an in-register bitonic
+// sizes up to 1024 (metrics; rank_by_score up to 256): the row is read once with coalesced loads, ranked by an in-register bitonic
 // network, and the metric comes out of a shuffle scan / reduction.  HBM traffic is the
 // algorithmic 12 L + 12 bytes per query (8 L + 8 for rank_by_score's output).
 #pragma once
@@ -134,21 +134,23 @@ __device__ __forceinline__ void warp_inclusive_scan(float (&v)[E], int lane) {
 // the row of the warp's next query is in flight while the current one is ranked (the kernel is
 // otherwise bound by the latency of its own row loads).  Rows that cannot be staged (not 16-byte
 // aligned) are read with coalesced loads into the same buffers.
-template <int E>
-__global__ void __launch_bounds__(kMetricWarps * 32, 8)
+// WPB warps per CTA: 4 up to 256 documents (E <= 8), fewer for the longer lists, whose staging buffers and
+// registers (E keys, documents and terms per lane) are larger.
+template <int E, int WPB>
+__global__ void __launch_bounds__(WPB * 32, E <= 8 ? 8 : 1)
 rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const void* __restrict__ rel,
                          int rel_bytes, const void* __restrict__ n, int n_bytes, int B, int L, int k,
                          int exp_gain, int tma, float* __restrict__ out, int out_ld,
                          const PairTables* __restrict__ tabs) {
-  __shared__ __align__(16) unsigned char s_stage[kMetricWarps][2][32 * E * 12];
-  __shared__ int s_y[kMetricWarps][32 * E];
-  __shared__ uint64_t s_bar[kMetricWarps][2];
+  __shared__ __align__(16) unsigned char s_stage[WPB][2][32 * E * 12];
+  __shared__ int s_y[WPB][32 * E];
+  __shared__ uint64_t s_bar[WPB][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* raw_y = s_y[warp];
   const float* __restrict__ inv_disc = tabs->inv_disc;
   const uint32_t row_s_bytes = 4u * L, row_y_bytes = static_cast<uint32_t>(rel_bytes) * L;
-  const int stride = gridDim.x * kMetricWarps;
-  int b = blockIdx.x * kMetricWarps + warp;
+  const int stride = gridDim.x * WPB;
+  int b = blockIdx.x * WPB + warp;
   auto issue_row = [&](int q, int buf) {
     uint64_t* bar = &s_bar[warp][buf];
     unsigned char* stage = s_stage[warp][buf];
