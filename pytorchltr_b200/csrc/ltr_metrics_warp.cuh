@@ -136,8 +136,14 @@ __device__ __forceinline__ void warp_inclusive_scan(float (&v)[E], int lane) {
 // aligned) are read with coalesced loads into the same buffers.
 // WPB warps per CTA: 4 up to 256 documents (E <= 8), fewer for the longer lists, whose staging buffers and
 // registers (E keys, documents and terms per lane) are larger.
+#ifndef LTR_RM16_BLOCKS
+#define LTR_RM16_BLOCKS 1
+#endif
+#ifndef LTR_RM32_BLOCKS
+#define LTR_RM32_BLOCKS 1
+#endif
 template <int E, int WPB>
-__global__ void __launch_bounds__(WPB * 32, E <= 8 ? 8 : 1)
+__global__ void __launch_bounds__(WPB * 32, E <= 8 ? 8 : (E == 16 ? LTR_RM16_BLOCKS : LTR_RM32_BLOCKS))
 rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const void* __restrict__ rel,
                          int rel_bytes, const void* __restrict__ n, int n_bytes, int B, int L, int k,
                          int exp_gain, int tma, float* __restrict__ out, int out_ld,
