@@ -1312,15 +1312,22 @@ int ltr_rank_by_score(const float* scores, const void* n, int n_bytes, int B, in
   DeviceInfo di;
   rc = device_info(&di);
   if (rc != LTR_OK) return rc;
-  if (L <= 256 && !force_generic()) {
+  if (L <= 1024 && !force_generic()) {
+    // one warp per query up to 1024 documents (16 / 32 per lane beyond 256: the CTA-per-query kernel behind
+    // costs 8x more per query at 260 documents than this one at 256)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const long long want = (static_cast<long long>(B) + kMetricWarps - 1) / kMetricWarps;
-    const long long cap = static_cast<long long>(di.sms) * 12;
-    const int grid = static_cast<int>(want < cap ? want : cap);
-    if (L <= 128)
-      rank_by_score_warp_kernel<4><<<grid, kMetricWarps * 32, 0, st>>>(scores, n, n_bytes, B, L, ranking_out);
-    else
-      rank_by_score_warp_kernel<8><<<grid, kMetricWarps * 32, 0, st>>>(scores, n, n_bytes, B, L, ranking_out);
+#define LTR_RBS_LAUNCH(E, WPB)                                                                              \
+  do {                                                                                                     \
+    const long long want = (static_cast<long long>(B) + (WPB) - 1) / (WPB);                                \
+    const long long cap = static_cast<long long>(di.sms) * 12;                                             \
+    const int grid = static_cast<int>(want < cap ? want : cap);                                            \
+    rank_by_score_warp_kernel<E, WPB><<<grid, (WPB) * 32, 0, st>>>(scores, n, n_bytes, B, L, ranking_out); \
+  } while (0)
+    if (L <= 128) LTR_RBS_LAUNCH(4, 4);
+    else if (L <= 256) LTR_RBS_LAUNCH(8, 4);
+    else if (L <= 512) LTR_RBS_LAUNCH(16, 2);
+    else LTR_RBS_LAUNCH(32, 1);
+#undef LTR_RBS_LAUNCH
     LTR_CUDA(cudaGetLastError());
     return LTR_OK;
   }

@@ -310,14 +310,14 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
   }
 }
 
-template <int E>
-__global__ void __launch_bounds__(kMetricWarps * 32)
+template <int E, int WPB>
+__global__ void __launch_bounds__(WPB * 32)
 rank_by_score_warp_kernel(const float* __restrict__ scores, const void* __restrict__ n, int n_bytes,
                           int B, int L, int64_t* __restrict__ ranking_out) {
-  __shared__ MetricScratch<E> scratch[kMetricWarps];
+  __shared__ MetricScratch<E> scratch[WPB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   MetricScratch<E>& ws = scratch[warp];
-  for (int b = blockIdx.x * kMetricWarps + warp; b < B; b += gridDim.x * kMetricWarps) {
+  for (int b = blockIdx.x * WPB + warp; b < B; b += gridDim.x * WPB) {
     const int nb = load_n(n, n_bytes, b, L);
     const size_t base = static_cast<size_t>(b) * L;
 #pragma unroll
