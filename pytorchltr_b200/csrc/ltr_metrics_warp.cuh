@@ -11,10 +11,15 @@ namespace ltr {
 
 constexpr int kMetricWarps = 4;
 
+// Position p = lane * E + r of a row is read / written by lane `lane`: in a plain array the lanes of a warp
+// are E words apart and collide on gcd(E, 32) banks.  One pad word per 32 (pidx) makes both the blocked
+// access (lane * E + r) and the coalesced one (q * 32 + lane) conflict free.
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
+
 template <int E>
 struct MetricScratch {
-  float raw_s[32 * E];
-  int raw_y[32 * E];
+  float raw_s[33 * E];    // padded (pidx)
+  int raw_y[33 * E];      // padded (pidx)
 };
 
 // Exact (32-bit key, document) order of two neighbouring ranks: true when (ka, da) must come after (kb, db).
@@ -30,7 +35,7 @@ __device__ __forceinline__ bool key_doc_after(uint32_t ka, int da, uint32_t kb, 
 // only then the exact keys are fetched again (raw_s) and the neighbours are put right by odd-even
 // transposition rounds (runs of equal key bits are short: scores closer than 2^-15 relative), with the
 // exact 64-bit network as the last resort for pathological inputs.
-template <int E>
+template <int E, bool PADDED = false>
 __device__ __forceinline__ void warp_rank_by_score(const float (&sv)[E], int nb, int lane,
                                                    const float* __restrict__ raw_s, int (&doc)[E]) {
   constexpr uint32_t kIdxMask = 32u * E - 1u;
@@ -54,7 +59,8 @@ __device__ __forceinline__ void warp_rank_by_score(const float (&sv)[E], int nb,
 
   uint32_t ek[E];
 #pragma unroll
-  for (int r = 0; r < E; ++r) ek[r] = lane * E + r < nb ? desc_key_f32(raw_s[doc[r]]) : kPadKey;
+  for (int r = 0; r < E; ++r)
+    ek[r] = lane * E + r < nb ? desc_key_f32(raw_s[PADDED ? pidx(doc[r]) : doc[r]]) : kPadKey;
   for (int round = 0; round < 8; ++round) {
     bool swapped = false;
     // even phase: (0,1), (2,3), ... inside the lane
@@ -149,10 +155,14 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
                          int exp_gain, int tma, float* __restrict__ out, int out_ld,
                          const PairTables* __restrict__ tabs) {
   __shared__ __align__(16) unsigned char s_stage[WPB][2][32 * E * 12];
-  __shared__ int s_y[WPB][32 * E];
+  __shared__ int s_y[WPB][33 * E];                // grades, padded (pidx)
+  __shared__ float s_pad[WPB][E >= 16 ? 33 * E : 1];   // E >= 16: the scores once more, padded (pidx)
   __shared__ uint64_t s_bar[WPB][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* raw_y = s_y[warp];
+  // padding pays from 16 documents per lane on (16- / 32-way conflicts); below, the extra copy costs more
+  constexpr bool kPad = E >= 16;
+  auto yi = [](int i) { return kPad ? pidx(i) : i; };
   const float* __restrict__ inv_disc = tabs->inv_disc;
   const uint32_t row_s_bytes = 4u * L, row_y_bytes = static_cast<uint32_t>(rel_bytes) * L;
   const int stride = gridDim.x * WPB;
@@ -191,7 +201,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 #pragma unroll
       for (int q = 0; q < E; ++q) {
         const int j = q * 32 + lane;
-        if (j < L) raw_y[j] = load_int_clamped(sy, rel_bytes, j);
+        if (j < L) raw_y[yi(j)] = load_int_clamped(sy, rel_bytes, j);
       }
     } else {
 #pragma unroll
@@ -199,15 +209,25 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
         const int j = q * 32 + lane;
         if (j < L) {
           raw_s[j] = scores[base + j];
-          raw_y[j] = load_int_clamped(rel, rel_bytes, base + j);
+          raw_y[yi(j)] = load_int_clamped(rel, rel_bytes, base + j);
         }
       }
     }
+    float* pad = s_pad[warp];
     __syncwarp();
+    if constexpr (kPad) {
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int j = q * 32 + lane;
+        pad[j + q] = j < L ? raw_s[j] : 0.0f;          // pidx(j) = j + q
+      }
+      __syncwarp();
+    }
     float sv[E];
     int doc[E];
 #pragma unroll
-    for (int r = 0; r < E; ++r) sv[r] = lane * E + r < nb ? raw_s[lane * E + r] : 0.0f;
+    for (int r = 0; r < E; ++r)
+      sv[r] = lane * E + r < nb ? (kPad ? pad[pidx(lane * E + r)] : raw_s[lane * E + r]) : 0.0f;
     warp_rank_by_score<E>(sv, nb, lane, raw_s, doc);
 
     // relevance per rank; ranks >= nb are the padded documents in index order, whose relevance
@@ -217,7 +237,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 #pragma unroll
     for (int r = 0; r < E; ++r) {
       const int p = lane * E + r;
-      iy[r] = p < L ? raw_y[p < nb ? doc[r] : p] : 0;
+      iy[r] = p < L ? raw_y[yi(p < nb ? doc[r] : p)] : 0;
       ry[r] = static_cast<float>(iy[r]);
     }
 
@@ -252,7 +272,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         const int j = lane * E + r;
-        yk[r] = j < nb ? desc_key_i32(raw_y[j]) : kPadKey;
+        yk[r] = j < nb ? desc_key_i32(raw_y[yi(j)]) : kPadKey;
       }
       warp_bitonic_sort32<E>(yk, lane);
 #pragma unroll
@@ -260,7 +280,7 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
         const int p = lane * E + r;
         int gy = 0;
         if (p < nb) gy = static_cast<int>(~yk[r] ^ 0x80000000u);
-        else if (p < L) gy = raw_y[p];
+        else if (p < L) gy = raw_y[yi(p)];
         const float g = exp_gain ? gain_of_grade(gy) : static_cast<float>(gy);
         iterm[r] = p < L ? g * __ldg(inv_disc + p) : 0.0f;
       }
@@ -293,17 +313,18 @@ rank_metrics_warp_kernel(int metric, const float* __restrict__ scores, const voi
           term[r] = term[r] / iv;
         }
       }
-      // stage through shared memory (the grades are dead) for coalesced stores
-      float* o = reinterpret_cast<float*>(raw_y);
+      // stage through shared memory for coalesced stores: the padded array (its scores are dead), or, for
+      // short lists, the grades' array (dead too)
+      float* o = kPad ? pad : reinterpret_cast<float*>(raw_y);
       __syncwarp();
 #pragma unroll
-      for (int r = 0; r < E; ++r) o[lane * E + r] = term[r];
+      for (int r = 0; r < E; ++r) o[yi(lane * E + r)] = term[r];
       __syncwarp();
       float* __restrict__ go = out + static_cast<size_t>(b) * out_ld;
 #pragma unroll
       for (int q = 0; q < E; ++q) {
         const int j = q * 32 + lane;
-        if (j < L) go[j] = o[j];
+        if (j < L) go[j] = o[yi(j)];
       }
     }
     __syncwarp();
@@ -323,25 +344,25 @@ rank_by_score_warp_kernel(const float* __restrict__ scores, const void* __restri
 #pragma unroll
     for (int q = 0; q < E; ++q) {
       const int j = q * 32 + lane;
-      if (j < L) ws.raw_s[j] = scores[base + j];
+      if (j < L) ws.raw_s[j + q] = scores[base + j];   // pidx(j) = j + q
     }
     __syncwarp();
     float sv[E];
     int doc[E];
 #pragma unroll
-    for (int r = 0; r < E; ++r) sv[r] = lane * E + r < nb ? ws.raw_s[lane * E + r] : 0.0f;
-    warp_rank_by_score<E>(sv, nb, lane, ws.raw_s, doc);
+    for (int r = 0; r < E; ++r) sv[r] = lane * E + r < nb ? ws.raw_s[pidx(lane * E + r)] : 0.0f;
+    warp_rank_by_score<E, true>(sv, nb, lane, ws.raw_s, doc);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < E; ++r) {
       const int p = lane * E + r;
-      ws.raw_y[p] = p < nb ? doc[r] : p;
+      ws.raw_y[pidx(p)] = p < nb ? doc[r] : p;
     }
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < E; ++q) {
       const int j = q * 32 + lane;
-      if (j < L) ranking_out[base + j] = ws.raw_y[j];
+      if (j < L) ranking_out[base + j] = ws.raw_y[j + q];
     }
     __syncwarp();
   }
