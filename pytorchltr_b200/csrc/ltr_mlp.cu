@@ -142,9 +142,9 @@ static int launch_mlp_backward_hz(const float* features, const float* hz, long l
   using Hz = MlpHz<H1, H2>;
   constexpr int NHZ = (Hz::P + 31) / 32;
   const int nk = (F + 31) / 32;
-  if (2 * kMlpHzBufCols + 32 * nk + 32 * NHZ + 16 > 512) return LTR_EUNSUPPORTED;      // TMEM columns
+  if (2 * kMlpHzBufCols + 32 * nk + 32 * NHZ > 512) return LTR_EUNSUPPORTED;      // TMEM columns
   const size_t smem = 1024 + kMlpA2Bytes + static_cast<size_t>(nk + 2 * NHZ) * kMlpChunkX + kMlpN1 * 64 +
-                      kMlpOnesBytes + sizeof(MlpHzSmall);
+                      sizeof(MlpHzSmall);
   if (smem > 227u * 1024u) return LTR_EUNSUPPORTED;
   CUtensorMap map_x, map_hz;
   int rc = make_map_2d(&map_x, features, rows, F, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);

@@ -190,13 +190,14 @@ __device__ __forceinline__ void mlp_issue_layer1(uint32_t d_tmem, uint32_t xs, u
 }
 
 // Activation row kept for the backward pass (ltr_mlp_scores with hz_out): P floats per document,
-// H1 = relu(Z1 + b1) in columns [0, H1), the layer-2 pre-activation Z2 (bias included) in [Z0, Z0 + H2), zeros
-// elsewhere.  The backward kernel uses the row index of the dZ1 operand for both: rows [0, H1) carry dZ1,
+// H1 = relu(Z1 + b1) in columns [0, H1), the layer-2 pre-activation Z2 (bias included) in [Z0, Z0 + H2), 1.0 in
+// column Z0 + H2 (the sums of dZ1 / dZ2 over documents then fall out of the same product as dW2), zeros elsewhere.  The backward kernel uses the row index of the dZ1 operand for both: rows [0, H1) carry dZ1,
 // rows [Z0, Z0 + H2) carry dZ2 -- which needs Z0 + H2 <= 64 (true for 50-10 and 32-8).
 template <int H1, int H2>
 struct MlpHz {
   static constexpr int Z0 = (H1 + 3) / 4 * 4;
-  static constexpr int P = (Z0 + H2 + 3) / 4 * 4;
+  static constexpr int ONE = Z0 + H2;               // a column of ones: its products with dZ1 / dZ2 are db1 / db2
+  static constexpr int P = (ONE + 1 + 3) / 4 * 4;
   static constexpr bool kFits = Z0 + H2 <= kMlpN1;
 };
 
@@ -354,7 +355,7 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                           : (j >= Hz::Z0 && j < Hz::Z0 + H2
                                  ? (((j - Hz::Z0) & 1) ? row.z2[(j >= Hz::Z0 && j < Hz::Z0 + H2 ? j - Hz::Z0 : 0) >> 1].y
                                                        : row.z2[(j >= Hz::Z0 && j < Hz::Z0 + H2 ? j - Hz::Z0 : 0) >> 1].x)
-                                 : 0.0f);
+                                 : (j == Hz::ONE ? 1.0f : 0.0f));
           }
           o[q] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -875,8 +876,8 @@ mlp_backward_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 //   warps   dZ2 = ds * w3 * [Z2 > 0] (Z2 read from the staged activation tile) -> TMEM; dW3 / db3 in registers
 //   MMA-dH  dH1 (128 x 64) = dZ2 W2          A from TMEM, W2^T in shared memory
 //   warps   dZ1 = dH1 * [H1 > 0]; rows [0, H1) of the operand buffer get dZ1^T, rows [Z0, Z0 + H2) get dZ2^T
-//   MMA2    [dZ1^T ; dZ2^T] (64 x 128 documents) . [X | H1 Z2 | 1] (128 documents x (F + 64 + 8)): the rows of
-//           dZ1 against X give dW1, the rows of dZ2 against H1 give dW2, either against the ones give db1 / db2
+//   MMA2    [dZ1^T ; dZ2^T] (64 x 128 documents) . [X | H1 Z2 1] (128 documents x (F + 64)): the rows of dZ1
+//           against X give dW1, the rows of dZ2 against H1 give dW2, either against the column of ones db1 / db2
 //           (the other blocks of the product are never read).  X and the activation tile are both MN-major
 //           operands exactly as TMA leaves them (128-byte swizzle, 32-byte atom); accumulators stay in TMEM.
 // The masks are the forward pass's own (same H1 and Z2 bits), so the result is the gradient of exactly the
@@ -916,14 +917,12 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
   unsigned char* xmn = a2s + kMlpA2Bytes;           // feature tile, MN-major form
   unsigned char* hzs = xmn + nk * kMlpChunkX;       // two stages of the activation tile, MN-major form
   unsigned char* w2ts = hzs + 2 * NHZ * kMlpChunkX; // W2^T [j][i], K-major, 64-byte swizzle
-  unsigned char* ones = w2ts + kMlpN1 * 64;
-  MlpHzSmall* sp = reinterpret_cast<MlpHzSmall*>(ones + kMlpOnesBytes);
+  MlpHzSmall* sp = reinterpret_cast<MlpHzSmall*>(w2ts + kMlpN1 * 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int tmem_cols = 512;
   const uint32_t d2col = 2 * kMlpHzBufCols;         // dW1 block | dW2 block | bias block
   for (int t = threadIdx.x; t < kMlpMaxH2; t += blockDim.x) sp->w3[t] = t < h2n ? w3[t] : 0.0f;
   for (int t = threadIdx.x; t < kMlpA2Bytes / 4; t += blockDim.x) reinterpret_cast<float*>(a2s)[t] = 0.0f;
-  for (int t = threadIdx.x; t < kMlpOnesBytes / 4; t += blockDim.x) reinterpret_cast<float*>(ones)[t] = 1.0f;
   for (int t = threadIdx.x; t < kMlpMaxH2 * kMlpMaxH1; t += blockDim.x) {
     const int i = t / kMlpMaxH1, j = t - i * kMlpMaxH1;
     const float v = (i < h2n && j < h1n) ? w2[i * h1n + j] : 0.0f;
@@ -978,10 +977,8 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
   } else if (warp == 5) {
     if (lane == 0 && my_tiles > 0) {
       constexpr uint32_t idesc_dh = umma_idesc_tf32(kMlpTileDocs, kMlpN1, 0, 0);
-      constexpr uint32_t idesc_b = umma_idesc_tf32(64, 8, 0, 0);
       constexpr uint32_t idesc_hz = umma_idesc_tf32(64, HZN, 0, 1);
       const uint32_t idesc_x = umma_idesc_tf32(64, xn, 0, 1);
-      const uint64_t ones_desc = umma_desc(smem_u32(ones), 16, 1024, 2);
       const uint32_t a2 = smem_u32(a2s), x_mn = smem_u32(xmn), hz0 = smem_u32(hzs), w2ta = smem_u32(w2ts);
       uint32_t acc = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -997,18 +994,22 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
         umma_commit(&sp->bar_dh);
         // [dW1 | dW2 | db] += [dZ1^T ; dZ2^T] [X | H1 Z2 | 1]
         mbar_wait_guarded<true>(&sp->bar_a2_full, it & 1);   // (the warps read the activation tile before: it has landed)
-        const uint32_t hz = hz0 + b * NHZ * kMlpChunkX;
+        // (the issuing thread is a serial resource: 32 MMAs per tile, descriptors advanced by one add each)
+        const uint64_t a_desc0 = umma_desc(a2, 16, 1024, 2);
+        const uint64_t x_desc0 = umma_desc(x_mn, kMlpChunkX, 512, kUmmaLayout32BAtom);
+        const uint64_t h_desc0 = umma_desc(hz0 + b * NHZ * kMlpChunkX, kMlpChunkX, 512, kUmmaLayout32BAtom);
+#pragma unroll
         for (int dg = 0; dg < 4; ++dg) {
           mbar_wait_guarded<true>(&sp->bar_mnf[dg], it & 1);
           tc_fence_after();
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const int ks = 4 * dg + k4;
-            const uint64_t adesc = umma_desc(a2 + dg * (kMlpN1 * 128) + k4 * 32, 16, 1024, 2);
-            umma_tf32(tmem + d2col, adesc, umma_desc(x_mn + ks * 1024, kMlpChunkX, 512, kUmmaLayout32BAtom), idesc_x, acc);
-            umma_tf32(tmem + d2col + xn, adesc, umma_desc(hz + ks * 1024, kMlpChunkX, 512, kUmmaLayout32BAtom), idesc_hz,
-                      acc);
-            umma_tf32(tmem + d2col + xn + HZN, adesc, ones_desc, idesc_b, acc);
+            // start addresses live in the low 14 bits of the descriptors, in 16-byte units
+            const uint64_t adesc = a_desc0 + static_cast<uint64_t>((dg * (kMlpN1 * 128) + k4 * 32) >> 4);
+            const uint64_t koff = static_cast<uint64_t>((ks * 1024) >> 4);
+            umma_tf32(tmem + d2col, adesc, x_desc0 + koff, idesc_x, acc);
+            umma_tf32(tmem + d2col + xn, adesc, h_desc0 + koff, idesc_hz, acc);
             acc = 1;
           }
           umma_commit(&sp->bar_mne[dg]);
@@ -1131,7 +1132,7 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
     mbar_wait_guarded(&sp->bar_a2_free, (my_tiles - 1) & 1);
     tc_fence_after();
     const int j = warp * 16 + lane;
-    const int ncols = xn + HZN + 8;
+    const int ncols = xn + HZN;
     for (int c0 = 0; c0 < ncols; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem + d2col + c0 + lane_addr, v);
@@ -1143,10 +1144,10 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
           const float val = __uint_as_float(v[k]);
           if (j < h1n) {
             if (c < g.F) out[static_cast<size_t>(j) * g.F + c] = val;
-            if (c == xn + HZN) out[off_b1 + j] = val;
+            if (c == xn + Hz::ONE) out[off_b1 + j] = val;
           } else if (j >= Hz::Z0 && j - Hz::Z0 < h2n) {
             if (c >= xn && c - xn < h1n) out[off_w2 + (j - Hz::Z0) * h1n + (c - xn)] = val;
-            if (c == xn + HZN) out[off_b2 + (j - Hz::Z0)] = val;
+            if (c == xn + Hz::ONE) out[off_b2 + (j - Hz::Z0)] = val;
           }
         }
       }

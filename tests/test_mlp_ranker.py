@@ -241,7 +241,10 @@ def test_mlp_backward_from_kept_activations_vs_oracle(rows, F, H1, H2):
     z0 = 52 if (H1, H2) == (50, 10) else 32          # columns of the kernel instantiation (50-10, or 32-8 padded)
     assert np.abs(hzn[:, :H1] - h1).max() <= 2e-5 * max(1.0, np.abs(h1).max())
     assert np.abs(hzn[:, z0:z0 + H2] - z2).max() <= 2e-5 * max(1.0, np.abs(z2).max())
-    assert (hzn[:, H1:z0] == 0).all() and (hzn[:, z0 + H2:] == 0).all() and hzn.shape[1] == (64 if H1 == 50 else 40)
+    one = z0 + (10 if (H1, H2) == (50, 10) else 8)   # the column of ones that yields db1 / db2
+    assert (hzn[:, H1:z0] == 0).all() and (hzn[:, z0 + H2:one] == 0).all()
+    assert (hzn[:, one] == 1).all() and (hzn[:, one + 1:] == 0).all()
+    assert hzn.shape[1] == (64 if H1 == 50 else 44)
     rc, out = _call_backward(lib, x, p, ds, hz)
     assert rc == 0
     torch.cuda.synchronize()
