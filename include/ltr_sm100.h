@@ -195,12 +195,16 @@ int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride
  * tensor copies, accumulators in tensor memory): TF32 operands, float32 accumulation -- the arithmetic of
  * torch.backends.cuda.matmul.allow_tf32 = True; layers 2-3 are float32.  The features are read once, only
  * the score leaves the SM.  Requires F % 4 == 0, 16-byte aligned features / w1, H1 <= 64, H2 <= 16
- * (LTR_EUNSUPPORTED otherwise: the caller keeps its own modules for such a model).
+ * (LTR_EUNSUPPORTED otherwise: the caller keeps its own modules for such a model).  Any width F: W1 stays in
+ * shared memory beside whole 128-document tiles while that fits (F <= 288), wider rows (Yahoo's 699 -> 700)
+ * stream W1 with the tile in 64-column slabs that accumulate in tensor memory.  Rows of a multiple of 32 bytes
+ * (F % 8 == 0) stream about 20 % faster than F % 8 == 4.
  * hz_out (NULL to skip; what a training step passes): [rows * ltr_mlp_hz_pitch(H1, H2)] floats, the activations
  * ltr_mlp_backward can start from instead of recomputing layer 1 -- per document relu(W1 x + b1) in columns
- * [0, H1), the layer-2 pre-activation in [roundup4(H1), + H2), zeros elsewhere (256 B at 50-10, written with
- * 128-bit stores next to the 544 B of features read).  ltr_mlp_hz_pitch is 0 for shapes without this path
- * (H1 = 50, H2 = 10 and H1 <= 32, H2 <= 8 have it).
+ * [0, H1), the layer-2 pre-activation in [Z0, Z0 + H2) with Z0 = roundup4(H1) of the kernel instantiation (52 /
+ * 10 at 50-10; 32 / 8 for H1 <= 32, H2 <= 8), 1.0 in the column after them (its products are db1 / db2), zeros
+ * elsewhere (256 B at 50-10, written with 128-bit stores next to the 544 B of features read).
+ * ltr_mlp_hz_pitch is 0 for shapes without this path (H1 = 50, H2 = 10 and H1 <= 32, H2 <= 8 have it).
  */
 int ltr_mlp_hz_pitch(int H1, int H2);
 int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1, const float *b1,
@@ -216,13 +220,14 @@ int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1
  *   [dW1 (H1*F) | db1 (H1) | dW2 (H2*H1) | db2 (H2) | dW3 (H2) | db3 (1)]
  * in torch.nn.Linear's layouts.  dW1 multiplies TF32 operands (dZ1 and the features), everything else is
  * float32; sums are formed in a fixed order (bit-reproducible).  `workspace`: device memory, >=
- * ltr_mlp_workspace_bytes(F, H1, H2) bytes.  Same shape limits as ltr_mlp_scores; one feature tile, W1 and the
- * dZ1 operand must fit in shared memory together (F up to about 224).
+ * ltr_mlp_workspace_bytes(F, H1, H2) bytes.  Same shape limits as ltr_mlp_scores; without hz one feature tile,
+ * W1 and the dZ1 operand must fit in shared memory together (F up to 136; LTR_EUNSUPPORTED beyond) -- with hz
+ * any width: a CTA accumulates up to 224 columns of dW1, wider rows are split into column slabs over the CTAs.
  * d loss / d features is not formed (the features are data, not a trainable module's output).
  * hz: the activation rows kept by ltr_mlp_scores (hz_out), or NULL.  With them the launch reads features and
  * activations once each (no W1, no layer 1 again), uses the forward pass's own ReLU masks (the gradient of
  * exactly the function the forward kernel computed) and forms ALL sums over documents as one tensor-core
- * product per 8 documents: [dZ1^T ; dZ2^T] (64 x 8) . [X | H1 | 1] gives dW1, dW2, db1, db2 in one accumulator.
+ * product per 8 documents: [dZ1^T ; dZ2^T] (64 x 8) . [X | H1 Z2 1] gives dW1, dW2, db1, db2 in one accumulator.
  */
 size_t ltr_mlp_grad_len(int F, int H1, int H2);
 size_t ltr_mlp_workspace_bytes(int F, int H1, int H2);

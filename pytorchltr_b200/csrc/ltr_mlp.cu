@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -69,6 +70,8 @@ static MlpGeom mlp_geometry(int F, int stages) {
   g.stage_bytes = g.nfull * kMlpChunkX + kMlpTileDocs * g.tail_pitch;
   g.w1_bytes = g.nfull * kMlpChunkW + kMlpN1 * g.tail_pitch;
   g.stages = stages;
+  g.slab_chunks = 0;
+  g.nchunks = (F + 31) / 32;
   return g;
 }
 
@@ -138,14 +141,21 @@ static int mlp_hz_pitch(int H1, int H2) {
 template <int H1, int H2>
 static int launch_mlp_backward_hz(const float* features, const float* hz, long long rows, int F, const float* w2,
                                   const float* w3, int h1, int h2, const float* dscores, float* partials, int len,
-                                  int* grid_out, cudaStream_t st, const DeviceInfo& di) {
+                                  int* nparts_out, int* nslabs_out, int* slab_cols_out, cudaStream_t st,
+                                  const DeviceInfo& di) {
   using Hz = MlpHz<H1, H2>;
   constexpr int NHZ = (Hz::P + 31) / 32;
-  const int nk = (F + 31) / 32;
-  if (2 * kMlpHzBufCols + 32 * nk + 32 * NHZ > 512) return LTR_EUNSUPPORTED;      // TMEM columns
-  const size_t smem = 1024 + kMlpA2Bytes + static_cast<size_t>(nk + 2 * NHZ) * kMlpChunkX + kMlpN1 * 64 +
-                      sizeof(MlpHzSmall);
-  if (smem > 227u * 1024u) return LTR_EUNSUPPORTED;
+  // feature columns per CTA: bounded by the TMEM columns of the dW1 accumulator and by the shared memory of one
+  // MN-major tile; wider rows are split into column slabs over the CTAs
+  const int nk_all = (F + 31) / 32;
+  int nk_max = (512 - 2 * kMlpHzBufCols - 32 * NHZ) / 32;
+  const size_t fixed = 1024 + kMlpA2Bytes + static_cast<size_t>(2 * NHZ) * kMlpChunkX + kMlpN1 * 64 + sizeof(MlpHzSmall);
+  const int nk_smem = static_cast<int>((227u * 1024u - fixed) / kMlpChunkX);
+  if (nk_smem < nk_max) nk_max = nk_smem;
+  if (nk_max < 1) return LTR_EUNSUPPORTED;
+  const int nslabs = (nk_all + nk_max - 1) / nk_max;
+  const int nk = (nk_all + nslabs - 1) / nslabs;
+  const size_t smem = fixed + static_cast<size_t>(nk) * kMlpChunkX;
   CUtensorMap map_x, map_hz;
   int rc = make_map_2d(&map_x, features, rows, F, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != LTR_OK) return rc;
@@ -153,14 +163,20 @@ static int launch_mlp_backward_hz(const float* features, const float* hz, long l
   if (rc != LTR_OK) return rc;
   MlpGeom g = mlp_geometry(F, 1);
   const int ntiles = static_cast<int>((rows + kMlpTileDocs - 1) / kMlpTileDocs);
-  int grid = ntiles < di.sms ? ntiles : di.sms;
-  if (grid > kMlpMaxCtas) grid = kMlpMaxCtas;
+  // CTA b: column slab b % nslabs of the tiles b / nslabs, b / nslabs + nparts, ...
+  int cap = di.sms < kMlpMaxCtas ? di.sms : kMlpMaxCtas;
+  if (cap < nslabs) return LTR_EUNSUPPORTED;
+  int nparts = cap / nslabs;
+  if (nparts > ntiles) nparts = ntiles;
+  const int grid = nparts * nslabs;
   LTR_CUDA(cudaFuncSetAttribute(mlp_backward_hz_kernel<H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   mlp_backward_hz_kernel<H1, H2><<<grid, kMlpHzThreads, smem, st>>>(map_x, map_hz, g, w2, w3, h1, h2, dscores, rows,
-                                                                    ntiles, partials, len);
+                                                                    ntiles, partials, len, nslabs, 32 * nk);
   LTR_CUDA(cudaGetLastError());
-  *grid_out = grid;
+  *nparts_out = nparts;
+  *nslabs_out = nslabs;
+  *slab_cols_out = 32 * nk;
   return LTR_OK;
 }
 
@@ -181,10 +197,32 @@ int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1
   if (rows == 0) return LTR_OK;
   const size_t budget = 227u * 1024u - 1024u - sizeof(MlpSmallParams);
   MlpGeom g = mlp_geometry(F, 1);
-  if (static_cast<size_t>(g.w1_bytes) + g.stage_bytes > budget) return LTR_EUNSUPPORTED;
-  int stages = static_cast<int>((budget - g.w1_bytes) / g.stage_bytes);
-  g.stages = stages > 4 ? 4 : stages;
   MlpMaps m;
+  // W1 resident beside whole feature tiles while two of them fit (rows up to 192 floats); beyond that an
+  // inference call streams W1 with the tile through a ring of four 2-chunk slabs (measured: 1.2-1.4x the
+  // single-stage resident form at 200..288 features, tools/mlp_slab_ab.sh), a call that also writes the activation
+  // rows stays resident until a tile no longer fits (288 features), then streams as well
+  int slab_chunks = 2, slab_stages = 4;
+  const size_t resident = static_cast<size_t>(g.w1_bytes) + g.stage_bytes;
+  bool slabs = resident > budget || (!hz_out && resident + g.stage_bytes > budget && F >= 32);
+  if (const char* v = getenv("LTR_MLP_SLAB")) {         // "chunks,stages" (A/B runs): force the streamed-W1 form
+    if (sscanf(v, "%d,%d", &slab_chunks, &slab_stages) == 2 && slab_chunks >= 1 && slab_stages >= 1 &&
+        slab_stages <= 8 && static_cast<size_t>(slab_chunks) * slab_stages * (kMlpChunkX + kMlpChunkW) <= budget)
+      slabs = F >= 32;
+    else
+      slab_chunks = 2, slab_stages = 4;
+  }
+  if (slabs) {
+    // rows too wide for W1 and a whole tile side by side: stream both in slabs of two chunks, four stages
+    if (F < 32) return LTR_EUNSUPPORTED;
+    g.slab_chunks = slab_chunks;
+    g.stages = slab_stages;
+    g.stage_bytes = g.slab_chunks * (kMlpChunkX + kMlpChunkW);
+    g.w1_bytes = 0;
+  } else {
+    const int stages = static_cast<int>((budget - g.w1_bytes) / g.stage_bytes);
+    g.stages = stages > 4 ? 4 : stages;
+  }
   rc = mlp_make_maps(&m, g, features, rows, w1, H1);
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -224,13 +262,16 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
   if (hz) {
     // the forward pass kept [H1 | Z2]: every byte once, no layer 1 again
     if (ltr_mlp_hz_pitch(H1, H2) == 0 || !aligned16(hz)) return LTR_EINVAL;
-    int hgrid = 0;
+    int nparts = 0, nslabs = 1, slab_cols = 0;
     rc = H1 == 50 ? launch_mlp_backward_hz<50, 10>(features, hz, rows, F, w2, w3, H1, H2, dscores,
-                                                   static_cast<float*>(workspace), len, &hgrid, st, di)
+                                                   static_cast<float*>(workspace), len, &nparts, &nslabs, &slab_cols,
+                                                   st, di)
                   : launch_mlp_backward_hz<32, 8>(features, hz, rows, F, w2, w3, H1, H2, dscores,
-                                                  static_cast<float*>(workspace), len, &hgrid, st, di);
+                                                  static_cast<float*>(workspace), len, &nparts, &nslabs, &slab_cols,
+                                                  st, di);
     if (rc != LTR_OK) return rc;
-    mlp_reduce_kernel<<<(len + 63) / 64, 256, 0, st>>>(static_cast<float*>(workspace), hgrid, len, grads_out);
+    mlp_reduce_kernel<<<(len + 63) / 64, 256, 0, st>>>(static_cast<float*>(workspace), nparts, len, grads_out, nslabs,
+                                                       slab_cols, F, H1 * F);
     LTR_CUDA(cudaGetLastError());
     return LTR_OK;
   }
@@ -267,7 +308,7 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
 #undef LTR_MLP_BWD
   LTR_CUDA(cudaGetLastError());
   const int rgrid = (len + 63) / 64;
-  mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out);
+  mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out, 1, F, F, H1 * F);
   LTR_CUDA(cudaGetLastError());
   return LTR_OK;
 }

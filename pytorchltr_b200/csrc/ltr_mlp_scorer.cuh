@@ -37,6 +37,10 @@ struct MlpGeom {
   int stage_bytes;   // one feature tile
   int w1_bytes;      // W1 in the same form (64 rows)
   int stages;
+  int slab_chunks;   // 0: W1 resident, one stage = one feature tile.  > 0 (wide rows, forward only): W1 does not
+                     // fit beside a tile, so a stage holds `slab_chunks` chunks of the tile and the matching
+                     // chunks of W1, and the tile's product accumulates over ceil(nchunks / slab_chunks) stages
+  int nchunks;       // ceil(F / 32)
 };
 
 // ---- tcgen05 / TMA-tensor wrappers ------------------------------------------------------------------
@@ -133,8 +137,8 @@ struct MlpSmallParams {
   float b3;
   uint32_t tmem_base;
   uint64_t bar_w;
-  uint64_t bar_full[4];
-  uint64_t bar_empty[4];
+  uint64_t bar_full[8];
+  uint64_t bar_empty[8];
   uint64_t bar_tfull[2];
   uint64_t bar_tempty[2];
   uint64_t bar_aux[8];
@@ -294,7 +298,25 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t tmem = sp->tmem_base;
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (lane == 0 && g.slab_chunks > 0) {
+      // wide rows: (tile, slab) pairs through the stage ring; columns past F and hidden units past H1 arrive as
+      // zeros (out-of-range elements of a tensor copy), so every chunk is a full 32-column box
+      int v = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c0 = 0; c0 < g.nchunks; c0 += g.slab_chunks, ++v) {
+          const int s = v % g.stages;
+          const int nch = g.nchunks - c0 < g.slab_chunks ? g.nchunks - c0 : g.slab_chunks;
+          unsigned char* stage = xs + static_cast<size_t>(s) * g.stage_bytes;
+          mbar_wait_guarded<true>(&sp->bar_empty[s], ((v / g.stages) & 1) ^ 1u);
+          mbar_arrive_expect_tx(&sp->bar_full[s], nch * (kMlpChunkX + kMlpChunkW));
+          for (int c = 0; c < nch; ++c) {
+            tma_load_2d(stage + c * kMlpChunkX, &map_x, (c0 + c) * 32, tile * kMlpTileDocs, &sp->bar_full[s]);
+            tma_load_2d(stage + g.slab_chunks * kMlpChunkX + c * kMlpChunkW, &map_w, (c0 + c) * 32, 0,
+                        &sp->bar_full[s]);
+          }
+        }
+      }
+    } else if (lane == 0) {
       mbar_arrive_expect_tx(&sp->bar_w, g.w1_bytes);
       mlp_load_tile(w1s, &map_w, &map_w_tail, g, 0, kMlpChunkW, &sp->bar_w);
       int it = 0;
@@ -308,7 +330,34 @@ mlp_scores_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (lane == 0 && g.slab_chunks > 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kMlpTileDocs, kMlpN1, 0, 0);
+      int it = 0, v = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        mbar_wait_guarded<true>(&sp->bar_tempty[b], ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int c0 = 0; c0 < g.nchunks; c0 += g.slab_chunks, ++v) {
+          const int s = v % g.stages;
+          const int nch = g.nchunks - c0 < g.slab_chunks ? g.nchunks - c0 : g.slab_chunks;
+          const uint32_t xa = smem_u32(xs + static_cast<size_t>(s) * g.stage_bytes);
+          const uint32_t wa = xa + g.slab_chunks * kMlpChunkX;
+          mbar_wait_guarded<true>(&sp->bar_full[s], (v / g.stages) & 1);
+          tc_fence_after();
+          for (int c = 0; c < nch; ++c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_tf32(tmem + b * kMlpN1, umma_desc(xa + c * kMlpChunkX + k * 32, 16, 1024, 2),
+                        umma_desc(wa + c * kMlpChunkW + k * 32, 16, 1024, 2), idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&sp->bar_empty[s]);
+        }
+        umma_commit(&sp->bar_tfull[b]);
+      }
+    } else if (lane == 0) {
       mbar_wait_guarded<true>(&sp->bar_w, 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -904,14 +953,21 @@ __global__ void __launch_bounds__(kMlpHzThreads, 1)
 mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __grid_constant__ CUtensorMap map_hz,
                        const MlpGeom g, const float* __restrict__ w2, const float* __restrict__ w3, int h1n, int h2n,
                        const float* __restrict__ dscores, long long rows, int ntiles, float* __restrict__ partials,
-                       int partial_len) {
+                       int partial_len, int nslabs, int slab_cols) {
+  // Wide rows: the dW1 accumulator of one CTA holds `slab_cols` feature columns (TMEM columns, shared memory of
+  // one MN-major tile), so CTA b takes column slab b % nslabs of the tiles b / nslabs, b / nslabs + nparts, ...
+  // Neighbouring CTAs walk the same tiles: the activation rows they share come out of L2.  mlp_reduce_kernel
+  // sums a dW1 column over the CTAs of its slab and every other gradient over the CTAs of slab 0.
+  const int slab = blockIdx.x % nslabs, part = blockIdx.x / nslabs, nparts = gridDim.x / nslabs;
+  const int f_off = slab * slab_cols;
+  const int f_cols = g.F - f_off < slab_cols ? g.F - f_off : slab_cols;
   using Hz = MlpHz<H1, H2>;
   static_assert(Hz::kFits, "dZ2 rows must fit behind the dZ1 rows of the 64-row operand");
   constexpr int NHZ = (Hz::P + 31) / 32;            // activation chunks of 32 columns
   constexpr int HZN = 32 * NHZ;                     // accumulator columns they take
   extern __shared__ __align__(1024) unsigned char mlp_smem[];
   unsigned char* base = mlp_smem + ((1024u - (smem_u32(mlp_smem) & 1023u)) & 1023u);
-  const int nk = (g.F + 31) / 32;
+  const int nk = (f_cols + 31) / 32;
   const int xn = 32 * nk;
   unsigned char* a2s = base;                        // [dZ1^T ; dZ2^T], K-major, 128-byte swizzle
   unsigned char* xmn = a2s + kMlpA2Bytes;           // feature tile, MN-major form
@@ -950,7 +1006,7 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sp->tmem_base;
-  const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int my_tiles = part < ntiles ? (ntiles - part + nparts - 1) / nparts : 0;
 
   if (warp == 4) {
     if (lane == 0 && my_tiles > 0) {
@@ -959,17 +1015,17 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
         mbar_wait_guarded<true>(&sp->bar_hze[s], ((it >> 1) & 1) ^ 1u);
         mbar_arrive_expect_tx(&sp->bar_hzf[s], NHZ * kMlpChunkX);
         for (int c = 0; c < NHZ; ++c)
-          tma_load_2d(hzs + (s * NHZ + c) * kMlpChunkX, &map_hz, c * 32, (blockIdx.x + it * gridDim.x) * kMlpTileDocs,
+          tma_load_2d(hzs + (s * NHZ + c) * kMlpChunkX, &map_hz, c * 32, (part + it * nparts) * kMlpTileDocs,
                       &sp->bar_hzf[s]);
       };
       load_hz(0);
       for (int it = 0; it < my_tiles; ++it) {
-        const int row0 = (blockIdx.x + it * gridDim.x) * kMlpTileDocs;
+        const int row0 = (part + it * nparts) * kMlpTileDocs;
         for (int dg = 0; dg < 4; ++dg) {
           mbar_wait_guarded<true>(&sp->bar_mne[dg], (it & 1) ^ 1u);   // MMA2 of tile it - 1 has read these documents
           mbar_arrive_expect_tx(&sp->bar_mnf[dg], nk * 4096);
           for (int c = 0; c < nk; ++c)
-            tma_load_2d(xmn + c * kMlpChunkX + dg * 4096, &map_x_mn, c * 32, row0 + dg * 32, &sp->bar_mnf[dg]);
+            tma_load_2d(xmn + c * kMlpChunkX + dg * 4096, &map_x_mn, f_off + c * 32, row0 + dg * 32, &sp->bar_mnf[dg]);
         }
         if (it + 1 < my_tiles) load_hz(it + 1);
       }
@@ -1039,7 +1095,7 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
       const int b = it & 1;
       const uint32_t buf = tmem + b * kMlpHzBufCols + lane_addr;
       const unsigned char* stage = hzs + b * NHZ * kMlpChunkX;
-      const long long r = static_cast<long long>(blockIdx.x + it * gridDim.x) * kMlpTileDocs + t;
+      const long long r = static_cast<long long>(part + it * nparts) * kMlpTileDocs + t;
       const float ds = r < rows ? dscores[r] : 0.0f;
       mbar_wait_guarded(&sp->bar_hzf[b], (it >> 1) & 1);
       // dZ2 = ds * w3 * [Z2 > 0]
@@ -1143,7 +1199,7 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
           const int c = c0 + k;
           const float val = __uint_as_float(v[k]);
           if (j < h1n) {
-            if (c < g.F) out[static_cast<size_t>(j) * g.F + c] = val;
+            if (c < f_cols && f_off + c < g.F) out[static_cast<size_t>(j) * g.F + f_off + c] = val;
             if (c == xn + Hz::ONE) out[off_b1 + j] = val;
           } else if (j >= Hz::Z0 && j - Hz::Z0 < h2n) {
             if (c >= xn && c - xn < h1n) out[off_w2 + (j - Hz::Z0) * h1n + (c - xn)] = val;
@@ -1159,17 +1215,22 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
 }
 
 // out[k] = sum over the CTAs' partial vectors in a fixed order: four runs of consecutive CTAs per element (one
-// thread each, coalesced 256-byte rows), then ((r0 + r1) + r2) + r3
+// thread each, coalesced 256-byte rows), then ((r0 + r1) + r2) + r3.  With column slabs (nslabs > 1, kept-activation
+// backward of wide rows) partial vector p belongs to slab p % nslabs: dW1 element (j, c) (k < w1_len, c = k % F) is
+// summed over the vectors of slab c / slab_cols, every other element over those of slab 0.
 __global__ void __launch_bounds__(256)
-mlp_reduce_kernel(const float* __restrict__ partials, int nparts, int len, float* __restrict__ out) {
+mlp_reduce_kernel(const float* __restrict__ partials, int nparts, int len, float* __restrict__ out, int nslabs,
+                  int slab_cols, int F, int w1_len) {
   __shared__ float run[4][64];
   const int kl = threadIdx.x & 63, sub = threadIdx.x >> 6;
   const int k = blockIdx.x * 64 + kl;
   const int per = (nparts + 3) / 4;
   const int p0 = sub * per, p1 = p0 + per < nparts ? p0 + per : nparts;
   float s = 0.0f;
-  if (k < len)
-    for (int p = p0; p < p1; ++p) s += partials[static_cast<size_t>(p) * len + k];
+  if (k < len) {
+    const int slab = (nslabs > 1 && k < w1_len) ? (k % F) / slab_cols : 0;
+    for (int p = p0; p < p1; ++p) s += partials[static_cast<size_t>(p * nslabs + slab) * len + k];
+  }
   run[sub][kl] = s;
   __syncthreads();
   if (sub == 0 && k < len) out[k] = ((run[0][kl] + run[1][kl]) + run[2][kl]) + run[3][kl];

@@ -184,8 +184,10 @@ class _MlpScores(torch.autograd.Function):
         rows = x2.shape[0]
         # TMA needs feature rows of a multiple of 16 bytes: other widths (MQ2007's 46, Yahoo's 699) get zero
         # columns appended -- one extra copy of the features per call; a dataset kept on the device can be
-        # stored padded once instead (zero features times zero weight columns change nothing)
-        Fp = (F + 3) // 4 * 4
+        # stored padded once instead (zero features times zero weight columns change nothing).  When a copy is
+        # made anyway it goes to a multiple of 8 floats: rows that start on 32-byte sectors stream ~20 % faster
+        # (700 -> 704 features: 5.3 -> 6.4 TB/s, tools/mlp_width_sweep.py)
+        Fp = F if F % 4 == 0 else (F + 7) // 8 * 8
         if Fp != F:
             x2 = torch.nn.functional.pad(x2, (0, Fp - F))
 

@@ -138,11 +138,15 @@ def _split(out, F, H1, H2):
 
 SHAPES = [(128, 136, 50, 10), (1000, 136, 50, 10), (40000, 136, 50, 10), (5000, 128, 50, 10), (5000, 32, 50, 10),
           (3000, 24, 50, 10), (700, 8, 50, 10), (5000, 48, 64, 16), (5000, 100, 20, 5), (9000, 64, 32, 8), (1, 136, 50, 10)]
-KEPT_SHAPES = [s_ for s_ in SHAPES if (s_[2], s_[3]) in ((50, 10), (32, 8), (20, 5))] + [(3000, 220, 50, 10)]
+# rows wider than 288 features: W1 streams through the stage ring beside the tile (forward), the dW1 columns come
+# from several launches (backward from kept activations)
+WIDE_SHAPES = [(3000, 700, 50, 10), (1000, 320, 50, 10), (2100, 1024, 20, 5), (700, 292, 32, 8)]
+KEPT_SHAPES = ([s_ for s_ in SHAPES if (s_[2], s_[3]) in ((50, 10), (32, 8), (20, 5))] + [(3000, 220, 50, 10)]
+               + WIDE_SHAPES)
 
 
 @gpu
-@pytest.mark.parametrize("rows,F,H1,H2", SHAPES + [(5000, 220, 20, 5)])
+@pytest.mark.parametrize("rows,F,H1,H2", SHAPES + [(5000, 220, 20, 5)] + WIDE_SHAPES)
 def test_mlp_scores_vs_oracle(rows, F, H1, H2):
     lib = _lib.lib()
     p = _params(F, H1, H2, 3, "cuda")
@@ -300,8 +304,18 @@ def test_mlp_unsupported_shapes_return_code():
     assert _call_scores(lib, x, p)[0] == -2                  # F % 4 != 0
     p = _params(32, 70, 10, 0, "cuda")
     assert _call_scores(lib, torch.randn(10, 32, device="cuda"), p)[0] == -2     # H1 > 64
+    # the recomputing backward keeps W1 and a whole tile in shared memory: rows beyond that need kept activations
     p = _params(700, 50, 10, 0, "cuda")
-    assert _call_scores(lib, torch.randn(10, 700, device="cuda"), p)[0] == -2    # a tile does not fit shared memory
+    x = torch.randn(10, 700, device="cuda")
+    n = lib.ltr_mlp_grad_len(700, 50, 10)
+    out = torch.empty(n, device="cuda")
+    wsb = lib.ltr_mlp_workspace_bytes(700, 50, 10)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    ds = torch.randn(10, device="cuda")
+    rc = lib.ltr_mlp_backward(x.data_ptr(), 10, 700, p[0].data_ptr(), p[1].data_ptr(), 50, p[2].data_ptr(),
+                              p[3].data_ptr(), 10, p[4].data_ptr(), p[5].data_ptr(), None, ds.data_ptr(),
+                              out.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+    assert rc == -2
 
 
 @gpu
@@ -344,8 +358,8 @@ def test_mlp_ranker_matches_unfused_modules(loss_name):
 @gpu
 @pytest.mark.parametrize("F", [46, 220, 699])
 def test_mlp_ranker_other_feature_widths(F):
-    """MQ2007 (46: padded to 48 on the fly), Istella (220: kernels as they are), Yahoo (699: beyond a shared-memory
-    tile, runs on torch's layers with a warning) -- the module works for all of them."""
+    """MQ2007 (46: padded to 48 on the fly), Istella (220: kernels as they are), Yahoo (699: padded to 700, W1
+    streamed beside the tile, dW1 in four column slabs) -- all on the library's kernels, no fallback warning."""
     import warnings
     from pytorchltr_b200.fused import MLPRanker
     torch.manual_seed(2)
@@ -363,7 +377,7 @@ def test_mlp_ranker_other_feature_widths(F):
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
+            warnings.simplefilter("error")
             s_f = fused(xs)
         s_p = plain(xs)
         s_f.backward(g)
