@@ -201,10 +201,10 @@ int ltr_linear_listnet_backward(const float *qgrad, const float *g, int g_stride
  * (F % 8 == 0) stream about 20 % faster than F % 8 == 4.
  * hz_out (NULL to skip; what a training step passes): [rows * ltr_mlp_hz_pitch(H1, H2)] floats, the activations
  * ltr_mlp_backward can start from instead of recomputing layer 1 -- per document relu(W1 x + b1) in columns
- * [0, H1), the layer-2 pre-activation in [Z0, Z0 + H2) with Z0 = roundup4(H1) of the kernel instantiation (52 /
- * 10 at 50-10; 32 / 8 for H1 <= 32, H2 <= 8), 1.0 in the column after them (its products are db1 / db2), zeros
- * elsewhere (256 B at 50-10, written with 128-bit stores next to the 544 B of features read).
- * ltr_mlp_hz_pitch is 0 for shapes without this path (H1 = 50, H2 = 10 and H1 <= 32, H2 <= 8 have it).
+ * [0, H1), the layer-2 pre-activation in [Z0, Z0 + H2), 1.0 in column ONE (its products are db1 / db2), zeros
+ * elsewhere; (Z0, ONE, pitch) = (32, 40, 44) for H1 <= 32, H2 <= 8 and (52, 62, 64) for other H1 <= 50, H2 <= 10
+ * (256 B per document, written with 128-bit stores next to the 544 B of features read).  ltr_mlp_hz_pitch is 0
+ * for larger hidden layers: they have no such path.
  */
 int ltr_mlp_hz_pitch(int H1, int H2);
 int ltr_mlp_scores(const float *features, long long rows, int F, const float *w1, const float *b1,

@@ -133,8 +133,9 @@ static int launch_mlp_scores(const MlpMaps& m, const MlpGeom& g, const float* b1
 }
 
 static int mlp_hz_pitch(int H1, int H2) {
-  if (H1 == 50 && H2 == 10) return MlpHz<50, 10>::P;
-  if (H1 >= 1 && H2 >= 1 && H1 <= 32 && H2 <= 8) return MlpHz<32, 8>::P;
+  if (H1 < 1 || H2 < 1) return 0;
+  if (H1 <= 32 && H2 <= 8) return MlpHz<32, 8>::P;
+  if (H1 <= 50 && H2 <= 10) return MlpHz<50, 10>::P;
   return 0;
 }
 
@@ -227,10 +228,11 @@ int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (hz_out && (ltr_mlp_hz_pitch(H1, H2) == 0 || !aligned16(hz_out))) return LTR_EINVAL;
-  if (H1 == 50 && H2 == 10)
-    return launch_mlp_scores<50, 10>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, hz_out, st, di);
+  // the smallest instantiation that holds the model (hidden units beyond H1 / H2 are zero weights)
   if (H1 <= 32 && H2 <= 8)
     return launch_mlp_scores<32, 8>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, hz_out, st, di);
+  if (H1 <= 50 && H2 <= 10)
+    return launch_mlp_scores<50, 10>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, hz_out, st, di);
   return launch_mlp_scores<64, 16>(m, g, b1, w2, b2, w3, b3, H1, H2, rows, scores_out, nullptr, st, di);
 }
 
@@ -263,7 +265,7 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
     // the forward pass kept [H1 | Z2]: every byte once, no layer 1 again
     if (ltr_mlp_hz_pitch(H1, H2) == 0 || !aligned16(hz)) return LTR_EINVAL;
     int nparts = 0, nslabs = 1, slab_cols = 0;
-    rc = H1 == 50 ? launch_mlp_backward_hz<50, 10>(features, hz, rows, F, w2, w3, H1, H2, dscores,
+    rc = (H1 > 32 || H2 > 8) ? launch_mlp_backward_hz<50, 10>(features, hz, rows, F, w2, w3, H1, H2, dscores,
                                                    static_cast<float*>(workspace), len, &nparts, &nslabs, &slab_cols,
                                                    st, di)
                   : launch_mlp_backward_hz<32, 8>(features, hz, rows, F, w2, w3, H1, H2, dscores,
@@ -302,8 +304,8 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
                                                                   b2, w3, b3, H1, H2, dscores, rows, ntiles,       \
                                                                   tmem_cols, partials, len, mlp_trace_buffer());   \
   } while (0)
-  if (H1 == 50 && H2 == 10) LTR_MLP_BWD(50, 10);
-  else if (H1 <= 32 && H2 <= 8) LTR_MLP_BWD(32, 8);
+  if (H1 <= 32 && H2 <= 8) LTR_MLP_BWD(32, 8);
+  else if (H1 <= 50 && H2 <= 10) LTR_MLP_BWD(50, 10);
   else LTR_MLP_BWD(64, 16);
 #undef LTR_MLP_BWD
   LTR_CUDA(cudaGetLastError());
