@@ -180,6 +180,15 @@ def main():
         run_bwd(lib, *args, ds, hz=hz)                # backward from the kept activations (+ reduce)
         run_bwd(lib, *args, ds)                       # backward recomputing layer 1 (+ reduce)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "prof_wide":        # Yahoo's width (699 -> 700), 383k documents
+        rows = 2995 * 128
+        args = make(rows, 700, 50, 10, exact=False)
+        ds = torch.randn(rows, device="cuda")
+        hz = make_hz(lib, args[0], args[1], args[3])
+        run_fwd(lib, *args)
+        run_fwd(lib, *args, hz=hz)
+        run_bwd(lib, *args, ds, hz=hz)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "bwd":
         print("PROBE", "OK" if bwd_checks(lib) else "FAIL")
         return
