@@ -311,6 +311,26 @@ int ltr_p2p_error(ltr_p2p *p);
 void ltr_p2p_destroy(ltr_p2p *p);
 
 /*
+ * Vector form of the exchange, for the one other exchange step next to the path: the parameter gradient of a
+ * data-parallel ranker (SURVEY.md 8(f) N1 with 8(e)'s query sharding; the reference has no distributed code --
+ * this is the all-reduce torch's DistributedDataParallel would issue through NCCL).  Same mailbox, same
+ * protocol, any grid: values[0..k) (device) is replaced by the sum over the ranks, 65536 floats per launch.
+ * ltr_mlp_backward_allreduce is ltr_mlp_backward with that exchange FUSED into its final reduction: the thread
+ * that sums element k over the CTAs' partial vectors pushes the sum into every peer's mailbox over NVLink and
+ * adds what the peers pushed, in rank order -- grads_out leaves the launch already summed over the ranks,
+ * bit-identical on every rank, one launch fewer than reduce + all-reduce and no library collective (gradients
+ * longer than 65536 floats take the unfused vector exchange after the reduction).  Every rank must make the
+ * call with the same model shape (a rank with rows == 0 contributes zeros).  With the loss already divided by
+ * the global query count (sharded_mean_loss), the SUM over ranks is the gradient of the global mean.
+ */
+int ltr_p2p_allreduce_vec(ltr_p2p *p, float *values, long long k, void *stream);
+int ltr_mlp_backward_allreduce(const float *features, long long rows, int F, const float *w1,
+                               const float *b1, int H1, const float *w2, const float *b2, int H2,
+                               const float *w3, const float *b3, const float *hz,
+                               const float *dscores, float *grads_out, void *workspace,
+                               size_t workspace_bytes, ltr_p2p *p2p, void *stream);
+
+/*
  * Host-buffer form of the three loss families (the call the reference's CPU path is
  * compared with end to end): copies scores / relevance / n from host memory into `workspace`,
  * runs the fused loss + gradient kernel and copies loss_out [B] and dscores_out [B*L] (if not

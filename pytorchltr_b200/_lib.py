@@ -20,6 +20,7 @@ SYMBOLS = (
     "ltr_linear_listnet_workspace_bytes", "ltr_linear_listnet", "ltr_linear_listnet_backward", "ltr_collate",
     "ltr_pbm_probabilities", "ltr_loss_host_ex", "ltr_scale_rows_host", "ltr_collate_sampled", "ltr_collate_sparse",
     "ltr_p2p_create", "ltr_p2p_connect", "ltr_p2p_allreduce_sum", "ltr_p2p_error", "ltr_p2p_destroy",
+    "ltr_p2p_allreduce_vec", "ltr_mlp_backward_allreduce",
     "ltr_mlp_scores", "ltr_mlp_hz_pitch", "ltr_mlp_grad_len", "ltr_mlp_workspace_bytes", "ltr_mlp_backward",
 )
 
@@ -95,6 +96,8 @@ def _declare(lib):
     lib.ltr_p2p_connect.argtypes = [c_void_p, c_void_p]
     lib.ltr_p2p_allreduce_sum.restype = c_int
     lib.ltr_p2p_allreduce_sum.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    lib.ltr_p2p_allreduce_vec.restype = c_int
+    lib.ltr_p2p_allreduce_vec.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]
     lib.ltr_p2p_error.restype = c_int
     lib.ltr_p2p_error.argtypes = [c_void_p]
     lib.ltr_p2p_destroy.restype = None
@@ -112,6 +115,10 @@ def _declare(lib):
     lib.ltr_mlp_backward.argtypes = [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p]
+    lib.ltr_mlp_backward_allreduce.restype = c_int
+    lib.ltr_mlp_backward_allreduce.argtypes = [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_size_t, c_void_p, c_void_p]
     lib.ltr_collate_sampled.restype = c_int
     lib.ltr_collate_sampled.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

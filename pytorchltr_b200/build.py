@@ -20,7 +20,7 @@ SOURCES = ["ltr_kernels.cu", "ltr_mlp.cu"]
 # headers a source does NOT include (so editing them does not recompile it)
 NOT_INCLUDED = {"ltr_kernels.cu": {"ltr_mlp_scorer.cuh"},
                 "ltr_mlp.cu": {f for f in os.listdir(CSRC) if f.endswith(".cuh")} -
-                              {"ltr_mlp_scorer.cuh", "ltr_common.cuh", "ltr_host.cuh"}}
+                              {"ltr_mlp_scorer.cuh", "ltr_common.cuh", "ltr_host.cuh", "ltr_p2p.cuh"}}
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -26,6 +26,7 @@
 #include "ltr_pair_cta.cuh"
 #include "ltr_pair_ring.cuh"
 #include "ltr_pair_warp.cuh"
+#include "ltr_p2p.cuh"
 #include "ltr_sm100.h"
 
 namespace ltr {
@@ -1561,27 +1562,10 @@ int ltr_linear_listnet_backward(const float* qgrad, const float* g, int g_stride
   return LTR_OK;
 }
 
-// ---- scalar all-reduce over NVLink peer memory ----------------------------------------------------------
-// The path's only exchange is the [sum of losses (, count)] behind a global mean: a few floats per step,
-// pure latency.  Instead of a library collective (~20 us inside a step of ~450 us at 8 GPUs) every rank
-// owns a small mailbox in device memory, exported to the other ranks of the node by CUDA IPC; one tiny
-// kernel per step writes the rank's values straight into every peer's mailbox over NVLink (64-bit stores
-// carrying {value, sequence number}: data and flag arrive together, as in NCCL's LL protocol), waits until
-// its own mailbox holds the current sequence number from every rank, and sums the values in rank order
-// (deterministic).  The sequence number lives on the device and is advanced by the kernel itself, so the
-// launch can be captured in a CUDA graph and replayed; two slot sets alternate, because a rank can run at
-// most one exchange ahead of the slowest one.  A rank that never shows up trips a ~2 s timeout and raises
-// the mailbox's error flag instead of hanging the GPU.
-constexpr int kP2PMaxRanks = 16;
-constexpr int kP2PMaxValues = 4;
-
-struct P2PMailbox {
-  unsigned long long slot[2][kP2PMaxRanks][kP2PMaxValues];   // {sequence << 32 | float bits}
-  P2PMailbox* peers[kP2PMaxRanks];                            // this rank's view of every rank's mailbox
-  unsigned int seq;
-  unsigned int error;
-};
-
+// ---- all-reduce over NVLink peer memory (ltr_p2p.cuh) ---------------------------------------------------
+// The loss path's only exchange is the [sum of losses (, count)] behind a global mean: a few floats per step,
+// pure latency -- one single-CTA kernel instead of a library collective (~20 us inside a step of ~450 us at
+// 8 GPUs).  The vector form carries the parameter gradient of a data-parallel ranker (ltr_mlp.cu).
 __global__ void __launch_bounds__(kP2PMaxRanks * kP2PMaxValues)
 p2p_allreduce_kernel(float* __restrict__ values, int k, int rank, int world, P2PMailbox* __restrict__ mine) {
   __shared__ unsigned int seq_s;
@@ -1604,7 +1588,7 @@ p2p_allreduce_kernel(float* __restrict__ values, int k, int rank, int world, P2P
     unsigned long long w = *src;
     const long long t0 = clock64();
     while (static_cast<unsigned int>(w >> 32) != seq) {
-      if (clock64() - t0 > 4000000000LL) { mine->error = 1u; break; }
+      if (clock64() - t0 > kP2PTimeoutCycles) { mine->error = 1u; break; }
       w = *src;
     }
     recv[peer][j] = __uint_as_float(static_cast<unsigned int>(w & 0xffffffffull));
@@ -1617,11 +1601,14 @@ p2p_allreduce_kernel(float* __restrict__ values, int k, int rank, int world, P2P
   }
 }
 
-struct ltr_p2p {
-  int rank = 0, world = 1, device = 0;
-  P2PMailbox* mine = nullptr;
-  void* opened[kP2PMaxRanks] = {};
-};
+// values[0..k) (any k, pieces of kP2PVecCapacity per launch): replaced by the sum over the ranks
+__global__ void __launch_bounds__(256)
+p2p_allreduce_vec_kernel(float* __restrict__ values, int k, int rank, int world, P2PMailbox* __restrict__ mine) {
+  const unsigned int seq = p2p_vec_begin(mine);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x)
+    values[j] = p2p_vec_element(mine, rank, world, seq, j, values[j]);
+  p2p_vec_finish(mine, seq);
+}
 
 int ltr_p2p_create(int rank, int world, ltr_p2p** out, unsigned char* handle_out) {
   if (!out || !handle_out || world < 1 || world > kP2PMaxRanks || rank < 0 || rank >= world) return LTR_EINVAL;
@@ -1631,8 +1618,8 @@ int ltr_p2p_create(int rank, int world, ltr_p2p** out, unsigned char* handle_out
   p->rank = rank;
   p->world = world;
   cudaError_t e = cudaGetDevice(&p->device);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->mine), sizeof(P2PMailbox));
-  if (e == cudaSuccess) e = cudaMemset(p->mine, 0, sizeof(P2PMailbox));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->mine), p2p_mailbox_bytes(world));
+  if (e == cudaSuccess) e = cudaMemset(p->mine, 0, p2p_mailbox_bytes(world));
   cudaIpcMemHandle_t h;
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->mine);
   if (e != cudaSuccess) {
@@ -1662,6 +1649,8 @@ int ltr_p2p_connect(ltr_p2p* p, const unsigned char* handles) {
     table[r] = static_cast<P2PMailbox*>(ptr);
   }
   LTR_CUDA(cudaMemcpy(p->mine->peers, table, sizeof(table), cudaMemcpyHostToDevice));
+  const unsigned int w = static_cast<unsigned int>(p->world);
+  LTR_CUDA(cudaMemcpy(&p->mine->world, &w, sizeof(w), cudaMemcpyHostToDevice));
   return LTR_OK;
 }
 
@@ -1672,6 +1661,20 @@ int ltr_p2p_allreduce_sum(ltr_p2p* p, float* values, int k, void* stream) {
   p2p_allreduce_kernel<<<1, kP2PMaxRanks * kP2PMaxValues, 0, static_cast<cudaStream_t>(stream)>>>(
       values, k, p->rank, p->world, p->mine);
   LTR_CUDA(cudaGetLastError());
+  return LTR_OK;
+}
+
+// values [k] (device, any k >= 1): replaced by the sum over all ranks, kP2PVecCapacity floats per launch.
+// Every rank must call it with the same k.  Enqueued on `stream`; CUDA-graph capturable.
+int ltr_p2p_allreduce_vec(ltr_p2p* p, float* values, long long k, void* stream) {
+  if (!p || !values || k < 1) return LTR_EINVAL;
+  for (long long off = 0; off < k; off += kP2PVecCapacity) {
+    const int piece = static_cast<int>(k - off < kP2PVecCapacity ? k - off : kP2PVecCapacity);
+    const int grid = (piece + 255) / 256 < 64 ? (piece + 255) / 256 : 64;
+    p2p_allreduce_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(values + off, piece, p->rank,
+                                                                                 p->world, p->mine);
+    LTR_CUDA(cudaGetLastError());
+  }
   return LTR_OK;
 }
 

@@ -245,9 +245,13 @@ size_t ltr_mlp_workspace_bytes(int F, int H1, int H2) {
   return ltr_mlp_grad_len(F, H1, H2) * kMlpMaxCtas * sizeof(float);
 }
 
-int ltr_mlp_backward(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
-                     const float* w2, const float* b2, int H2, const float* w3, const float* b3, const float* hz,
-                     const float* dscores, float* grads_out, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+// p2p (or NULL): the ranks' gradients are summed over NVLink peer memory inside the final reduction
+static int mlp_backward_impl(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
+                             const float* w2, const float* b2, int H2, const float* w3, const float* b3,
+                             const float* hz, const float* dscores, float* grads_out, void* workspace,
+                             size_t workspace_bytes, void* stream, ltr_p2p* p2p) {
   int rc = mlp_check(features, rows, F, w1, H1, w2, H2, w3);
   if (rc != LTR_OK) return rc;
   if (!grads_out || !workspace || (rows > 0 && !dscores)) return LTR_EINVAL;
@@ -257,9 +261,17 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
   if (rc != LTR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int len = static_cast<int>(ltr_mlp_grad_len(F, H1, H2));
+  // the exchange rides in the reduction when the vector fits one mailbox piece, else it follows it
+  const bool fused_x = p2p && len <= kP2PVecCapacity;
+  P2PMailbox* box = fused_x ? p2p->mine : nullptr;
+  const int xrank = p2p ? p2p->rank : 0, xworld = p2p ? p2p->world : 1;
+  auto after = [&]() -> int {
+    return (p2p && !fused_x) ? ltr_p2p_allreduce_vec(p2p, grads_out, len, stream) : LTR_OK;
+  };
   if (rows == 0) {
+    // a rank without documents still takes part in the exchange
     LTR_CUDA(cudaMemsetAsync(grads_out, 0, sizeof(float) * len, st));
-    return LTR_OK;
+    return p2p ? ltr_p2p_allreduce_vec(p2p, grads_out, len, stream) : LTR_OK;
   }
   if (hz) {
     // the forward pass kept [H1 | Z2]: every byte once, no layer 1 again
@@ -273,9 +285,9 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
                                                   st, di);
     if (rc != LTR_OK) return rc;
     mlp_reduce_kernel<<<(len + 63) / 64, 256, 0, st>>>(static_cast<float*>(workspace), nparts, len, grads_out, nslabs,
-                                                       slab_cols, F, H1 * F);
+                                                       slab_cols, F, H1 * F, box, xrank, xworld);
     LTR_CUDA(cudaGetLastError());
-    return LTR_OK;
+    return after();
   }
   MlpGeom g = mlp_geometry(F, 1);
   const int mn_chunks = (F + 31) / 32;
@@ -310,9 +322,27 @@ int ltr_mlp_backward(const float* features, long long rows, int F, const float* 
 #undef LTR_MLP_BWD
   LTR_CUDA(cudaGetLastError());
   const int rgrid = (len + 63) / 64;
-  mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out, 1, F, F, H1 * F);
+  mlp_reduce_kernel<<<rgrid, 256, 0, st>>>(partials, grid, len, grads_out, 1, F, F, H1 * F, box, xrank, xworld);
   LTR_CUDA(cudaGetLastError());
-  return LTR_OK;
+  return after();
+}
+
+extern "C" {
+
+int ltr_mlp_backward(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
+                     const float* w2, const float* b2, int H2, const float* w3, const float* b3, const float* hz,
+                     const float* dscores, float* grads_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return mlp_backward_impl(features, rows, F, w1, b1, H1, w2, b2, H2, w3, b3, hz, dscores, grads_out, workspace,
+                           workspace_bytes, stream, nullptr);
+}
+
+int ltr_mlp_backward_allreduce(const float* features, long long rows, int F, const float* w1, const float* b1, int H1,
+                               const float* w2, const float* b2, int H2, const float* w3, const float* b3,
+                               const float* hz, const float* dscores, float* grads_out, void* workspace,
+                               size_t workspace_bytes, ltr_p2p* p2p, void* stream) {
+  if (!p2p) return LTR_EINVAL;
+  return mlp_backward_impl(features, rows, F, w1, b1, H1, w2, b2, H2, w3, b3, hz, dscores, grads_out, workspace,
+                           workspace_bytes, stream, p2p);
 }
 
 // debugging aid, not part of the public header: copies the trace of the last traced backward launch

@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include "ltr_common.cuh"
+#include "ltr_p2p.cuh"
 
 namespace ltr {
 
@@ -1218,14 +1219,19 @@ mlp_backward_hz_kernel(const __grid_constant__ CUtensorMap map_x_mn, const __gri
 // thread each, coalesced 256-byte rows), then ((r0 + r1) + r2) + r3.  With column slabs (nslabs > 1, kept-activation
 // backward of wide rows) partial vector p belongs to slab p % nslabs: dW1 element (j, c) (k < w1_len, c = k % F) is
 // summed over the vectors of slab c / slab_cols, every other element over those of slab 0.
+// With a mailbox (`mine`, ltr_p2p.cuh; len <= kP2PVecCapacity) the sum leaves the kernel already all-reduced over
+// the ranks of the node: the thread that owns element k pushes its value into every peer's mailbox over NVLink and
+// adds up what the peers pushed for k, in rank order -- the data-parallel gradient exchange fused into the
+// reduction that produces the gradient (one launch, no library collective, bit-identical on every rank).
 __global__ void __launch_bounds__(256)
 mlp_reduce_kernel(const float* __restrict__ partials, int nparts, int len, float* __restrict__ out, int nslabs,
-                  int slab_cols, int F, int w1_len) {
+                  int slab_cols, int F, int w1_len, P2PMailbox* __restrict__ mine, int rank, int world) {
   __shared__ float run[4][64];
   const int kl = threadIdx.x & 63, sub = threadIdx.x >> 6;
   const int k = blockIdx.x * 64 + kl;
   const int per = (nparts + 3) / 4;
   const int p0 = sub * per, p1 = p0 + per < nparts ? p0 + per : nparts;
+  const unsigned int seq = mine ? p2p_vec_begin(mine) : 0u;
   float s = 0.0f;
   if (k < len) {
     const int slab = (nslabs > 1 && k < w1_len) ? (k % F) / slab_cols : 0;
@@ -1233,7 +1239,12 @@ mlp_reduce_kernel(const float* __restrict__ partials, int nparts, int len, float
   }
   run[sub][kl] = s;
   __syncthreads();
-  if (sub == 0 && k < len) out[k] = ((run[0][kl] + run[1][kl]) + run[2][kl]) + run[3][kl];
+  if (sub == 0 && k < len) {
+    float v = ((run[0][kl] + run[1][kl]) + run[2][kl]) + run[3][kl];
+    if (mine) v = p2p_vec_element(mine, rank, world, seq, k, v);
+    out[k] = v;
+  }
+  if (mine) p2p_vec_finish(mine, seq);
 }
 
 }  // namespace ltr

@@ -102,6 +102,21 @@ class PeerScalarExchange:
                                                         torch.cuda.current_stream(values.device).cuda_stream))
         return values
 
+    def all_reduce_vec_(self, values: torch.Tensor) -> torch.Tensor:
+        """In place: ``values`` (float32 CUDA, contiguous, any length) becomes the sum over all ranks
+        (``ltr_p2p_allreduce_vec``: 65536 floats per launch, the same mailbox protocol)."""
+        if not (values.is_cuda and values.dtype == torch.float32 and values.is_contiguous() and values.numel() >= 1):
+            raise ValueError("values must be a non-empty contiguous float32 CUDA tensor")
+        with torch.cuda.device(values.device):
+            self._check(self._lib.ltr_p2p_allreduce_vec(self._handle, values.data_ptr(), values.numel(),
+                                                        torch.cuda.current_stream(values.device).cuda_stream))
+        return values
+
+    @property
+    def handle(self):
+        """The ``ltr_p2p *`` of this exchange (for entry points that fuse it: ``ltr_mlp_backward_allreduce``)."""
+        return self._handle
+
     def timed_out(self) -> bool:
         """True if an exchange gave up waiting for a peer (synchronises the device)."""
         return self._lib.ltr_p2p_error(self._handle) == 1
@@ -110,6 +125,9 @@ class PeerScalarExchange:
         if self._handle:
             self._lib.ltr_p2p_destroy(self._handle)
             self._handle = None
+
+
+PeerExchange = PeerScalarExchange      # scalars (loss sums) and vectors (parameter gradients) share one mailbox
 
 
 class _MeanOfShards(torch.autograd.Function):

@@ -165,10 +165,13 @@ class _MlpScores(torch.autograd.Function):
     """scores = l3(relu(l2(relu(l1(x))))) over the flat (rows, F) feature block: ``ltr_mlp_scores`` forward
     (features read once, layer 1 on tcgen05 with TF32 operands), ``ltr_mlp_backward`` for the parameter
     gradients (second pass over the features, dW1 on tcgen05).  Differentiable with respect to the six
-    parameters, not the features."""
+    parameters, not the features.  With an ``exchange`` (``distributed.PeerExchange``) the gradients come back
+    summed over the ranks of the node (``ltr_mlp_backward_allreduce``: the exchange runs inside the final
+    reduction of the backward pass, over NVLink peer memory)."""
 
     @staticmethod
-    def forward(ctx, features, w1, b1, w2, b2, w3, b3):
+    def forward(ctx, features, w1, b1, w2, b2, w3, b3, exchange=None):
+        ctx.exchange = exchange
         if ctx.needs_input_grad[0]:
             raise NotImplementedError(
                 "MLPRanker is differentiable with respect to its parameters only; `features` requires grad "
@@ -248,14 +251,19 @@ class _MlpScores(torch.autograd.Function):
         grads = torch.empty(n, dtype=torch.float32, device=dev)
         ws_bytes = lib.ltr_mlp_workspace_bytes(F, H1, H2)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ex = ctx.exchange
+
+        def call(hz_ptr):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            head = (x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5], hz_ptr,
+                    ds.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws_bytes)
+            if ex is None:
+                return lib.ltr_mlp_backward(*head, st)
+            return lib.ltr_mlp_backward_allreduce(*head, ex.handle, st)      # an unsupported shape exchanges nothing
         with torch.cuda.device(dev):
-            rc = lib.ltr_mlp_backward(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5],
-                                      None if hz is None else hz.data_ptr(), ds.data_ptr(), grads.data_ptr(),
-                                      ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
-            if rc == _LTR_EUNSUPPORTED and hz is not None:      # F beyond the kept-activation kernel: recompute
-                rc = lib.ltr_mlp_backward(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4],
-                                          ptr[5], None, ds.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws_bytes,
-                                          torch.cuda.current_stream(dev).cuda_stream)
+            rc = call(None if hz is None else hz.data_ptr())
+            if rc == _LTR_EUNSUPPORTED and hz is not None:      # no kept-activation kernel for this shape: recompute
+                rc = call(None)
         if rc == _LTR_EUNSUPPORTED:
             _warn_fallback(f"features={F}, hidden=({H1}, {H2}) is outside the backward kernel's limits")
             _, h1, h2 = _mlp_torch_forward(x2, *p)
@@ -263,6 +271,10 @@ class _MlpScores(torch.autograd.Function):
             dz2 = d * p[4].reshape(1, -1) * (h2 > 0)
             dz1 = (dz2 @ p[2]) * (h1 > 0)
             out = [dz1.t() @ x2, dz1.sum(0), dz2.t() @ h1, dz2.sum(0), (d * h2).sum(0).reshape(1, -1), d.sum().reshape(1)]
+            if ex is not None:
+                flat = torch.cat([t.reshape(-1) for t in out]).contiguous()
+                ex.all_reduce_vec_(flat)
+                out = [c.reshape(t.shape) for c, t in zip(flat.split([t.numel() for t in out]), out)]
         else:
             _lib.check(rc)
             o = [0, H1 * F, H1 * F + H1, H1 * F + H1 + H2 * H1, H1 * F + H1 + H2 * H1 + H2,
@@ -273,13 +285,15 @@ class _MlpScores(torch.autograd.Function):
         res = [None]
         for k in range(6):
             res.append(out[k].reshape(ctx.param_shapes[k]) if ctx.has[k] else None)
+        res.append(None)
         return tuple(res)
 
 
-def mlp_scores(features, w1, b1, w2, b2, w3, b3):
+def mlp_scores(features, w1, b1, w2, b2, w3, b3, exchange=None):
     """``(..., F) -> (..., 1)`` scores of the ReLU MLP with torch.nn.Linear-shaped parameters
-    ``w1 (H1, F), b1 (H1,), w2 (H2, H1), b2 (H2,), w3 (1, H2), b3 (1,)`` (biases may be None)."""
-    return _MlpScores.apply(features, w1, b1, w2, b2, w3, b3)
+    ``w1 (H1, F), b1 (H1,), w2 (H2, H1), b2 (H2,), w3 (1, H2), b3 (1,)`` (biases may be None).
+    ``exchange``: a ``distributed.PeerExchange``; the parameter gradients are then summed over its ranks."""
+    return _MlpScores.apply(features, w1, b1, w2, b2, w3, b3, exchange)
 
 
 class MLPRanker(torch.nn.Module):
@@ -291,14 +305,23 @@ class MLPRanker(torch.nn.Module):
     tcgen05 kernels: ``forward(xs: (B, L, F)) -> (B, L, 1)``, to be fed to any loss or metric of this package
     exactly as ``loss_fn(model(xs), ys, n)`` in the reference's training loop (``:83-138``).
     Layer 1 multiplies TF32 operands (what torch does under ``torch.backends.cuda.matmul.allow_tf32``).
+
+    Data-parallel training over the GPUs of one node (one process per GPU, each on its shard of the queries): pass
+    ``exchange=distributed.PeerExchange()``; every rank's ``backward`` then returns the parameter gradients SUMMED
+    over the ranks (the all-reduce DistributedDataParallel would issue, fused into the backward pass's final
+    reduction over NVLink peer memory).  With ``distributed.sharded_mean_loss`` -- the loss divided by the global
+    query count -- that sum is the gradient of the global mean, identical bits on every rank, so the replicas'
+    optimizers stay in step without a wrapper.
     """
 
-    def __init__(self, in_features: int, hidden=(50, 10)):
+    def __init__(self, in_features: int, hidden=(50, 10), exchange=None):
         super().__init__()
         h1, h2 = hidden
+        self.exchange = exchange
         self.l1 = torch.nn.Linear(in_features, h1)
         self.l2 = torch.nn.Linear(h1, h2)
         self.l3 = torch.nn.Linear(h2, 1)
 
     def forward(self, x):
-        return mlp_scores(x, self.l1.weight, self.l1.bias, self.l2.weight, self.l2.bias, self.l3.weight, self.l3.bias)
+        return mlp_scores(x, self.l1.weight, self.l1.bias, self.l2.weight, self.l2.bias, self.l3.weight, self.l3.bias,
+                          self.exchange)

@@ -302,11 +302,66 @@ def _nccl_worker_body(rank, world, port, B, L, out_dir):
     for _ in range(5):
         graph3.replay()
     torch.cuda.synchronize()
+    # vector form: the same sums as NCCL at lengths around the mailbox capacity (65536), many in a row
+    vec_ok = True
+    for it, k in enumerate((1, 1000, 65536, 65537, 200003, 7371, 7371, 7371)):
+        g = torch.Generator(device=dev).manual_seed(100 * rank + it)
+        v = torch.randn(k, device=dev, generator=g)
+        ref = v.clone()
+        dist.all_reduce(ref)
+        ex.all_reduce_vec_(v)
+        vec_ok = vec_ok and bool(torch.equal(v, ref))             # two ranks: a + b in either order
+    # data-parallel MLP ranker: every rank scores its shard; backward returns the gradient summed over the ranks
+    # (exchange fused into the final reduction), equal to local gradient + NCCL all-reduce; eager and captured
+    from pytorchltr_b200.fused import MLPRanker
+    import pytorchltr_b200.loss as Lmod
+    torch.manual_seed(7)                                  # the same initial model on every rank
+    Fm = 136
+    local = MLPRanker(Fm).to(dev)
+    shared = MLPRanker(Fm, exchange=ex).to(dev)
+    shared.load_state_dict(local.state_dict())
+    gx = torch.Generator(device=dev).manual_seed(50 + rank)
+    nq = st.shape[0]
+    xs = torch.randn(nq, L, Fm, device=dev, generator=gx)
+    hinge = Lmod.PairwiseHingeLoss()
+
+    def step(model):
+        for p_ in model.parameters():
+            p_.grad = None
+        (hinge(model(xs), yt, nt).sum() / B).backward()
+        return torch.cat([p_.grad.reshape(-1) for p_ in model.parameters()])
+    ref_g = step(local).clone()
+    dist.all_reduce(ref_g)
+    got_g = step(shared).clone()
+    mlp_ok = bool(torch.equal(got_g, ref_g))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(shared)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph4 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph4):
+        cap_g = step(shared)
+    for _ in range(3):
+        graph4.replay()
+    torch.cuda.synchronize()
+    mlp_ok = mlp_ok and bool(torch.equal(cap_g, ref_g))
+    # wide rows: gradient longer than one mailbox piece (unfused vector exchange after the reduction)
+    wide_l = MLPRanker(1400).to(dev)
+    wide_s = MLPRanker(1400, exchange=ex).to(dev)
+    wide_s.load_state_dict(wide_l.state_dict())
+    xw = torch.randn(64, 16, 1400, device=dev, generator=gx)
+    gw = torch.randn(64, 16, 1, device=dev, generator=gx)
+    wide_l(xw).backward(gw)
+    wide_s(xw).backward(gw)
+    rw = torch.cat([p_.grad.reshape(-1) for p_ in wide_l.parameters()])
+    dist.all_reduce(rw)
+    mlp_ok = mlp_ok and bool(torch.equal(torch.cat([p_.grad.reshape(-1) for p_ in wide_s.parameters()]), rw))
     p2p_ok = p2p_ok and not ex.timed_out()
     lo, hi = shard_bounds(B, rank, world)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), mean=mean.item(), grad=st.grad.cpu().numpy(),
              gmean=gmean.item(), ggrad=st2.grad.cpu().numpy(), lo=lo, hi=hi, gm=gm.item(),
-             p2p_ok=p2p_ok, pmean=pmean.item(), pgrad=st3.grad.cpu().numpy())
+             p2p_ok=p2p_ok, pmean=pmean.item(), pgrad=st3.grad.cpu().numpy(), vec_ok=vec_ok, mlp_ok=mlp_ok)
     dist.barrier()
     torch.cuda.synchronize()
 
@@ -341,6 +396,8 @@ def test_sharded_mean_loss_two_ranks_nccl(tmp_path):
         assert (np.abs(d["grad"] - ref) <= 1e-5 * gmax + 1e-9).all()
         assert np.allclose(d["grad"], d["ggrad"], rtol=1e-6, atol=0)
         assert bool(d["p2p_ok"]), "peer-memory all-reduce disagrees with NCCL (or timed out)"
+        assert bool(d["vec_ok"]), "peer-memory vector all-reduce disagrees with NCCL"
+        assert bool(d["mlp_ok"]), "MLPRanker(exchange=...) gradients differ from local gradients + NCCL all-reduce"
         assert float(d["pmean"]) == pytest.approx(loss.mean(), rel=1e-5)
         assert np.array_equal(d["pgrad"], d["ggrad"])
 

@@ -448,3 +448,58 @@ def test_mlp_ranker_rejects_feature_gradients_and_captures():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, want)
+
+
+@gpu
+def test_vector_exchange_and_fused_backward_on_one_rank():
+    """world = 1 (the rank is its own peer): the vector all-reduce is the identity, at any length and under graph
+    replay; ltr_mlp_backward_allreduce returns ltr_mlp_backward's bits.  (Two ranks: tests/test_gpu_round2.py.)"""
+    import ctypes
+    lib = _lib.lib()
+    h = ctypes.c_void_p()
+    blob = (ctypes.c_ubyte * 64)()
+    _lib.check(lib.ltr_p2p_create(0, 1, ctypes.byref(h), blob))
+    try:
+        _lib.check(lib.ltr_p2p_connect(h, blob))
+        st = torch.cuda.current_stream().cuda_stream
+        for k in (1, 77, 65536, 65537, 300001):
+            v = torch.randn(k, device="cuda")
+            ref = v.clone()
+            for _ in range(3):
+                _lib.check(lib.ltr_p2p_allreduce_vec(h, v.data_ptr(), k, st))
+            assert torch.equal(v, ref)
+        v = torch.randn(5000, device="cuda")
+        ref = v.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _lib.check(lib.ltr_p2p_allreduce_vec(h, v.data_ptr(), 5000, side.cuda_stream))
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            _lib.check(lib.ltr_p2p_allreduce_vec(h, v.data_ptr(), 5000, torch.cuda.current_stream().cuda_stream))
+        for _ in range(4):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(v, ref) and lib.ltr_p2p_error(h) == 0
+        for (rows, F, H1, H2) in [(5000, 136, 50, 10), (700, 700, 50, 10), (300, 1400, 50, 10), (0, 136, 50, 10)]:
+            p = _params(F, H1, H2, 5, "cuda")
+            x = torch.randn(max(rows, 1), F, device="cuda")[:rows]
+            ds = torch.randn(rows, device="cuda")
+            hz = _kept_activations(lib, x, p) if rows else None
+            rc, ref = _call_backward(lib, x, p, ds, hz)
+            assert rc == 0
+            n = lib.ltr_mlp_grad_len(F, H1, H2)
+            out = torch.full((n,), float("nan"), device="cuda")
+            wsb = lib.ltr_mlp_workspace_bytes(F, H1, H2)
+            ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+            rc = lib.ltr_mlp_backward_allreduce(x.data_ptr(), rows, F, p[0].data_ptr(), p[1].data_ptr(), H1,
+                                                p[2].data_ptr(), p[3].data_ptr(), H2, p[4].data_ptr(), p[5].data_ptr(),
+                                                None if hz is None else hz.data_ptr(), ds.data_ptr(), out.data_ptr(),
+                                                ws.data_ptr(), wsb, h, st)
+            assert rc == 0
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)
+        assert lib.ltr_p2p_error(h) == 0
+    finally:
+        lib.ltr_p2p_destroy(h)
