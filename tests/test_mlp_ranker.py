@@ -141,7 +141,8 @@ SHAPES = [(128, 136, 50, 10), (1000, 136, 50, 10), (40000, 136, 50, 10), (5000, 
           (4000, 136, 40, 10), (4000, 64, 50, 4)]
 # rows wider than 288 features: W1 streams through the stage ring beside the tile (forward), the dW1 columns come
 # from several launches (backward from kept activations)
-WIDE_SHAPES = [(3000, 700, 50, 10), (1000, 320, 50, 10), (2100, 1024, 20, 5), (700, 292, 32, 8)]
+WIDE_SHAPES = [(3000, 700, 50, 10), (1000, 320, 50, 10), (2100, 1024, 20, 5), (700, 292, 32, 8), (1, 700, 50, 10),
+               (129, 320, 32, 8), (260, 4096, 50, 10)]
 KEPT_SHAPES = ([s_ for s_ in SHAPES if s_[2] <= 50 and s_[3] <= 10] + [(3000, 220, 50, 10)]
                + WIDE_SHAPES)
 
