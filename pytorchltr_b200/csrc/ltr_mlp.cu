@@ -222,7 +222,9 @@ int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1
     g.w1_bytes = 0;
   } else {
     const int stages = static_cast<int>((budget - g.w1_bytes) / g.stage_bytes);
-    g.stages = stages > 4 ? 4 : stages;
+    int cap = 8;                                        // barriers of MlpSmallParams
+    if (const char* v = getenv("LTR_MLP_STAGES")) cap = atoi(v) >= 1 && atoi(v) <= 8 ? atoi(v) : cap;
+    g.stages = stages > cap ? cap : stages;
   }
   rc = mlp_make_maps(&m, g, features, rows, w1, H1);
   if (rc != LTR_OK) return rc;

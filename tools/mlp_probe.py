@@ -180,6 +180,11 @@ def main():
         run_bwd(lib, *args, ds, hz=hz)                # backward from the kept activations (+ reduce)
         run_bwd(lib, *args, ds)                       # backward recomputing layer 1 (+ reduce)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "prof_narrow":      # MQ2007's width (46 -> 48): not HBM-bound, what is it?
+        rows = 8192 * 200
+        args = make(rows, 48, 50, 10, exact=False)
+        run_fwd(lib, *args)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "prof_wide":        # Yahoo's width (699 -> 700), 383k documents
         rows = 2995 * 128
         args = make(rows, 700, 50, 10, exact=False)
