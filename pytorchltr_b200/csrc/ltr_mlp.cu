@@ -222,7 +222,7 @@ int ltr_mlp_scores(const float* features, long long rows, int F, const float* w1
     g.w1_bytes = 0;
   } else {
     const int stages = static_cast<int>((budget - g.w1_bytes) / g.stage_bytes);
-    int cap = 8;                                        // barriers of MlpSmallParams
+    int cap = 4;                                        // (8 barriers exist; deeper rings measured no faster)
     if (const char* v = getenv("LTR_MLP_STAGES")) cap = atoi(v) >= 1 && atoi(v) <= 8 ? atoi(v) : cap;
     g.stages = stages > cap ? cap : stages;
   }
