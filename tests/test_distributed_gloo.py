@@ -92,3 +92,28 @@ def test_sharded_mean_loss_matches_single_process(tmp_path):
         assert d["grad"] == pytest.approx(grad[lo:hi] / B, rel=1e-12, abs=1e-15)
         seen += hi - lo
     assert seen == B
+
+
+def test_peer_exchange_rejects_what_it_cannot_carry():
+    """Host-side argument checks of the peer-memory exchange (no GPU, no process group): CPU tensors, wrong dtypes
+    and empty vectors never reach the library; the exchange cannot be built without a process group."""
+    from pytorchltr_b200.distributed import PeerExchange, PeerScalarExchange
+    assert PeerExchange is PeerScalarExchange
+    ex = object.__new__(PeerScalarExchange)
+    for bad in (torch.zeros(8), torch.zeros(0), torch.zeros(8, dtype=torch.float64)):
+        with pytest.raises(ValueError):
+            ex.all_reduce_vec_(bad)
+        with pytest.raises(ValueError):
+            ex.all_reduce_(bad)
+    if not (dist.is_available() and dist.is_initialized()):
+        with pytest.raises(RuntimeError):
+            PeerScalarExchange()
+
+
+def test_mlp_ranker_takes_an_exchange_and_keeps_the_documented_state_dict():
+    from pytorchltr_b200.fused import MLPRanker
+    m = MLPRanker(136, exchange=None)
+    assert m.exchange is None and sorted(m.state_dict()) == ["l1.bias", "l1.weight", "l2.bias", "l2.weight",
+                                                              "l3.bias", "l3.weight"]
+    marker = object()
+    assert MLPRanker(46, hidden=(20, 5), exchange=marker).exchange is marker
