@@ -160,3 +160,42 @@ def check(rc: int):
     if rc != 0:
         msg = lib().ltr_strerror(rc).decode()
         raise LtrError(f"libltr_sm100: {msg} (code {rc})")
+
+
+# ---- device / stream plumbing for the callers of the library ---------------------------------------------------------
+# torch.cuda.current_stream() builds a Stream object and torch.cuda.device() always switches twice: together ~20 us
+# per call on the host, which is most of what a small-batch step costs.  These two do the same with one raw query
+# each.
+def raw_stream(device) -> int:
+    """``cudaStream_t`` (as an int) of torch's current stream on ``device``."""
+    import torch
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    try:
+        return torch._C._cuda_getCurrentRawStream(idx)
+    except AttributeError:                                # older / newer torch without the raw query
+        return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """``with on_device(dev):`` -- ``dev`` is the current CUDA device inside the block; switches (and switches back)
+    only when it is not already."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = -1
+
+    def __enter__(self):
+        import torch
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False

@@ -107,7 +107,7 @@ def host_loss(scores: torch.Tensor, relevance: torch.Tensor, n: torch.Tensor, fa
         lib = _lib.lib()
         ws_bytes = lib.ltr_host_workspace_bytes(B, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.ltr_loss_host_ex(family, mode, s.data_ptr(), y.data_ptr(), y.element_size(), nn.data_ptr(),
                                       nn.element_size(), B, L, float(sigma), loss_h.data_ptr(), None,
                                       1 if want_grad else 0, ws.data_ptr(), ws_bytes, _stream(dev))
@@ -130,7 +130,7 @@ def host_scaled_grad(g_scalar: float, grad_d: torch.Tensor) -> torch.Tensor:
         return out
     dev = grad_d.device
     scratch = torch.empty_like(grad_d) if g_scalar != 1.0 else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = _lib.lib().ltr_scale_rows_host(float(g_scalar), grad_d.data_ptr(), out.data_ptr(), B, L,
                                             _ptr(scratch), _stream(dev))
         _lib.check(rc)
@@ -148,7 +148,7 @@ def to_host(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
 
 
 def _stream(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    return _lib.raw_stream(device)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -166,7 +166,7 @@ def launch_loss(family: int, mode: int, s: torch.Tensor, y: torch.Tensor, nn: to
     grad = torch.empty((B, L), dtype=torch.float32, device=dev) if want_grad else None
     ranking = torch.empty((B, L), dtype=torch.int64, device=dev) if want_ranking else None
     lib = _lib.lib()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         st = _stream(dev)
         if family != _lib.FAMILY_LISTNET:
             # scheduling workspace of the O(L^2) losses (longest queries first): scratch from the
@@ -212,7 +212,7 @@ def scale_rows(g: torch.Tensor, dscores: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(dscores)
     if B == 0:
         return out
-    with torch.cuda.device(dscores.device):
+    with _lib.on_device(dscores.device):
         rc = _lib.lib().ltr_scale_rows(g.data_ptr(), g_stride, dscores.data_ptr(), out.data_ptr(), B, L,
                                        _stream(dscores.device))
     _lib.check(rc)
@@ -311,7 +311,7 @@ def rank_metric(metric: int, scores, relevance, n, k: Optional[int], exp: bool):
     all_k = metric != _lib.METRIC_ARP and k is None
     out = torch.empty((B, L) if all_k else (B,), dtype=torch.float32, device=dev)
     if B > 0:
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = _lib.lib().ltr_rank_metrics(metric, s.data_ptr(), y.data_ptr(), y.element_size(),
                                              nn.data_ptr(), nn.element_size(), B, L,
                                              1 if metric == _lib.METRIC_ARP else kk,
@@ -328,7 +328,7 @@ def rank_by_score(scores, n):
     s, _, nn, B, L = normalise(scores, None, n, dev)
     out = torch.empty((B, L), dtype=torch.int64, device=dev)
     if B > 0:
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = _lib.lib().ltr_rank_by_score(s.data_ptr(), nn.data_ptr(), nn.element_size(), B, L,
                                               out.data_ptr(), _stream(dev))
         _lib.check(rc)

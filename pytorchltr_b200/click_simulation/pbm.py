@@ -38,12 +38,12 @@ def pbm_probabilities(rankings, ys, n, relevance_probs, cutoff: Optional[int] = 
     cp = torch.zeros((B, L), dtype=torch.float32, device=dev)
     pr = torch.zeros((B, L), dtype=torch.float32, device=dev)
     if B > 0:
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = _lib.lib().ltr_pbm_probabilities(rk.data_ptr(), y.data_ptr(), y.element_size(), nn_.data_ptr(),
                                                   nn_.element_size(), rp.data_ptr(), rp.numel(),
                                                   0 if cutoff is None else int(cutoff), float(eta), B, L,
                                                   cp.data_ptr(), pr.data_ptr(),
-                                                  torch.cuda.current_stream(dev).cuda_stream)
+                                                  _lib.raw_stream(dev))
         _lib.check(rc)
     return cp, pr
 

@@ -201,11 +201,11 @@ class DeviceRankingDataset:
             if sel is not None:
                 sel = sel.contiguous()
         lib = _lib.lib()
-        st = torch.cuda.current_stream(dev).cuda_stream
+        st = _lib.raw_stream(dev)
         sel_ptr, sel_ld = (None, 0) if sel is None else (sel.data_ptr(), sel.shape[1])
         if not sparse:
             feats = torch.empty((B, L, F), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 if sel is None:
                     rc = lib.ltr_collate(self.features.data_ptr(), self.relevance.data_ptr(), self.offsets.data_ptr(),
                                          idx.data_ptr(), B, L, F, feats.data_ptr(), rel.data_ptr(), n.data_ptr(),
@@ -233,7 +233,7 @@ class DeviceRankingDataset:
         nnz = int(out_ptr[-1])
         coo = torch.empty((3, nnz), dtype=torch.int64, device=dev)
         val = torch.empty(nnz, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.ltr_collate_sparse(self.indptr.data_ptr(), self.indices.data_ptr(), self.values.data_ptr(),
                                         self.relevance.data_ptr(), self.offsets.data_ptr(), idx.data_ptr(), sel_ptr,
                                         sel_ld, out_ptr.data_ptr(), B, L, nnz, coo.data_ptr(), val.data_ptr(),

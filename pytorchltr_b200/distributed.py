@@ -14,6 +14,8 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from pytorchltr_b200 import _lib
+
 
 def shard_bounds(num_queries: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous ``[lo, hi)`` block of queries owned by ``rank``; blocks differ by at most
@@ -97,9 +99,9 @@ class PeerScalarExchange:
         """In place: ``values`` (float32 CUDA, 1..4 elements) becomes the sum over all ranks."""
         if not (values.is_cuda and values.dtype == torch.float32 and values.is_contiguous() and 1 <= values.numel() <= 4):
             raise ValueError("values must be a contiguous float32 CUDA tensor with 1 to 4 elements")
-        with torch.cuda.device(values.device):
+        with _lib.on_device(values.device):
             self._check(self._lib.ltr_p2p_allreduce_sum(self._handle, values.data_ptr(), values.numel(),
-                                                        torch.cuda.current_stream(values.device).cuda_stream))
+                                                        _lib.raw_stream(values.device)))
         return values
 
     def all_reduce_vec_(self, values: torch.Tensor) -> torch.Tensor:
@@ -107,9 +109,9 @@ class PeerScalarExchange:
         (``ltr_p2p_allreduce_vec``: 65536 floats per launch, the same mailbox protocol)."""
         if not (values.is_cuda and values.dtype == torch.float32 and values.is_contiguous() and values.numel() >= 1):
             raise ValueError("values must be a non-empty contiguous float32 CUDA tensor")
-        with torch.cuda.device(values.device):
+        with _lib.on_device(values.device):
             self._check(self._lib.ltr_p2p_allreduce_vec(self._handle, values.data_ptr(), values.numel(),
-                                                        torch.cuda.current_stream(values.device).cuda_stream))
+                                                        _lib.raw_stream(values.device)))
         return values
 
     @property

@@ -57,8 +57,8 @@ class _LinearListNet(torch.autograd.Function):
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         dscores = torch.empty((B, L), dtype=torch.float32, device=dev)
         qgrad = torch.empty((B, F + 1), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            st = torch.cuda.current_stream(dev).cuda_stream
+        with _lib.on_device(dev):
+            st = _lib.raw_stream(dev)
             rc = lib.ltr_linear_listnet(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(),
                                         y.data_ptr(), y.element_size(), nn_.data_ptr(), nn_.element_size(),
                                         B, L, F, None, loss.data_ptr(), dscores.data_ptr(), qgrad.data_ptr(),
@@ -102,10 +102,10 @@ class _LinearListNet(torch.autograd.Function):
             gb = torch.empty(1, dtype=torch.float32, device=dev)
             ws_bytes = lib.ltr_linear_listnet_workspace_bytes(F)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 rc = lib.ltr_linear_listnet_backward(qgrad.data_ptr(), g.data_ptr(), g_stride, B, F, gw.data_ptr(),
                                                      gb.data_ptr(), ws.data_ptr(), ws_bytes,
-                                                     torch.cuda.current_stream(dev).cuda_stream)
+                                                     _lib.raw_stream(dev))
             _lib.check(rc)
         else:
             x, dscores = ctx.saved_tensors
@@ -217,10 +217,10 @@ class _MlpScores(torch.autograd.Function):
         pitch = lib.ltr_mlp_hz_pitch(H1, H2)
         if pitch and any(ctx.needs_input_grad[1:]):
             hz = torch.empty((rows, pitch), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.ltr_mlp_scores(x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5],
                                     scores.data_ptr(), None if hz is None else hz.data_ptr(),
-                                    torch.cuda.current_stream(dev).cuda_stream)
+                                    _lib.raw_stream(dev))
         if rc == _LTR_EUNSUPPORTED:
             _warn_fallback(f"features={F}, hidden=({H1}, {H2}) is outside the scorer kernel's limits")
             scores = _mlp_torch_forward(x2, *p)[0]
@@ -254,13 +254,13 @@ class _MlpScores(torch.autograd.Function):
         ex = ctx.exchange
 
         def call(hz_ptr):
-            st = torch.cuda.current_stream(dev).cuda_stream
+            st = _lib.raw_stream(dev)
             head = (x2.data_ptr(), rows, F, ptr[0], ptr[1], H1, ptr[2], ptr[3], H2, ptr[4], ptr[5], hz_ptr,
                     ds.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws_bytes)
             if ex is None:
                 return lib.ltr_mlp_backward(*head, st)
             return lib.ltr_mlp_backward_allreduce(*head, ex.handle, st)      # an unsupported shape exchanges nothing
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = call(None if hz is None else hz.data_ptr())
             if rc == _LTR_EUNSUPPORTED and hz is not None:      # no kept-activation kernel for this shape: recompute
                 rc = call(None)
