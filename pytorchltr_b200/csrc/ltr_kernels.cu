@@ -1267,7 +1267,6 @@ int ltr_rank_metrics(int metric, const float* scores, const void* rel, int rel_b
     if (rc != LTR_OK) return rc;
     int tma = rows_tma_ok(scores, rel, rel_bytes, L);
     if (const char* v = getenv("LTR_TMA")) tma = tma && strcmp(v, "0") != 0;
-    const long long want = (static_cast<long long>(B) + kMetricWarps - 1) / kMetricWarps;
 #define LTR_RANKM_LAUNCH(E, WPB)                                                                               \
   do {                                                                                                        \
     int per_sm = 0;                                                                                           \
