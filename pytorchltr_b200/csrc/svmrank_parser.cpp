@@ -3,10 +3,16 @@
 // Replaces the reference's single-threaded C parser pytorchltr/datasets/svmrank/parser/svmrank_parser.h
 // (:174-515, a table-driven DFA over 8 KB fread chunks) and its Cython wrapper svmrank_parser.pyx:19-59.
 // Same grammar, same values, same result layout (dense row-major matrix of width max_col + 1 - min_col,
-// int32 labels, int64 query ids), different machine: the file is read once into memory, cut into one
-// slice per thread at line boundaries, every thread parses its slice into private COO buffers with a
-// hand-written scanner (no per-byte table lookups), and the dense matrix is then filled in parallel
-// (float64 like the reference, or float32 -- what the GPU path consumes -- without a second copy).
+// int32 labels, int64 query ids), different machine: the file is mapped (the page cache's pages, nothing
+// copied), cut into one slice per thread at line boundaries, every thread
+// parses its slice into private COO buffers sized once from a count of the ':' in the slice, and the dense
+// matrix is then filled in parallel (float64 like the reference, or float32 -- what the GPU path consumes
+// -- without a second copy).  The scanner has two tiers: the common feature token
+//   ' ' digits ':' ['-'] digits ['.' digits] followed by ' ' or '\n'   (at most 8 digits per run)
+// is measured with two 16-byte SSE2 compares (where do the digits stop?) and converted with the 8-digit
+// SWAR multiply trick -- no data-dependent loop, so none of the ~3 branch mispredictions per token that
+// cost the byte-at-a-time loop ~200 cycles per value; every other token (exponents, several signs, long
+// runs, comments, '\r', errors) takes the byte-at-a-time path below, which alone decides what is an error.
 //
 // Grammar (reference DFA, :80-131): line := ' '* label ' '+ "qid:" digits (' '+ col ':' value)* ' '*
 // ['#' comment] '\n'; a line that starts with '#' is a comment; '\r' before '\n' is accepted after a
@@ -26,8 +32,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <emmintrin.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -35,14 +47,40 @@ namespace {
 
 enum : int { PARSE_OK = 0, PARSE_FILE_ERROR = 1, PARSE_FORMAT_ERROR = 2, PARSE_MEMORY_ERROR = 3 };
 
+// growable array without value-initialisation (the COO buffers are written once, front to back)
+template <typename T>
+struct Buf {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  Buf() = default;
+  Buf(const Buf&) = delete;
+  Buf& operator=(const Buf&) = delete;
+  Buf(Buf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  ~Buf() { free(p); }
+  void reserve(size_t c) {
+    if (c <= cap) return;
+    T* q = static_cast<T*>(realloc(p, c * sizeof(T)));
+    if (!q) throw std::bad_alloc();
+    p = q;
+    cap = c;
+  }
+  void push_back(T v) {
+    if (n == cap) reserve(cap ? 2 * cap : 1024);
+    p[n++] = v;
+  }
+  size_t size() const { return n; }
+  const T* data() const { return p; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Slice {
   const char* begin = nullptr;
   const char* end = nullptr;
-  std::vector<int32_t> ys;
-  std::vector<int64_t> qids;
-  std::vector<uint32_t> row;     // row inside the slice
-  std::vector<uint32_t> col;
-  std::vector<double> val;
+  Buf<int32_t> ys;
+  Buf<int64_t> qids;
+  Buf<uint64_t> row_start;   // index of the row's first value in col / val
+  Buf<uint32_t> col;
+  Buf<double> val;
   uint32_t min_col = 0xffffffffu, max_col = 0;
   bool any_col = false;
   int status = PARSE_OK;
@@ -62,11 +100,59 @@ struct Pow10Table {
 };
 const Pow10Table kPow10;
 
-// Parses the lines of one slice (the slice ends right after a '\n' or at end of file).
+// ---- fast tier -------------------------------------------------------------------------------------------
+constexpr size_t kTextPad = 64;   // readable bytes behind the text (zeros): 16-byte loads never leave the mapping
+
+// bit i set: byte i of the 16 bytes at p is not a decimal digit; bit 16 always set
+inline uint32_t nondigit_mask(const char* p) {
+  const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+  const __m128i lo = _mm_cmplt_epi8(v, _mm_set1_epi8('0'));
+  const __m128i hi = _mm_cmpgt_epi8(v, _mm_set1_epi8('9'));
+  return static_cast<uint32_t>(_mm_movemask_epi8(_mm_or_si128(lo, hi))) | 0x10000u;
+}
+
+// the decimal number in the len (1..8) digits at p
+inline uint64_t parse_digits(const char* p, int len) {
+  uint64_t v;
+  memcpy(&v, p, 8);
+  // first digit to the top byte position it would have in an 8-digit number, '0' in front
+  if (len < 8) v = (v << (64 - 8 * len)) | (0x3030303030303030ull >> (8 * len));
+  v = (v & 0x0F0F0F0F0F0F0F0Full) * 2561 >> 8;
+  v = (v & 0x00FF00FF00FF00FFull) * 6553601 >> 16;
+  return (v & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32;
+}
+
+const uint64_t kPow10Int[9] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull};
+
+inline size_t count_byte(const char* p, const char* end, char c) {
+  size_t n = 0;
+  const __m128i needle = _mm_set1_epi8(c);
+  for (; p + 16 <= end; p += 16)
+    n += static_cast<size_t>(__builtin_popcount(static_cast<unsigned>(
+        _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(p)), needle)))));
+  for (; p < end; ++p) n += *p == c;
+  return n;
+}
+
+// Parses the lines of one slice (the slice ends right after a '\n' or at end of file; kTextPad readable
+// bytes follow the text).
 void parse_slice(Slice* s) {
   const char* p = s->begin;
   const char* const end = s->end;
+  // LTR_SVMRANK_SLOW=1: byte-at-a-time tier only (tests compare the two tiers on hostile inputs)
+  const char* const slow_env = getenv("LTR_SVMRANK_SLOW");
+  const bool fast = !(slow_env && slow_env[0] == '1');
   try {
+    {
+      // every value and every "qid:" has one ':' -- an upper bound that is exact for files without comments
+      const size_t colons = count_byte(p, end, ':');
+      const size_t lines = count_byte(p, end, '\n') + 1;
+      s->ys.reserve(lines);
+      s->qids.reserve(lines);
+      s->row_start.reserve(lines);
+      s->col.reserve(colons + 1);
+      s->val.reserve(colons + 1);
+    }
     while (p < end) {
       while (p < end && *p == ' ') ++p;                       // START_Y: leading blanks
       if (p >= end) break;
@@ -84,11 +170,42 @@ void parse_slice(Slice* s) {
       p += 4;
       int64_t qid = 0;
       while (p < end && is_digit(*p)) qid = qid * 10 + (*p++ - '0');
-      const uint32_t row = static_cast<uint32_t>(s->ys.size());
+      s->row_start.push_back(s->val.size());
       s->ys.push_back(static_cast<int32_t>(y));
       s->qids.push_back(qid);
       // features
       for (;;) {
+        // fast tier: one blank, column, ':', optional '-', digits, optional '.' digits, then ' ' or '\n'
+        if (fast && *p == ' ' && p + 1 < end) {
+          const char* q = p + 1;
+          const int nc = __builtin_ctz(nondigit_mask(q));
+          if (nc >= 1 && nc <= 8 && q[nc] == ':') {
+            const char* t = q + nc + 1;
+            const int neg = *t == '-';
+            t += neg;
+            const uint32_t m = nondigit_mask(t);
+            const int n1 = __builtin_ctz(m);
+            const int dot = t[n1 <= 15 ? n1 : 15] == '.';
+            const int n2 = dot ? __builtin_ctz(m >> (n1 + 1)) : 0;            // (bit 16 stops the count)
+            const int stop = n1 + dot + n2;
+            if (n1 >= 1 && n1 <= 8 && n2 <= 8 && (!dot || n2 >= 1) && stop <= 15 && t + stop < end &&
+                (t[stop] == ' ' || t[stop] == '\n')) {
+              const uint64_t col = parse_digits(q, nc);
+              uint64_t mag = parse_digits(t, n1);
+              if (dot) mag = mag * kPow10Int[n2] + parse_digits(t + n1 + 1, n2);
+              const long sval = neg ? -static_cast<long>(mag) : static_cast<long>(mag);
+              const double fv = static_cast<double>(sval) * kPow10(-n2);        // reference :395-398
+              const uint32_t c32 = static_cast<uint32_t>(col);
+              s->col.push_back(c32);
+              s->val.push_back(fv);
+              if (c32 < s->min_col) s->min_col = c32;
+              if (c32 > s->max_col) s->max_col = c32;
+              s->any_col = true;
+              p = t + stop;
+              continue;
+            }
+          }
+        }
         bool blank = false;
         while (p < end && *p == ' ') { ++p; blank = true; }
         if (p >= end) break;
@@ -126,7 +243,6 @@ void parse_slice(Slice* s) {
         if (p < end && *p != ' ' && *p != '#' && *p != '\r' && *p != '\n') { s->status = PARSE_FORMAT_ERROR; return; }
         double fv = static_cast<double>(sign * val);
         fv = fv * kPow10(expval * expsign - decplaces);                             // reference :395-398
-        s->row.push_back(row);
         s->col.push_back(static_cast<uint32_t>(col));
         s->val.push_back(fv);
         const uint32_t c32 = static_cast<uint32_t>(col);
@@ -147,7 +263,13 @@ extern "C" {
 struct ltr_svmrank_result {
   std::vector<Slice> slices;
   std::vector<uint64_t> row_base;   // first global row of every slice
-  std::vector<char> text;
+  char* text = nullptr;             // the file (mapped), at least kTextPad readable zero bytes behind it
+  size_t text_bytes = 0, map_bytes = 0;
+  void unmap() {
+    if (text) munmap(text, map_bytes);
+    text = nullptr;
+  }
+  ~ltr_svmrank_result() { unmap(); }
   uint64_t rows = 0, cols = 0;
   uint32_t min_col = 0;
 };
@@ -156,33 +278,54 @@ struct ltr_svmrank_result {
 int ltr_svmrank_parse(const char* path, int n_threads, ltr_svmrank_result** out) {
   if (!path || !out) return PARSE_FORMAT_ERROR;
   *out = nullptr;
-  FILE* fp = fopen(path, "rb");
-  if (!fp) return PARSE_FILE_ERROR;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return PARSE_FILE_ERROR;
   ltr_svmrank_result* r = nullptr;
   try {
     r = new ltr_svmrank_result();
-    if (fseek(fp, 0, SEEK_END) != 0) { fclose(fp); delete r; return PARSE_FILE_ERROR; }
-    const long size = ftell(fp);
-    if (size < 0 || fseek(fp, 0, SEEK_SET) != 0) { fclose(fp); delete r; return PARSE_FILE_ERROR; }
-    r->text.resize(static_cast<size_t>(size));
-    if (size > 0 && fread(r->text.data(), 1, static_cast<size_t>(size), fp) != static_cast<size_t>(size)) {
-      fclose(fp);
-      delete r;
-      return PARSE_FILE_ERROR;
-    }
-    fclose(fp);
-    fp = nullptr;
+    const off_t size = lseek(fd, 0, SEEK_END);
+    if (size < 0) { const int e = errno; close(fd); delete r; errno = e; return PARSE_FILE_ERROR; }
+    r->text_bytes = static_cast<size_t>(size);
     if (n_threads < 1) n_threads = static_cast<int>(std::thread::hardware_concurrency());
     if (n_threads < 1) n_threads = 1;
+    {
+      // The page cache's own pages, mapped read-only over an anonymous region one page longer than the file: the
+      // zero page behind the text keeps the scanner's 16-byte loads inside the mapping, and nothing is copied.
+      const size_t page = static_cast<size_t>(sysconf(_SC_PAGESIZE));
+      const size_t file_span = (r->text_bytes + page - 1) / page * page;
+      r->map_bytes = file_span + page;
+      void* region = mmap(nullptr, r->map_bytes, PROT_READ, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+      if (region == MAP_FAILED) { close(fd); delete r; return PARSE_MEMORY_ERROR; }
+      r->text = static_cast<char*>(region);
+      if (r->text_bytes > 0) {
+        void* m = mmap(region, r->text_bytes, PROT_READ, MAP_PRIVATE | MAP_FIXED, fd, 0);
+        if (m != MAP_FAILED) {
+          madvise(region, r->text_bytes, MADV_SEQUENTIAL);
+        } else {
+          // a file that cannot be mapped (some network / pseudo file systems): read it into the region instead
+          if (mprotect(region, r->map_bytes, PROT_READ | PROT_WRITE) != 0) {
+            const int e = errno; close(fd); delete r; errno = e; return PARSE_FILE_ERROR;
+          }
+          size_t off = 0;
+          while (off < r->text_bytes) {
+            const ssize_t got = pread(fd, r->text + off, r->text_bytes - off, static_cast<off_t>(off));
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) { const int e = got < 0 ? errno : EIO; close(fd); delete r; errno = e; return PARSE_FILE_ERROR; }
+            off += static_cast<size_t>(got);
+          }
+        }
+      }
+      close(fd);
+    }
     const size_t min_slice = 1u << 16;
-    size_t want = r->text.size() / min_slice + 1;
+    size_t want = r->text_bytes / min_slice + 1;
     if (want > static_cast<size_t>(n_threads)) want = static_cast<size_t>(n_threads);
-    const char* base = r->text.data();
-    const char* const end = base + r->text.size();
+    const char* base = r->text;
+    const char* const end = base + r->text_bytes;
     r->slices.resize(want);
     const char* cur = base;
     for (size_t i = 0; i < want; ++i) {
-      const char* stop = i + 1 == want ? end : base + (r->text.size() * (i + 1)) / want;
+      const char* stop = i + 1 == want ? end : base + (r->text_bytes * (i + 1)) / want;
       if (stop < cur) stop = cur;
       while (stop < end && stop > base && stop[-1] != '\n') ++stop;      // cut right after a newline
       r->slices[i].begin = cur;
@@ -216,9 +359,8 @@ int ltr_svmrank_parse(const char* path, int n_threads, ltr_svmrank_result** out)
     r->rows = rows;
     r->min_col = any ? min_col : 0;
     r->cols = any ? static_cast<uint64_t>(max_col) + 1 - min_col : 0;     // nr_cols - min_col, :478
-    std::vector<char>().swap(r->text);                                      // the text is no longer needed
+    r->unmap();                                                             // the text is no longer needed
   } catch (const std::bad_alloc&) {
-    if (fp) fclose(fp);
     delete r;
     return PARSE_MEMORY_ERROR;
   }
@@ -249,8 +391,12 @@ int fill_impl(const ltr_svmrank_result* r, T* xs, int32_t* ys, int64_t* qids, in
     if (xs) {
       const uint64_t cols = r->cols;
       memset(xs + base * cols, 0, s.ys.size() * cols * sizeof(T));
-      for (size_t k = 0; k < s.val.size(); ++k)       // later duplicates overwrite earlier ones, :481-483
-        xs[(base + s.row[k]) * cols + (s.col[k] - r->min_col)] = static_cast<T>(s.val[k]);
+      for (size_t row = 0; row < s.ys.size(); ++row) {
+        T* out = xs + (base + row) * cols;
+        const size_t k1 = row + 1 < s.ys.size() ? s.row_start[row + 1] : s.val.size();
+        for (size_t k = s.row_start[row]; k < k1; ++k)   // later duplicates overwrite earlier ones, :481-483
+          out[s.col[k] - r->min_col] = static_cast<T>(s.val[k]);
+      }
     }
   };
   if (n_threads == 1 || n <= 1) {
@@ -283,14 +429,13 @@ int ltr_svmrank_fill_csr(const ltr_svmrank_result* r, int64_t* indptr, int64_t* 
   for (size_t i = 0; i < r->slices.size(); ++i) {
     const Slice& s = r->slices[i];
     const uint64_t base = r->row_base[i];
-    size_t k = 0;
     for (size_t row = 0; row < s.ys.size(); ++row) {
       indptr[base + row] = static_cast<int64_t>(nnz);
-      while (k < s.val.size() && s.row[k] == row) {
+      const size_t k1 = row + 1 < s.ys.size() ? s.row_start[row + 1] : s.val.size();
+      for (size_t k = s.row_start[row]; k < k1; ++k) {
         if (indices) indices[nnz] = static_cast<int64_t>(s.col[k] - r->min_col);
         if (values) values[nnz] = static_cast<float>(s.val[k]);
         ++nnz;
-        ++k;
       }
     }
   }

@@ -90,3 +90,72 @@ def test_load_svmrank_to_device_dataset(tmp_path):
     filt = load_svmrank(path, filter_queries=True)
     keep = [i for i in range(len(unique)) if ys[offsets[i]:offsets[i + 1]].sum() > 0]
     assert len(filt) == len(keep) and np.array_equal(filt.qids.numpy(), unique[keep])
+
+
+def _both_tiers(path, threads):
+    """(fast-tier result or exception type, slow-tier result or exception type)"""
+    out = []
+    for slow in ("0", "1"):
+        os.environ["LTR_SVMRANK_SLOW"] = slow
+        try:
+            out.append(parse_svmrank_file(path, n_threads=threads))
+        except Exception as e:  # noqa: BLE001
+            out.append(type(e))
+        finally:
+            os.environ.pop("LTR_SVMRANK_SLOW", None)
+    return out
+
+
+def _same(a, b):
+    if isinstance(a, type) or isinstance(b, type):
+        return a is b
+    return all(x.shape == y.shape and x.dtype == y.dtype and np.array_equal(x.view(np.uint8), y.view(np.uint8))
+               for x, y in zip(a, b))
+
+
+HOSTILE_TOKENS = ["1:0", "2:7", "3:-4.25", "4:--3.5", "5:12345678", "6:123456789", "7:0.12345678", "8:0.123456789",
+                  "9:1.5e3", "10:2.5E-2", "11:3.25e+1", "12:00012.5000", "13:99999999.99999999", "14:-0", "15:-0.0",
+                  "99999:1", "16:1234567.12345678", "18:4.5e-", "19:1.0e+"]   # (column ids stay small: dense output)
+BROKEN_TOKENS = ["17:3.e", "20:", "21:.", "22:1.", "23:a", "24:1x", "25:1e5", ":5", "26 :5", "27:-", "28:1..2", "29:1.2.3", "x:1"]
+
+
+def _line(rng, tokens, y=None, qid=None):
+    y = rng.integers(0, 5) if y is None else y
+    qid = rng.integers(1, 50) if qid is None else qid
+    sep = lambda: " " * int(rng.choice([1, 1, 1, 2, 3]))  # noqa: E731
+    return f"{y}{sep()}qid:{qid}" + "".join(sep() + t for t in tokens)
+
+
+def test_fast_and_slow_tiers_agree_on_hostile_files(tmp_path):
+    """The two scanner tiers (SSE2 / SWAR token path, byte-at-a-time path) give the same bits -- or the same error --
+    on files mixing every token form the grammar has, with comments, CRLF, blank runs, a missing final newline and,
+    in a second family of files, exactly one malformed token at a random place."""
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        lines = []
+        for _ in range(int(rng.integers(1, 40))):
+            k = int(rng.integers(0, 12))
+            toks = [str(t) for t in rng.choice(HOSTILE_TOKENS, size=k)]
+            toks += [f"{int(rng.integers(1, 300))}:{rng.random() * 10 ** int(rng.integers(-3, 6)):.{int(rng.integers(1, 9))}g}"
+                     for _ in range(int(rng.integers(0, 20)))]
+            toks = [t for t in toks if "e" not in t.split(":")[1] or "." in t.split(":")[1]]   # grammar: exponent needs a fraction
+            rng.shuffle(toks)
+            line = _line(rng, toks)
+            r = rng.random()
+            if r < 0.1:
+                line += " # a comment with 5:6 in it"
+            elif r < 0.2:
+                line += "\r"
+            elif r < 0.25:
+                line = "# whole-line comment 1:2"
+            lines.append(line)
+        if trial % 2 == 1:                                  # one malformed token somewhere
+            i = int(rng.integers(0, len(lines)))
+            if not lines[i].startswith("#"):
+                lines[i] = lines[i].split(" #")[0].rstrip("\r") + " " + str(rng.choice(BROKEN_TOKENS))
+        text = "\n".join(lines) + ("\n" if rng.random() < 0.7 else "")
+        path = tmp_path / f"hostile{trial}.txt"
+        path.write_text(text)
+        for threads in (1, 3):
+            fast, slow = _both_tiers(str(path), threads)
+            assert _same(fast, slow), (trial, threads, text[:400])
