@@ -159,3 +159,32 @@ def test_fast_and_slow_tiers_agree_on_hostile_files(tmp_path):
         for threads in (1, 3):
             fast, slow = _both_tiers(str(path), threads)
             assert _same(fast, slow), (trial, threads, text[:400])
+
+
+def test_csr_export_matches_the_dense_matrix(tmp_path):
+    """ltr_svmrank_fill_csr (the sparse=True datasets) against the dense fill of the same parse: every stored value at
+    its row / column, rows without features, several slices."""
+    from pytorchltr_b200.datasets.svmrank import _Parsed
+    rng = np.random.default_rng(3)
+    lines = []
+    for i in range(5000):
+        cols = np.sort(rng.choice(np.arange(3, 60), size=int(rng.integers(0, 12)), replace=False))
+        lines.append(f"{int(rng.integers(0, 5))} qid:{i // 25 + 1} " + " ".join(f"{c}:{rng.random() + 0.01:.5g}" for c in cols) + " ")
+    path = tmp_path / "sparse.txt"
+    path.write_text("\n".join(lines) + "\n")
+    for threads in (1, 5):
+        with _Parsed(str(path), threads) as p:
+            xs = np.empty((p.rows, p.cols), dtype=np.float32)
+            ys = np.empty(p.rows, dtype=np.int32)
+            qids = np.empty(p.rows, dtype=np.int64)
+            assert p.h.ltr_svmrank_fill_f32(p.handle, xs.ctypes.data, ys.ctypes.data, qids.ctypes.data, threads) == 0
+            indptr = np.empty(p.rows + 1, dtype=np.int64)
+            indices = np.empty(p.nnz, dtype=np.int64)
+            values = np.empty(p.nnz, dtype=np.float32)
+            assert p.h.ltr_svmrank_fill_csr(p.handle, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data) == 0
+        assert p.rows == 5000 and indptr[0] == 0 and indptr[-1] == len(values) == int((xs != 0).sum())
+        dense = np.zeros_like(xs)
+        rows = np.repeat(np.arange(5000), np.diff(indptr))
+        dense[rows, indices] = values
+        assert np.array_equal(dense, xs)
+        assert (np.diff(qids) >= 0).all() and ys.min() >= 0
